@@ -1,0 +1,77 @@
+"""The oracle (oracle/farseg_oracle.py) is pinned two ways:
+  * against the committed fixtures produced from the REAL reference (tests/golden/make_golden.py);
+  * when /root/reference is present (build container only), bit-exact against the reference itself.
+"""
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle.farseg_oracle import (FarSegOracle, bce_loss_oracle, deterministic_fill, dice_loss_oracle,
+                                  synthetic_batch)
+
+CASES = ['r18_k5_2x64', 'r50_k15_1x64', 'r18_k1_2x64']
+
+
+def _run_oracle(case):
+    resnet, k, n, h, w, dec = case
+    m = deterministic_fill(FarSegOracle(resnet, k, dec), 0)
+    x, y = synthetic_batch(n, h, w, max(k, 2))
+    m.train()
+    if k == 1:
+        logit = m.logits(x)
+        losses = dict(bce_loss=bce_loss_oracle(logit, y), dice_loss=dice_loss_oracle(logit, y))
+    else:
+        logit = m.logits(x)
+        losses = dict(ce_loss=F.cross_entropy(logit, y.long(), ignore_index=255), dice_loss=dice_loss_oracle(logit, y))
+    sum(losses.values()).backward()
+    return m, x, y, logit, losses
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_oracle_matches_golden(name, golden_dir):
+    g = torch.load(os.path.join(golden_dir, name + '.pt'), weights_only=False)
+    torch.set_num_threads(8)
+    m, x, y, logit, losses = _run_oracle(g['case'])
+    for k, v in g['losses'].items():
+        assert abs(float(losses[k]) - v) <= 1e-6 * max(1, abs(v)), (k, float(losses[k]), v)
+    torch.testing.assert_close(logit.detach()[:, :, ::4, ::4], g['logit_slice'], rtol=1e-5, atol=1e-6)
+    named = dict(m.named_parameters())
+    assert set(named) == set(g['grad_norm'])
+    for k, v in g['grad_norm'].items():
+        got = float(named[k].grad.double().norm())
+        assert abs(got - v) <= 1e-4 * max(v, 1e-6), (k, got, v)
+    for k, v in g['stem_bn_running'].items():
+        torch.testing.assert_close(m.state_dict()[k], v, rtol=1e-5, atol=1e-6)
+    m.eval()
+    with torch.no_grad():
+        prob = m(x)
+    mask = prob.argmax(dim=1).to(torch.uint8) if g['case'][1] > 1 else (prob > 0.5).to(torch.uint8)
+    # fp32 CPU oracle vs fp32 CPU reference: same ops in the same order -> identical masks
+    assert torch.equal(mask, g['eval_mask'])
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/ever'), reason='reference tree only exists in the build container')
+def test_oracle_bit_exact_vs_reference(golden_dir):
+    sys.path.insert(0, '/root/reference')
+    sys.path.insert(0, os.path.join(golden_dir, '_stubs'))
+    sys.path.insert(0, golden_dir)
+    import make_golden as mg
+    name = 'r18_k5_2x64'
+    resnet, k, n, h, w, dec = mg.CASES[name]
+    ref = deterministic_fill(mg.RefFarSeg(mg.ref_config(resnet, k, dec)), 0)
+    ora = deterministic_fill(FarSegOracle(resnet, k, dec), 0)
+    assert list(ref.state_dict().keys()) == list(ora.state_dict().keys())
+    x, y = synthetic_batch(n, h, w, k)
+    ref.train(), ora.train()
+    torch.set_num_threads(8)
+    lr, _ = ref(x, dict(cls=y))
+    lo = ora(x, dict(cls=y))
+    for kk in lr:
+        assert torch.equal(lr[kk], lo[kk]), kk
+    sum(lr.values()).backward()
+    sum(lo.values()).backward()
+    for (ka, pa), (kb, pb) in zip(ref.named_parameters(), ora.named_parameters()):
+        assert ka == kb and torch.equal(pa.grad, pb.grad), ka

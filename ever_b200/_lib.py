@@ -1,0 +1,37 @@
+"""ctypes binding of libevb200.so.  There is NO fallback: if the library is missing or a call fails the
+product path raises (the oracle under oracle/ is never used here)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libevb200.so')
+_lib = None
+
+
+class EvbError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EvbError('libevb200.so not built (%s): run `python -m ever_b200.build` / __graft_entry__.build(); '
+                           'there is no CPU or PyTorch fallback' % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.evb_last_cuda_error.restype = ctypes.c_char_p
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise EvbError('%s failed: rc=%d cuda=%s' % (what, rc, lib().evb_last_cuda_error().decode()))
+
+
+def ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,356 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), NHWC bf16 activations.
+//
+//   D[128 output pixels, NT output channels] = sum over taps, channel blocks of
+//        A[128 pixels, 64 ch]  (TMA 5-D box of the activation tensor, shifted by the tap, OOB -> 0 = padding)
+//      x B[NT out-ch, 64 ch]   (TMA 3-D box of the packed weights [tap][Cout][Cin])
+//
+// One CTA per (pixel tile, out-channel tile).  Warp 0 = TMA producer, warp 1 = tcgen05.mma issuer
+// (single elected thread) + TMEM allocator, warps 2-5 = epilogue (tcgen05.ld -> bias / residual add ->
+// bf16 -> global).  fp32 accumulators live in TMEM.  Forward, stride-1 dgrad (flipped taps on the
+// transposed weight pack), stride-2 forward (5-D "phase" view of the input) and stride-2 dgrad (one launch
+// per output phase) are all the same kernel with a different tap table.
+//
+// Replaces (reference): every nn.Conv2d forward / input-gradient on the FarSeg path, i.e.
+// ever/module/_resnets.py:21-29,139-150, ever/module/ops.py:53-55, ever/module/fpn.py:165,179,
+// ever/module/fs_relation.py:25-27,42,49 (cuDNN through ATen in the reference).
+#include "common.cuh"
+
+namespace evb {
+
+struct ConvTap {
+  int dw, dh;   // pixel offset of the A box for this tap
+  int coff;     // channel offset inside dim 0 of the A map (phase view: q * C)
+  int phase;    // coordinate on dim 4 of the A map
+  int slab;     // which [Cout][Cin] weight slab
+};
+constexpr int kMaxTaps = 9;
+
+struct IgemmParams {
+  int ntaps, kblocks;
+  ConvTap taps[kMaxTaps];
+  int bw, bh, bn;
+  int tiles_w, tiles_h, tiles_n, tiles_c;
+  __nv_bfloat16* out;
+  long long o_sn, o_sh, o_sw;
+  int No, Ho, Wo, Cout;
+  const float* bias;
+  const __nv_bfloat16* add;
+  long long a_sn, a_sh, a_sw;
+  int add_shift, add_mode;
+};
+
+template <int NT>
+struct IgemmCfg {
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = NT * 128;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (NT == 256) ? 4 : (NT == 128) ? 6 : 8;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(192, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ IgemmParams p) {
+  using Cfg = IgemmCfg<NT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE);
+  uint64_t* empty = full + Cfg::STAGES;
+  uint64_t* tfull = empty + Cfg::STAGES;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int t = blockIdx.x;
+  const int tc = t % p.tiles_c; t /= p.tiles_c;
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h;
+  const int tn = t / p.tiles_h;
+  const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, cout0 = tc * NT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tslot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t taddr = *tslot;
+  const int niter = p.ntaps * p.kblocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        const ConvTap tp = p.taps[tap];
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1, 0x100 + stage);
+          uint8_t* a_dst = smem + stage * Cfg::STAGE;
+          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE);
+          tma_load_5d(a_dst, &tmA, &full[stage], tp.coff + kb * 64, w0 + tp.dw, h0 + tp.dh, n0, tp.phase);
+          tma_load_3d(a_dst + Cfg::A_BYTES, &tmB, &full[stage], kb * 64, cout0, tp.slab);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, NT, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < niter; ++it) {
+        mbar_wait(&full[stage], phase, 0x200 + stage);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE);
+        const uint32_t b_base = a_base + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          umma_bf16(taddr, make_smem_desc(a_base + k * 32, 0, 1024), make_smem_desc(b_base + k * 32, 0, 1024), idesc,
+                    (it | k) != 0);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int wl = r % p.bw, hl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
+    const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
+    const bool valid = (n < p.No) && (h < p.Ho) && (w < p.Wo);
+    __nv_bfloat16* orow = p.out + n * p.o_sn + h * p.o_sh + w * p.o_sw;
+    const __nv_bfloat16* arow = nullptr;
+    if (p.add_mode) arow = p.add + n * p.a_sn + (h >> p.add_shift) * p.a_sh + (w >> p.add_shift) * p.a_sw;
+    mbar_wait(tfull, 0, 0x300);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < NT / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(taddr + (uint32_t(q * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int ch = cout0 + c * 32 + g * 8;
+          if (ch < p.Cout) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+            if (p.bias) {
+              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + ch);
+              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + ch + 4);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (p.add_mode) {
+              // reference adds two bf16 tensors: round the conv result first, then add, then round
+              float a[8];
+              unpack8(*reinterpret_cast<const bf16x8*>(arow + ch), a);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j]) + a[j];
+            }
+            *reinterpret_cast<bf16x8*>(orow + ch) = pack8(f);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(taddr, Cfg::TMEM_COLS);
+  }
+}
+
+static int pow2_le(int x, int cap) {
+  int r = 1;
+  while (r * 2 <= x && r * 2 <= cap) r *= 2;
+  return r;
+}
+
+struct ADesc {  // activation tensor [N,H,W,C] bf16 viewed for a conv of the given stride
+  const void* ptr;
+  int N, H, W, C;
+};
+
+static int make_a_map(CUtensorMap* m, const ADesc& a, int stride, int bw, int bh, int bn) {
+  uint64_t dims[5], strides[4];
+  uint32_t box[5] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn, 1};
+  if (stride == 1) {
+    dims[0] = a.C; dims[1] = a.W; dims[2] = a.H; dims[3] = a.N; dims[4] = 1;
+    strides[0] = (uint64_t)a.C * 2; strides[1] = (uint64_t)a.W * a.C * 2; strides[2] = (uint64_t)a.H * a.W * a.C * 2;
+    strides[3] = (uint64_t)a.N * a.H * a.W * a.C * 2;
+  } else {  // stride 2: (q*C+c, w', h', n, p) with w = 2w'+q, h = 2h'+p
+    if ((a.H & 1) || (a.W & 1)) return EVB_ERR_ARG;
+    dims[0] = 2 * (uint64_t)a.C; dims[1] = a.W / 2; dims[2] = a.H / 2; dims[3] = a.N; dims[4] = 2;
+    strides[0] = (uint64_t)2 * a.C * 2; strides[1] = (uint64_t)2 * a.W * a.C * 2;
+    strides[2] = (uint64_t)a.H * a.W * a.C * 2; strides[3] = (uint64_t)a.W * a.C * 2;
+  }
+  return evb_make_tmap_bf16(m, a.ptr, 5, dims, strides, box);
+}
+
+template <int NT>
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
+  using Cfg = IgemmCfg<NT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(igemm_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
+      return EVB_ERR_CUDA;
+    attr_set = true;
+  }
+  const int grid = p.tiles_c * p.tiles_w * p.tiles_h * p.tiles_n;
+  igemm_kernel<NT><<<grid, 192, Cfg::SMEM, st>>>(tmA, tmB, p);
+  return cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
+}
+
+// Core host entry: `a` is the tensor the A boxes are cut from, (To_n, To_h, To_w) the pixel grid the tiles
+// enumerate (output grid for fwd / stride-1 dgrad, per-phase grid for stride-2 dgrad).
+static int run_igemm(const ADesc& a, int a_stride, const void* wpk, int w_rows, int w_cin, int w_slabs,
+                     IgemmParams p, int force_nt, cudaStream_t st) {
+  if (a.C % 64 || w_cin % 64 || p.Cout % 8) return EVB_ERR_ARG;
+  p.bw = pow2_le(p.Wo, 128);
+  p.bh = pow2_le(p.Ho, 128 / p.bw);
+  p.bn = 128 / (p.bw * p.bh);
+  p.tiles_w = (p.Wo + p.bw - 1) / p.bw;
+  p.tiles_h = (p.Ho + p.bh - 1) / p.bh;
+  p.tiles_n = (p.No + p.bn - 1) / p.bn;
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  int nt = 64;
+  if (force_nt) {
+    nt = force_nt;
+  } else {
+    const int cands[3] = {256, 128, 64};
+    bool found = false;
+    for (int i = 0; i < 3 && !found; ++i) {
+      const int c = cands[i];
+      if (c > 64 && c > p.Cout) continue;
+      if ((long long)tiles_m * ((p.Cout + c - 1) / c) >= 118) { nt = c; found = true; }
+    }
+    if (!found) nt = 64;
+  }
+  p.tiles_c = (p.Cout + nt - 1) / nt;
+  CUtensorMap tmA, tmB;
+  int rc = make_a_map(&tmA, a, a_stride, p.bw, p.bh, p.bn);
+  if (rc) return rc;
+  uint64_t wd[3] = {(uint64_t)w_cin, (uint64_t)w_rows, (uint64_t)w_slabs};
+  uint64_t ws[2] = {(uint64_t)w_cin * 2, (uint64_t)w_cin * w_rows * 2};
+  uint32_t wb[3] = {64, (uint32_t)nt, 1};
+  rc = evb_make_tmap_bf16(&tmB, wpk, 3, wd, ws, wb);
+  if (rc) return rc;
+  switch (nt) {
+    case 256: return launch_igemm<256>(tmA, tmB, p, st);
+    case 128: return launch_igemm<128>(tmA, tmB, p, st);
+    case 64: return launch_igemm<64>(tmA, tmB, p, st);
+  }
+  return EVB_ERR_ARG;
+}
+
+}  // namespace evb
+
+using namespace evb;
+
+// y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w) (+bias) (+add).  ksize in {1,3}, pad = ksize/2, stride in {1,2}.
+// wpk: bf16 [ksize*ksize][w_rows][Cin], w_rows >= Cout.  add_mode: 0 none, 1 same-shape bf16 tensor,
+// 2 half-resolution tensor [N,Ho/2,Wo/2,Cout] sampled nearest (FPN top-down, ever/module/fpn.py:96-105).
+extern "C" int evb_conv2d_fwd(const void* x, int N, int H, int W, int Cin, const void* wpk, int w_rows, int ksize,
+                              int stride, void* y, int Cout, const float* bias, const void* add, int add_mode,
+                              int force_nt, void* stream) {
+  if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return EVB_ERR_ARG;
+  IgemmParams p{};
+  const int Ho = H / stride, Wo = W / stride;
+  p.kblocks = Cin / 64;
+  p.ntaps = ksize * ksize;
+  for (int r = 0; r < ksize; ++r)
+    for (int s = 0; s < ksize; ++s) {
+      ConvTap& t = p.taps[r * ksize + s];
+      const int oh = r - ksize / 2, ow = s - ksize / 2;  // input offset relative to stride*h
+      t.slab = r * ksize + s;
+      if (stride == 1) {
+        t.dh = oh; t.dw = ow; t.coff = 0; t.phase = 0;
+      } else {  // 2h+oh = 2(h+dh)+ph
+        const int ph = oh & 1, pw = ow & 1;
+        t.dh = (oh - ph) / 2; t.dw = (ow - pw) / 2; t.phase = ph; t.coff = pw * Cin;
+      }
+    }
+  p.out = (__nv_bfloat16*)y;
+  p.o_sw = Cout; p.o_sh = (long long)Wo * Cout; p.o_sn = (long long)Ho * Wo * Cout;
+  p.No = N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
+  p.bias = bias;
+  p.add_mode = add_mode ? 1 : 0;
+  if (add_mode) {
+    p.add = (const __nv_bfloat16*)add;
+    p.add_shift = add_mode == 2 ? 1 : 0;
+    const int Ha = Ho >> p.add_shift, Wa = Wo >> p.add_shift;
+    p.a_sw = Cout; p.a_sh = (long long)Wa * Cout; p.a_sn = (long long)Ha * Wa * Cout;
+  }
+  ADesc a{x, N, H, W, Cin};
+  return run_igemm(a, stride, wpk, w_rows, Cin, ksize * ksize, p, force_nt, (cudaStream_t)stream);
+}
+
+// dx[N,H,W,Cin] (+)= conv_transpose(dy[N,Ho,Wo,Cout], w).  wpk_t: bf16 [ksize*ksize][w_rows>=Cin][Cout]
+// (the transposed pack, same tap order r*ksize+s as the forward pack).  accumulate: add into the bf16 dx.
+extern "C" int evb_conv2d_dgrad(const void* dy, int N, int Ho, int Wo, int Cout, const void* wpk_t, int w_rows,
+                                int ksize, int stride, void* dx, int H, int W, int Cin, int accumulate, int force_nt,
+                                void* stream) {
+  if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return EVB_ERR_ARG;
+  if (H != Ho * stride || W != Wo * stride) return EVB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  ADesc a{dy, N, Ho, Wo, Cout};
+  IgemmParams base{};
+  base.kblocks = Cout / 64;
+  base.out = (__nv_bfloat16*)dx;
+  base.No = N; base.Cout = Cin;
+  base.bias = nullptr;
+  if (stride == 1) {
+    IgemmParams p = base;
+    p.ntaps = ksize * ksize;
+    for (int r = 0; r < ksize; ++r)
+      for (int s = 0; s < ksize; ++s) {
+        ConvTap& t = p.taps[r * ksize + s];
+        t.dh = -(r - ksize / 2); t.dw = -(s - ksize / 2); t.coff = 0; t.phase = 0; t.slab = r * ksize + s;
+      }
+    p.o_sw = Cin; p.o_sh = (long long)W * Cin; p.o_sn = (long long)H * W * Cin;
+    p.Ho = H; p.Wo = W;
+    if (accumulate) { p.add_mode = 1; p.add = (const __nv_bfloat16*)dx; p.a_sn = p.o_sn; p.a_sh = p.o_sh; p.a_sw = p.o_sw; }
+    return run_igemm(a, 1, wpk_t, w_rows, Cout, ksize * ksize, p, force_nt, st);
+  }
+  // stride 2: output phase (ph,pw): dx[2i+ph, 2j+pw] = sum over taps with (ph - (r-pad)) even of dy[i + dh, j + dw] w[r,s]
+  const int pad = ksize / 2;
+  if (ksize == 1 && !accumulate &&
+      cudaMemsetAsync(dx, 0, (size_t)N * H * W * Cin * 2, st) != cudaSuccess)
+    return EVB_ERR_CUDA;
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      IgemmParams p = base;
+      p.ntaps = 0;
+      for (int r = 0; r < ksize; ++r)
+        for (int s = 0; s < ksize; ++s) {
+          const int nh = ph - (r - pad), nw = pw - (s - pad);  // 2*h_out = 2i + nh
+          if ((nh & 1) || (nw & 1)) continue;
+          ConvTap& t = p.taps[p.ntaps++];
+          t.dh = nh / 2; t.dw = nw / 2; t.coff = 0; t.phase = 0; t.slab = r * ksize + s;
+        }
+      p.out = (__nv_bfloat16*)dx + ((long long)ph * W + pw) * Cin;
+      p.o_sw = 2LL * Cin; p.o_sh = 2LL * W * Cin; p.o_sn = (long long)H * W * Cin;
+      p.Ho = H / 2; p.Wo = W / 2;
+      if (accumulate) { p.add_mode = 1; p.add = p.out; p.a_sn = p.o_sn; p.a_sh = p.o_sh; p.a_sw = p.o_sw; }
+      if (p.ntaps == 0) continue;  // phase receives no gradient (1x1 stride 2): dx was zeroed above
+      int rc = run_igemm(a, 1, wpk_t, w_rows, Cout, ksize * ksize, p, force_nt, st);
+      if (rc) return rc;
+    }
+  return EVB_OK;
+}

@@ -1,0 +1,90 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution against torch's conv (the reference's arithmetic:
+nn.Conv2d -> cuDNN), fp32 math on the same bf16-rounded operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_conv(x_nhwc, w, stride, bias=None):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    y = F.conv2d(x, w.to(torch.bfloat16).float(), bias, stride=stride, padding=w.shape[-1] // 2)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def _close(got, ref, tol=1.2e-2):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= tol * scale, (err, scale)
+
+
+CASES = [
+    # n, h, w, cin, cout, k, stride
+    (2, 16, 16, 64, 64, 1, 1),
+    (2, 16, 16, 64, 64, 3, 1),
+    (1, 32, 32, 128, 256, 3, 1),
+    (2, 16, 16, 256, 128, 1, 1),
+    (2, 32, 32, 64, 128, 3, 2),
+    (2, 32, 32, 128, 256, 1, 2),
+    (1, 8, 8, 512, 512, 3, 1),
+    (3, 24, 40, 64, 192, 3, 1),   # ragged tiles
+    (1, 128, 128, 256, 256, 3, 1),
+]
+
+
+@pytest.mark.parametrize('case', CASES)
+@pytest.mark.parametrize('nt', [0, 64, 128, 256])
+def test_conv_fwd(case, nt):
+    from ever_b200 import ops
+    n, h, w, cin, cout, k, s = case
+    if nt > max(cout, 64):
+        pytest.skip('tile wider than Cout')
+    g = torch.Generator(device='cuda').manual_seed(1)
+    x = torch.randn(n, h, w, cin, device='cuda', generator=g).to(torch.bfloat16)
+    wt = torch.randn(cout, cin, k, k, device='cuda', generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    bias = torch.randn(cout, device='cuda', generator=g)
+    wf, _ = ops.pack_conv_weight_torch(wt)
+    y = ops.conv2d_fwd(x, wf, k, s, cout, bias=bias, force_nt=nt)
+    torch.cuda.synchronize()
+    _close(y, _ref_conv(x, wt, s, bias))
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_conv_dgrad(case):
+    from ever_b200 import ops
+    n, h, w, cin, cout, k, s = case
+    g = torch.Generator(device='cuda').manual_seed(2)
+    ho, wo = h // s, w // s
+    dy = torch.randn(n, ho, wo, cout, device='cuda', generator=g).to(torch.bfloat16)
+    wt = torch.randn(cout, cin, k, k, device='cuda', generator=g) * (2.0 / (cout * k * k)) ** 0.5
+    _, wb = ops.pack_conv_weight_torch(wt)
+    dx = ops.conv2d_dgrad(dy, wb, k, s, cin)
+    torch.cuda.synchronize()
+    torch.backends.cudnn.allow_tf32 = False
+    ref = torch.nn.grad.conv2d_input((n, cin, h, w), wt.to(torch.bfloat16).float(), dy.float().permute(0, 3, 1, 2),
+                                     stride=s, padding=k // 2).permute(0, 2, 3, 1)
+    _close(dx, ref)
+    # accumulate mode adds into an existing bf16 tensor
+    base = torch.randn(n, h, w, cin, device='cuda', generator=g).to(torch.bfloat16)
+    acc = base.clone()
+    ops.conv2d_dgrad(dy, wb, k, s, cin, out=acc, accumulate=True)
+    torch.cuda.synchronize()
+    _close(acc, ref + base.float(), tol=2e-2)
+
+
+def test_conv_fwd_fpn_add():
+    from ever_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(3)
+    x = torch.randn(2, 32, 32, 128, device='cuda', generator=g).to(torch.bfloat16)
+    top = torch.randn(2, 16, 16, 256, device='cuda', generator=g).to(torch.bfloat16)
+    wt = torch.randn(256, 128, 1, 1, device='cuda', generator=g) * 0.1
+    wf, _ = ops.pack_conv_weight_torch(wt)
+    y = ops.conv2d_fwd(x, wf, 1, 1, 256, add=top, add_mode=2)
+    torch.cuda.synchronize()
+    lat = _ref_conv(x, wt, 1).to(torch.bfloat16)
+    up = F.interpolate(top.float().permute(0, 3, 1, 2), scale_factor=2, mode='nearest').permute(0, 2, 3, 1).to(torch.bfloat16)
+    _close(y, (lat + up).float(), tol=1e-2)

@@ -40,3 +40,22 @@ def conv2d_dgrad(dy, wpk_t, ksize, stride, cin, out=None, accumulate=False, forc
                                  c_int(cin), c_int(1 if accumulate else 0), c_int(force_nt), stream()),
           'evb_conv2d_dgrad')
     return out
+
+
+def conv2d_wgrad(x, dy, ksize, stride, dw=None, accumulate=False, ws=None, force_nt=0, force_split=0):
+    n, h, w, cin = x.shape
+    cout = dy.shape[3]
+    need = lib().evb_conv2d_wgrad_workspace
+    need.restype = ctypes.c_longlong
+    nbytes = need(c_int(n), c_int(h // stride), c_int(w // stride), c_int(cin), c_int(cout), c_int(ksize),
+                  c_int(force_nt), c_int(force_split))
+    if ws is None or ws.numel() * ws.element_size() < nbytes:
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=x.device)
+    if dw is None:
+        assert not accumulate
+        dw = torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
+    check(lib().evb_conv2d_wgrad(ptr(x), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(dy), c_int(cout), c_int(ksize),
+                                 c_int(stride), ptr(dw), c_int(1 if accumulate else 0), ptr(ws),
+                                 ctypes.c_longlong(ws.numel() * ws.element_size()), c_int(force_nt),
+                                 c_int(force_split), stream()), 'evb_conv2d_wgrad')
+    return dw

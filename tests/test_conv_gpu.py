@@ -88,3 +88,24 @@ def test_conv_fwd_fpn_add():
     lat = _ref_conv(x, wt, 1).to(torch.bfloat16)
     up = F.interpolate(top.float().permute(0, 3, 1, 2), scale_factor=2, mode='nearest').permute(0, 2, 3, 1).to(torch.bfloat16)
     _close(y, (lat + up).float(), tol=1e-2)
+
+
+@pytest.mark.parametrize('case', CASES + [(8, 16, 16, 192, 64, 1, 1)])
+@pytest.mark.parametrize('split', [0, 1, 3])
+def test_conv_wgrad(case, split):
+    from ever_b200 import ops
+    n, h, w, cin, cout, k, s = case
+    g = torch.Generator(device='cuda').manual_seed(4)
+    ho, wo = h // s, w // s
+    x = torch.randn(n, h, w, cin, device='cuda', generator=g).to(torch.bfloat16)
+    dy = torch.randn(n, ho, wo, cout, device='cuda', generator=g).to(torch.bfloat16)
+    dw = ops.conv2d_wgrad(x, dy, k, s, force_split=split)
+    torch.cuda.synchronize()
+    torch.backends.cudnn.allow_tf32 = False
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, k, k), dy.float().permute(0, 3, 1, 2),
+                                      stride=s, padding=k // 2)
+    _close(dw, ref, tol=2e-3)
+    dw2 = dw.clone()
+    ops.conv2d_wgrad(x, dy, k, s, dw=dw2, accumulate=True, force_split=split)
+    torch.cuda.synchronize()
+    _close(dw2, 2 * ref, tol=2e-3)

@@ -20,6 +20,8 @@ def lib():
                            'there is no CPU or PyTorch fallback' % LIB_PATH)
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.evb_last_cuda_error.restype = ctypes.c_char_p
+        for fn in ('evb_conv2d_wgrad_workspace', 'evb_bn_workspace', 'evb_loss_workspace', 'evb_sgd_workspace'):
+            getattr(_lib, fn).restype = ctypes.c_longlong
     return _lib
 
 

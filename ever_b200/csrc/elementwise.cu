@@ -1,0 +1,732 @@
+// HBM-bound kernels around the convolutions: BatchNorm (batch statistics, apply(+residual)(+ReLU),
+// backward), max-pool, bilinear (align_corners) up-sampling fwd/bwd, 2x2 sum-pool (nearest-up backward),
+// decoder merge, global average pool, stem im2col, weight packing.  NHWC bf16, 16-byte vector accesses,
+// fp32 math, rounding points chosen to mirror the reference's bf16-autocast flow.
+//
+// Reference ops replaced: nn.BatchNorm2d (ever/module/_resnets.py:46-49,83-87; fpn.py:166; fs_relation.py:43,50),
+// nn.ReLU, residual add (_resnets.py:66-67,109-110), nn.MaxPool2d(3,2,1) (_resnets.py:153),
+// nn.UpsamplingBilinear2d via Bf16compatible (ever/module/ops.py:152-166, fpn.py:168,180), F.interpolate nearest
+// backward (fpn.py:100), sum()/len() merge (fpn.py:189), F.adaptive_avg_pool2d (fs_relation.py:177).
+#include "common.cuh"
+
+namespace evb {
+
+constexpr int kEwThreads = 256;
+
+static inline int ew_blocks(long long work, int per_block, int cap = 148 * 16) {
+  long long b = (work + per_block - 1) / per_block;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-channel sums over M rows of an [M, C] bf16 matrix.  MODE 0: sum x, sum x^2.
+// MODE 1 (BN backward): g = dy * mask, sums g and g * xhat, xhat = (x - mean) * rstd.
+//   mask_mode 0: none; 1: (ymask > 0) from a stored post-activation tensor; 2: (x*scale+shift > 0) recomputed.
+// Output: partial[block][2][C] fp32 (reduced in fixed order by the finalize kernels -> deterministic).
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kEwThreads)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+              const __nv_bfloat16* __restrict__ ymask, const float* __restrict__ mean, const float* __restrict__ rstd,
+              const float* __restrict__ scale, const float* __restrict__ shift, int mask_mode, long long M, int C,
+              float* __restrict__ partial) {
+  extern __shared__ float sm[];  // [rows_par][cg][16]
+  const int cg = C / 8;
+  const int rows_par = kEwThreads / cg > 0 ? kEwThreads / cg : 1;
+  const int t = threadIdx.x;
+  const int g = t % cg, rsub = t / cg;
+  const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+  if (rsub < rows_par) {
+    for (int gg = g; gg < cg; gg += kEwThreads) {  // cg <= 256 in practice: single trip
+      float mu[8], rs[8], sc[8], sh[8];
+      if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          mu[j] = mean[gg * 8 + j];
+          rs[j] = rstd[gg * 8 + j];
+          if (mask_mode == 2) { sc[j] = scale[gg * 8 + j]; sh[j] = shift[gg * 8 + j]; }
+        }
+      }
+      for (long long r = r0 + rsub; r < r1; r += rows_par) {
+        float xv[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(x + r * C + gg * 8), xv);
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s0[j] += xv[j]; s1[j] += xv[j] * xv[j]; }
+        } else {
+          float gv[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(dy + r * C + gg * 8), gv);
+          if (mask_mode == 1) {
+            float yv[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(ymask + r * C + gg * 8), yv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
+          } else if (mask_mode == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gv[j] = bf16_round(xv[j] * sc[j] + sh[j]) > 0.f ? gv[j] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s0[j] += gv[j]; s1[j] += gv[j] * (xv[j] - mu[j]) * rs[j]; }
+        }
+      }
+    }
+  }
+  float* my = sm + (size_t)t * 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { my[j] = s0[j]; my[8 + j] = s1[j]; }
+  __syncthreads();
+  // outputs: for channel c = gg*8+j : which in {0,1}
+  for (int o = t; o < 2 * C; o += kEwThreads) {
+    const int which = o / C, c = o % C;
+    const int gg = c / 8, j = c % 8;
+    float acc = 0.f;
+    for (int rs_ = 0; rs_ < rows_par; ++rs_) acc += sm[((size_t)rs_ * cg + gg) * 16 + which * 8 + j];
+    partial[((size_t)blockIdx.x * 2 + which) * C + c] = acc;
+  }
+}
+
+// BN training statistics finalize: mean, biased var -> rstd, folded scale/shift, running-stat update
+// (momentum, unbiased var), reference semantics SURVEY.md Appendix D.
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, long long M, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                                   float eps, float* __restrict__ mean, float* __restrict__ rstd,
+                                   float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += partial[((size_t)b * 2) * C + c];
+    ss += partial[((size_t)b * 2 + 1) * C + c];
+  }
+  const double mu = s / (double)M;
+  double var = ss / (double)M - mu * mu;
+  if (var < 0) var = 0;
+  const float rs = (float)(1.0 / sqrt(var + (double)eps));
+  mean[c] = (float)mu;
+  rstd[c] = rs;
+  const float a = gamma[c] * rs;
+  scale[c] = a;
+  shift[c] = beta[c] - (float)mu * a;
+  if (running_mean) {
+    const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  }
+}
+
+// eval / frozen BN: fold running stats
+__global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C,
+                               float* scale, float* shift, float* mean, float* rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float rs = rsqrtf(rv[c] + eps);
+  const float a = gamma[c] * rs;
+  scale[c] = a;
+  shift[c] = beta[c] - rm[c] * a;
+  if (mean) { mean[c] = rm[c]; rstd[c] = rs; }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int accumulate, float* __restrict__ fresh) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += partial[((size_t)b * 2) * C + c];
+    ss += partial[((size_t)b * 2 + 1) * C + c];
+  }
+  if (fresh) { fresh[c] = (float)s; fresh[C + c] = (float)ss; }  // this launch's own sums: [dbeta | dgamma]
+  if (dgamma) { if (accumulate) dgamma[c] += (float)ss; else dgamma[c] = (float)ss; }
+  if (dbeta) { if (accumulate) dbeta[c] += (float)s; else dbeta[c] = (float)s; }
+}
+
+// y = act( bf16(x*scale+shift) [+ res] )
+__global__ void __launch_bounds__(kEwThreads)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, long long nvec, int C, int relu) {
+  const int cg = C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cg) * 8;
+    float v[8];
+    unpack8(reinterpret_cast<const bf16x8*>(x)[i], v);
+    const float4 a0 = *reinterpret_cast<const float4*>(scale + c0), a1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(shift + c0), b1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = v[j] * a[j] + b[j];
+    if (res) {
+      float rv[8];
+      unpack8(reinterpret_cast<const bf16x8*>(res)[i], rv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = bf16_round(v[j]) + rv[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    reinterpret_cast<bf16x8*>(y)[i] = pack8(v);
+  }
+}
+
+// dx = scale * (g - (dbeta + xhat * dgamma) / M),  g = dy * mask ;  optional dres (+)= g
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                    const __nv_bfloat16* __restrict__ ymask, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, int mask_mode, int frozen,
+                    __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres, int dres_acc, long long nvec, int C,
+                    float inv_m) {
+  const int cg = C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cg) * 8;
+    float g[8], xv[8];
+    unpack8(reinterpret_cast<const bf16x8*>(dy)[i], g);
+    unpack8(reinterpret_cast<const bf16x8*>(x)[i], xv);
+    if (mask_mode == 1) {
+      float yv[8];
+      unpack8(reinterpret_cast<const bf16x8*>(ymask)[i], yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+    } else if (mask_mode == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = bf16_round(xv[j] * scale[c0 + j] + shift[c0 + j]) > 0.f ? g[j] : 0.f;
+    }
+    if (dres) {
+      float d[8];
+      if (dres_acc) {
+        unpack8(reinterpret_cast<const bf16x8*>(dres)[i], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] += g[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = g[j];
+      }
+      reinterpret_cast<bf16x8*>(dres)[i] = pack8(d);
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      if (frozen) {
+        o[j] = g[j] * scale[c];
+      } else {
+        const float xh = (xv[j] - mean[c]) * rstd[c];
+        o[j] = scale[c] * (g[j] - (dbeta[c] + xh * dgamma[c]) * inv_m);
+      }
+    }
+    reinterpret_cast<bf16x8*>(dx)[i] = pack8(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ max pool 3x3 s2 p1
+__global__ void __launch_bounds__(kEwThreads)
+maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx, int N,
+                   int H, int W, int C) {
+  const int cg = C / 8, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Ho * Wo * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long p = i / cg;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * ho - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int w = 2 * wo - 1 + s;
+        if (w < 0 || w >= W) continue;
+        float v[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(x + (((long long)n * H + h) * W + w) * C + g * 8), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (v[j] > best[j] || (best[j] == -INFINITY)) { best[j] = v[j]; bi[j] = r * 3 + s; }  // first max wins
+      }
+    }
+    reinterpret_cast<bf16x8*>(y)[i] = pack8(best);
+    uint2 packed;
+    packed.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    packed.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    reinterpret_cast<uint2*>(idx)[i] = packed;
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx, __nv_bfloat16* __restrict__ dx,
+                   int N, int H, int W, int C) {
+  const int cg = C / 8, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * H * W * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long p = i / cg;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H);
+    const int n = (int)(p / H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    // windows (ho, wo) containing (h, w): 2ho-1 <= h <= 2ho+1
+    for (int ho = (h) / 2; ho <= (h + 1) / 2; ++ho) {
+      if (ho < 0 || ho >= Ho) continue;
+      const int r = h - (2 * ho - 1);
+      for (int wo = (w) / 2; wo <= (w + 1) / 2; ++wo) {
+        if (wo >= Wo) continue;
+        const int s = w - (2 * wo - 1);
+        const int code = r * 3 + s;
+        const long long o = (((long long)n * Ho + ho) * Wo + wo) * cg + g;
+        const uint2 pk = reinterpret_cast<const uint2*>(idx)[o];
+        float gv[8];
+        unpack8(reinterpret_cast<const bf16x8*>(dy)[o], gv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int b = (j < 4 ? (pk.x >> (8 * j)) : (pk.y >> (8 * (j - 4)))) & 0xff;
+          if (b == code) acc[j] += gv[j];
+        }
+      }
+    }
+    reinterpret_cast<bf16x8*>(dx)[i] = pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ bilinear (align_corners)
+// y[N, f*h, f*w, C] = bf16( bilinear( act(x) ) ),  act(x) = bf16(relu(x*scale+shift)) when scale != null.
+// Input rows have stride ldx (>= C) elements per pixel, output ldy.
+__global__ void __launch_bounds__(kEwThreads)
+bilinear_up_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                   __nv_bfloat16* __restrict__ y, int N, int h, int w, int C, int ldx, int ldy, int f) {
+  const int cg = C / 8, Ho = h * f, Wo = w * f;
+  const float sy = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
+  const float sx = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
+  const long long total = (long long)N * Ho * Wo * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long p = i / cg;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    const float fy = sy * oy, fx = sx * ox;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly = fy - y0, lx = fx - x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    float v00[8], v01[8], v10[8], v11[8];
+    const __nv_bfloat16* base = x + (long long)n * h * w * ldx + g * 8;
+    unpack8(*reinterpret_cast<const bf16x8*>(base + ((long long)y0 * w + x0) * ldx), v00);
+    unpack8(*reinterpret_cast<const bf16x8*>(base + ((long long)y0 * w + x1) * ldx), v01);
+    unpack8(*reinterpret_cast<const bf16x8*>(base + ((long long)y1 * w + x0) * ldx), v10);
+    unpack8(*reinterpret_cast<const bf16x8*>(base + ((long long)y1 * w + x1) * ldx), v11);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (scale) {
+        const float a = scale[g * 8 + j], b = shift[g * 8 + j];
+        v00[j] = fmaxf(bf16_round(v00[j] * a + b), 0.f);
+        v01[j] = fmaxf(bf16_round(v01[j] * a + b), 0.f);
+        v10[j] = fmaxf(bf16_round(v10[j] * a + b), 0.f);
+        v11[j] = fmaxf(bf16_round(v11[j] * a + b), 0.f);
+      }
+      // same association as ATen upsample_bilinear2d: hy*(hx*v00 + lx*v01) + ly*(hx*v10 + lx*v11)
+      o[j] = hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]);
+    }
+    *reinterpret_cast<bf16x8*>(y + (((long long)n * Ho + oy) * Wo + ox) * ldy + g * 8) = pack8(o);
+  }
+}
+
+// Gather form of the transpose: dx[n,iy,ix,:] = sum over outputs that read (iy,ix) of weight * dy.
+__global__ void __launch_bounds__(kEwThreads)
+bilinear_up_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N, int h, int w, int C,
+                       int lddy, int lddx, int f) {
+  const int cg = C / 8, Ho = h * f, Wo = w * f;
+  const float sy = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
+  const float sx = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
+  const long long total = (long long)N * h * w * cg;
+  constexpr int kMaxCand = 12;  // f <= 4: at most 2f+2 candidates per axis
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long p = i / cg;
+    const int ix = (int)(p % w); p /= w;
+    const int iy = (int)(p % h);
+    const int n = (int)(p / h);
+    float wy[kMaxCand], wx[kMaxCand];
+    int cy0 = iy * f - f - 1, cx0 = ix * f - f - 1;
+    int ny = 0, nx = 0;
+    // weights along y for candidates cy0 .. cy0+2f+2
+    for (int k = 0; k < 2 * f + 3 && k < kMaxCand; ++k) {
+      const int oy = cy0 + k;
+      float wgt = 0.f;
+      if (oy >= 0 && oy < Ho) {
+        const float fy = sy * oy;
+        const int y0 = (int)fy;
+        const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+        const float ly = fy - y0;
+        if (y0 == iy) wgt += 1.f - ly;
+        if (y1 == iy) wgt += ly;
+      }
+      wy[k] = wgt;
+      ny = k + 1;
+    }
+    for (int k = 0; k < 2 * f + 3 && k < kMaxCand; ++k) {
+      const int ox = cx0 + k;
+      float wgt = 0.f;
+      if (ox >= 0 && ox < Wo) {
+        const float fx = sx * ox;
+        const int x0 = (int)fx;
+        const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+        const float lx = fx - x0;
+        if (x0 == ix) wgt += 1.f - lx;
+        if (x1 == ix) wgt += lx;
+      }
+      wx[k] = wgt;
+      nx = k + 1;
+    }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int a = 0; a < ny; ++a) {
+      if (wy[a] == 0.f) continue;
+      const int oy = cy0 + a;
+      for (int b = 0; b < nx; ++b) {
+        const float wgt = wy[a] * wx[b];
+        if (wgt == 0.f) continue;
+        const int ox = cx0 + b;
+        float gv[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(dy + (((long long)n * Ho + oy) * Wo + ox) * lddy + g * 8), gv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += wgt * gv[j];
+      }
+    }
+    *reinterpret_cast<bf16x8*>(dx + (((long long)n * h + iy) * w + ix) * lddx + g * 8) = pack8(acc);
+  }
+}
+
+// dcoarse[n,h,w,:] (+)= sum of the 2x2 block of dfine  (backward of nearest x2)
+__global__ void __launch_bounds__(kEwThreads)
+sumpool2_kernel(const __nv_bfloat16* __restrict__ dfine, __nv_bfloat16* __restrict__ dcoarse, int N, int h, int w, int C,
+                int accumulate) {
+  const int cg = C / 8;
+  const long long total = (long long)N * h * w * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long p = i / cg;
+    const int x = (int)(p % w); p /= w;
+    const int y = (int)(p % h);
+    const int n = (int)(p / h);
+    float acc[8];
+    if (accumulate) unpack8(reinterpret_cast<const bf16x8*>(dcoarse)[i], acc);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx_ = 0; dx_ < 2; ++dx_) {
+        float v[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(dfine + (((long long)n * 2 * h + 2 * y + dy) * 2 * w + 2 * x + dx_) * C + g * 8), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+    reinterpret_cast<bf16x8*>(dcoarse)[i] = pack8(acc);
+  }
+}
+
+// out = (((0+a)+b)+c)+d) / 4 with bf16 rounding after every add (python sum() of bf16 tensors, fpn.py:189)
+__global__ void __launch_bounds__(kEwThreads)
+merge4_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, const __nv_bfloat16* c, const __nv_bfloat16* d,
+              __nv_bfloat16* out, long long nvec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float va[8], vb[8], vc[8], vd[8];
+    unpack8(reinterpret_cast<const bf16x8*>(a)[i], va);
+    unpack8(reinterpret_cast<const bf16x8*>(b)[i], vb);
+    unpack8(reinterpret_cast<const bf16x8*>(c)[i], vc);
+    unpack8(reinterpret_cast<const bf16x8*>(d)[i], vd);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) va[j] = bf16_round(bf16_round(bf16_round(va[j] + vb[j]) + vc[j]) + vd[j]) * 0.25f;
+    reinterpret_cast<bf16x8*>(out)[i] = pack8(va);
+  }
+}
+
+// y = bf16(x * alpha)   (and optional add of a second tensor: y = bf16(x*alpha + z))
+__global__ void __launch_bounds__(kEwThreads)
+scale_add_kernel(const __nv_bfloat16* x, float alpha, const __nv_bfloat16* z, __nv_bfloat16* y, long long nvec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    unpack8(reinterpret_cast<const bf16x8*>(x)[i], v);
+    if (z) {
+      float u[8];
+      unpack8(reinterpret_cast<const bf16x8*>(z)[i], u);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = v[j] * alpha + u[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= alpha;
+    }
+    reinterpret_cast<bf16x8*>(y)[i] = pack8(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ global average pool
+// out[n][c] = bf16(mean over hw)   (fp32 storage holding bf16-rounded values)
+__global__ void gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int HW, int C) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  const __nv_bfloat16* p = x + (long long)n * HW * C + c;
+  for (int i = 0; i < HW; ++i) s += __bfloat162float(p[(long long)i * C]);
+  out[n * C + c] = bf16_round(s / (float)HW);
+}
+// dx[n,hw,c] += bf16(dscene[n][c] / HW)
+__global__ void gap_bwd_kernel(const float* __restrict__ dscene, __nv_bfloat16* __restrict__ dx, int HW, int C,
+                               long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int n = (int)(i / ((long long)HW * C));
+    const float g = bf16_round(dscene[n * C + c] / (float)HW);
+    dx[i] = __float2bfloat16_rn(__bfloat162float(dx[i]) + g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ stem im2col
+// x: NCHW fp32 [N,Cin,H,W] -> A: [N*Ho*Wo][KP] bf16, k = c*49 + r*7 + s (7x7, stride 2, pad 3), zero padded to KP.
+__global__ void __launch_bounds__(kEwThreads)
+stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int N, int Cin, int H, int W, int KP) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int kg = KP / 8;
+  const long long total = (long long)N * Ho * Wo * kg;
+  const int K = Cin * 49;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % kg);
+    long long p = i / kg;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float val = 0.f;
+      if (k < K) {
+        const int c = k / 49, rs = k % 49, r = rs / 7, s = rs % 7;
+        const int h = 2 * ho - 3 + r, w = 2 * wo - 3 + s;
+        if (h >= 0 && h < H && w >= 0 && w < W) val = x[(((long long)n * Cin + c) * H + h) * W + w];
+      }
+      v[j] = val;
+    }
+    reinterpret_cast<bf16x8*>(a)[i] = pack8(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// w: OIHW fp32 [Co][Ci][k][k] -> wf: bf16 [k*k][CoP][CiP]  and  wb: bf16 [k*k][CiPb][CoPb]  (zero padded)
+__global__ void pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, int kk, __nv_bfloat16* __restrict__ wf,
+                                   int CoP, int CiP, __nv_bfloat16* __restrict__ wb, int CiPb, int CoPb) {
+  const long long nf = (long long)kk * CoP * CiP;
+  const long long nb = wb ? (long long)kk * CiPb * CoPb : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nb; i += (long long)gridDim.x * blockDim.x) {
+    if (i < nf) {
+      const int ci = (int)(i % CiP);
+      const int co = (int)((i / CiP) % CoP);
+      const int t = (int)(i / ((long long)CiP * CoP));
+      wf[i] = __float2bfloat16_rn((co < Co && ci < Ci) ? w[((long long)co * Ci + ci) * kk + t] : 0.f);
+    } else {
+      const long long k = i - nf;
+      const int co = (int)(k % CoPb);
+      const int ci = (int)((k / CoPb) % CiPb);
+      const int t = (int)(k / ((long long)CoPb * CiPb));
+      wb[k] = __float2bfloat16_rn((co < Co && ci < Ci) ? w[((long long)co * Ci + ci) * kk + t] : 0.f);
+    }
+  }
+}
+
+// generic strided fp32 2-D copy: dst[r*ldd + c] (+)= src[r*lds + c]
+__global__ void copy2d_kernel(const float* src, int lds, float* dst, int ldd, int rows, int cols, int accumulate) {
+  const long long total = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const float v = src[(long long)r * lds + c];
+    float* d = dst + (long long)r * ldd + c;
+    *d = accumulate ? *d + v : v;
+  }
+}
+
+}  // namespace evb
+
+using namespace evb;
+#define ST ((cudaStream_t)stream)
+#define LAUNCH_OK() (cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA)
+
+static int colsum_blocks(long long M, int C) {
+  const int cg = C / 8;
+  const int rows_par = kEwThreads / cg > 0 ? kEwThreads / cg : 1;
+  long long b = (M + (long long)rows_par * 8 - 1) / ((long long)rows_par * 8);
+  if (b > 148 * 4) b = 148 * 4;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+extern "C" long long evb_bn_workspace(long long M, int C) { return ((long long)colsum_blocks(M, C) + 1) * 2 * C * sizeof(float); }
+
+// Training BN statistics of x[M,C] + folded scale/shift + running-stat update.
+extern "C" int evb_bn_stats(const void* x, long long M, int C, const float* gamma, const float* beta, float* running_mean,
+                            float* running_var, float momentum, float eps, float* mean, float* rstd, float* scale,
+                            float* shift, void* ws, void* stream) {
+  if (C % 8 || C > 2048) return EVB_ERR_ARG;
+  const int nb = colsum_blocks(M, C);
+  colsum_kernel<0><<<nb, kEwThreads, kEwThreads * 16 * sizeof(float), ST>>>(
+      (const __nv_bfloat16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, M, C, (float*)ws);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>((const float*)ws, nb, M, C, gamma, beta, running_mean, running_var,
+                                                      momentum, eps, mean, rstd, scale, shift);
+  return LAUNCH_OK();
+}
+
+extern "C" int evb_bn_fold(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C,
+                           float* scale, float* shift, float* mean, float* rstd, void* stream) {
+  bn_fold_kernel<<<(C + 127) / 128, 128, 0, ST>>>(gamma, beta, rm, rv, eps, C, scale, shift, mean, rstd);
+  return LAUNCH_OK();
+}
+
+// y = act(bf16(x*scale+shift) [+res])
+extern "C" int evb_bn_apply(const void* x, const float* scale, const float* shift, const void* res, void* y, long long M,
+                            int C, int relu, void* stream) {
+  if (C % 8) return EVB_ERR_ARG;
+  const long long nvec = M * C / 8;
+  bn_apply_kernel<<<ew_blocks(nvec, kEwThreads * 4), kEwThreads, 0, ST>>>((const __nv_bfloat16*)x, scale, shift,
+                                                                       (const __nv_bfloat16*)res, (__nv_bfloat16*)y, nvec,
+                                                                       C, relu);
+  return LAUNCH_OK();
+}
+
+// BN (+ReLU mask) backward.  mask_mode: 0 none, 1 from ymask>0, 2 recomputed from x*scale+shift>0.
+// frozen!=0: statistics were constants (eval / frozen BN): dx = g*scale, dgamma/dbeta still produced.
+extern "C" int evb_bn_bwd(const void* dy, const void* x, const void* ymask, const float* mean, const float* rstd,
+                          const float* scale, const float* shift, int mask_mode, int frozen, void* dx, void* dres,
+                          int dres_acc, float* dgamma, float* dbeta, int param_acc, long long M, int C, void* ws,
+                          void* stream) {
+  if (C % 8 || C > 2048) return EVB_ERR_ARG;
+  const int nb = colsum_blocks(M, C);
+  colsum_kernel<1><<<nb, kEwThreads, kEwThreads * 16 * sizeof(float), ST>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)ymask, mean, rstd, scale, shift, mask_mode,
+      M, C, (float*)ws);
+  float* fresh = (float*)ws + (size_t)nb * 2 * C;
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>((const float*)ws, nb, C, dgamma, dbeta, param_acc, fresh);
+  const long long nvec = M * C / 8;
+  bn_bwd_apply_kernel<<<ew_blocks(nvec, kEwThreads * 4), kEwThreads, 0, ST>>>(
+      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ymask, mean, rstd, scale, shift, fresh + C,
+      fresh, mask_mode, frozen, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, dres_acc, nvec, C, 1.0f / (float)M);
+  return LAUNCH_OK();
+}
+
+// per-channel sum of dy[M,C] (conv bias gradient): db[c] (+)= sum_rows dy
+extern "C" int evb_bias_grad(const void* dy, long long M, int C, float* db, float* scratch_sq, int accumulate, void* ws,
+                             void* stream) {
+  if (C % 8 || C > 2048) return EVB_ERR_ARG;
+  const int nb = colsum_blocks(M, C);
+  colsum_kernel<0><<<nb, kEwThreads, kEwThreads * 16 * sizeof(float), ST>>>(
+      (const __nv_bfloat16*)dy, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, M, C, (float*)ws);
+  (void)scratch_sq;
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>((const float*)ws, nb, C, nullptr, db, accumulate, nullptr);
+  return LAUNCH_OK();
+}
+
+extern "C" int evb_maxpool3x3s2_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, void* stream) {
+  if (C % 8 || (H & 1) || (W & 1)) return EVB_ERR_ARG;
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  maxpool_fwd_kernel<<<ew_blocks(total, kEwThreads * 2), kEwThreads, 0, ST>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y,
+                                                                           (uint8_t*)idx, N, H, W, C);
+  return LAUNCH_OK();
+}
+extern "C" int evb_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, void* stream) {
+  const long long total = (long long)N * H * W * (C / 8);
+  maxpool_bwd_kernel<<<ew_blocks(total, kEwThreads * 2), kEwThreads, 0, ST>>>((const __nv_bfloat16*)dy,
+                                                                           (const uint8_t*)idx, (__nv_bfloat16*)dx, N, H, W, C);
+  return LAUNCH_OK();
+}
+
+extern "C" int evb_bilinear_up(const void* x, const float* scale, const float* shift, void* y, int N, int h, int w, int C,
+                               int ldx, int ldy, int f, void* stream) {
+  if (C % 8 || ldx % 8 || ldy % 8 || f < 1 || f > 4) return EVB_ERR_ARG;
+  const long long total = (long long)N * h * f * w * f * (C / 8);
+  bilinear_up_kernel<<<ew_blocks(total, kEwThreads * 2), kEwThreads, 0, ST>>>((const __nv_bfloat16*)x, scale, shift,
+                                                                           (__nv_bfloat16*)y, N, h, w, C, ldx, ldy, f);
+  return LAUNCH_OK();
+}
+extern "C" int evb_bilinear_up_bwd(const void* dy, void* dx, int N, int h, int w, int C, int lddy, int lddx, int f,
+                                   void* stream) {
+  if (C % 8 || lddx % 8 || lddy % 8 || f < 1 || f > 4) return EVB_ERR_ARG;
+  const long long total = (long long)N * h * w * (C / 8);
+  bilinear_up_bwd_kernel<<<ew_blocks(total, kEwThreads), kEwThreads, 0, ST>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx,
+                                                                           N, h, w, C, lddy, lddx, f);
+  return LAUNCH_OK();
+}
+
+extern "C" int evb_sumpool2(const void* dfine, void* dcoarse, int N, int h, int w, int C, int accumulate, void* stream) {
+  const long long total = (long long)N * h * w * (C / 8);
+  sumpool2_kernel<<<ew_blocks(total, kEwThreads * 2), kEwThreads, 0, ST>>>((const __nv_bfloat16*)dfine,
+                                                                        (__nv_bfloat16*)dcoarse, N, h, w, C, accumulate);
+  return LAUNCH_OK();
+}
+
+extern "C" int evb_merge4(const void* a, const void* b, const void* c, const void* d, void* out, long long numel,
+                          void* stream) {
+  const long long nvec = numel / 8;
+  merge4_kernel<<<ew_blocks(nvec, kEwThreads * 4), kEwThreads, 0, ST>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
+                                                                     (const __nv_bfloat16*)c, (const __nv_bfloat16*)d,
+                                                                     (__nv_bfloat16*)out, nvec);
+  return LAUNCH_OK();
+}
+
+extern "C" int evb_scale_add(const void* x, float alpha, const void* z, void* y, long long numel, void* stream) {
+  const long long nvec = numel / 8;
+  scale_add_kernel<<<ew_blocks(nvec, kEwThreads * 4), kEwThreads, 0, ST>>>((const __nv_bfloat16*)x, alpha,
+                                                                        (const __nv_bfloat16*)z, (__nv_bfloat16*)y, nvec);
+  return LAUNCH_OK();
+}
+
+extern "C" int evb_gap_fwd(const void* x, float* out, int N, int HW, int C, void* stream) {
+  dim3 grid((C + 127) / 128, N);
+  gap_fwd_kernel<<<grid, 128, 0, ST>>>((const __nv_bfloat16*)x, out, HW, C);
+  return LAUNCH_OK();
+}
+extern "C" int evb_gap_bwd(const float* dscene, void* dx, int N, int HW, int C, void* stream) {
+  const long long total = (long long)N * HW * C;
+  gap_bwd_kernel<<<ew_blocks(total, kEwThreads * 4), kEwThreads, 0, ST>>>(dscene, (__nv_bfloat16*)dx, HW, C, total);
+  return LAUNCH_OK();
+}
+
+extern "C" int evb_stem_im2col(const float* x, void* a, int N, int Cin, int H, int W, int KP, void* stream) {
+  if (KP % 8 || KP < Cin * 49 || (H & 1) || (W & 1)) return EVB_ERR_ARG;
+  const long long total = (long long)N * (H / 2) * (W / 2) * (KP / 8);
+  stem_im2col_kernel<<<ew_blocks(total, kEwThreads), kEwThreads, 0, ST>>>(x, (__nv_bfloat16*)a, N, Cin, H, W, KP);
+  return LAUNCH_OK();
+}
+
+extern "C" int evb_pack_weight(const float* w, int Co, int Ci, int kk, void* wf, int CoP, int CiP, void* wb, int CiPb,
+                               int CoPb, void* stream) {
+  const long long total = (long long)kk * CoP * CiP + (wb ? (long long)kk * CiPb * CoPb : 0);
+  pack_weight_kernel<<<ew_blocks(total, kEwThreads * 4), kEwThreads, 0, ST>>>(w, Co, Ci, kk, (__nv_bfloat16*)wf, CoP, CiP,
+                                                                           (__nv_bfloat16*)wb, CiPb, CoPb);
+  return LAUNCH_OK();
+}
+
+extern "C" int evb_copy2d_f32(const float* src, int lds, float* dst, int ldd, int rows, int cols, int accumulate,
+                              void* stream) {
+  copy2d_kernel<<<ew_blocks((long long)rows * cols, kEwThreads), kEwThreads, 0, ST>>>(src, lds, dst, ldd, rows, cols,
+                                                                                   accumulate);
+  return LAUNCH_OK();
+}

@@ -1,0 +1,457 @@
+// FS-Relation head kernels, scene-embedding MLP (tiny GEMV-class linears), and the fused
+// softmax cross-entropy + Dice loss (forward statistics and logit gradient).
+//
+// Reference: FSRelation.forward ever/module/fs_relation.py:57-73; scene encoder :22-28; FarSegHead GAP :177;
+// F.cross_entropy(ignore_index=255) in the user model; dice_loss_with_logits ever/module/loss.py:54-75
+// (select :26-37, dice_coeff :40-51, all_reduce_sum :20-23).  Arithmetic restated in SURVEY.md Appendix D.
+#include "common.cuh"
+
+namespace evb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ FS-Relation
+// u1, u2: [M, C] bf16 = 1x1 conv outputs (+bias) of the content encoder / feature re-encoder, pre-BN.
+// cf = relu(bn1(u1)), pf = relu(bn2(u2)); r = sigmoid(sum_c bf16(sf_c * cf_c)); z = bf16(r * pf).
+// One warp per pixel; lane handles 8-channel groups lane, lane+32, ...
+__global__ void __launch_bounds__(256)
+relation_fwd_kernel(const __nv_bfloat16* __restrict__ u1, const __nv_bfloat16* __restrict__ u2,
+                    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ scale2,
+                    const float* __restrict__ shift2, const float* __restrict__ sf, __nv_bfloat16* __restrict__ z, float* __restrict__ rel, long long M,
+                    int HW, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long m = warp0; m < M; m += nwarps) {
+    const int n = (int)(m / HW);
+    const __nv_bfloat16* row = u1 + m * C;
+    const __nv_bfloat16* row2 = u2 + m * C;
+    float dot = 0.f;
+    for (int c0 = lane * 8; c0 < C; c0 += 256) {
+      float v[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(row + c0), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float cf = fmaxf(bf16_round(v[j] * scale[c0 + j] + shift[c0 + j]), 0.f);
+        dot += bf16_round(sf[n * C + c0 + j] * cf);
+      }
+    }
+    dot = warp_sum(dot);
+    const float r = 1.f / (1.f + __expf(-dot));
+    if (lane == 0) rel[m] = r;
+    for (int c0 = lane * 8; c0 < C; c0 += 256) {
+      float v[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(row2 + c0), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = r * fmaxf(bf16_round(v[j] * scale2[c0 + j] + shift2[c0 + j]), 0.f);
+      *reinterpret_cast<bf16x8*>(z + m * C + c0) = pack8(v);
+    }
+  }
+}
+
+// g[M,2C] = gradient w.r.t. the two BN outputs (ReLU masks applied); dsf[n][c] += sum_pixels dlogit * cf.
+__global__ void __launch_bounds__(256)
+relation_bwd_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ u1,
+                    const __nv_bfloat16* __restrict__ u2, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ scale2, const float* __restrict__ shift2, const float* __restrict__ sf,
+                    const float* __restrict__ rel, __nv_bfloat16* __restrict__ g1, __nv_bfloat16* __restrict__ g2,
+                    float* __restrict__ dsf, long long M, int HW, int C, int px_per_warp) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long m0 = warp * px_per_warp;
+  if (m0 >= M) return;
+  // C <= 1024: each lane owns up to 4 groups of 8 channels
+  float acc[4][8];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+  int cur_n = (int)(m0 / HW);
+  const long long m1 = m0 + px_per_warp < M ? m0 + px_per_warp : M;
+  for (long long m = m0; m < m1; ++m) {
+    const int n = (int)(m / HW);
+    if (n != cur_n) {  // flush per-image accumulators
+      for (int a = 0, c0 = lane * 8; c0 < C; c0 += 256, ++a)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(dsf + cur_n * C + c0 + j, acc[a][j]); acc[a][j] = 0.f; }
+      cur_n = n;
+    }
+    const __nv_bfloat16* row = u1 + m * C;
+    const __nv_bfloat16* row2 = u2 + m * C;
+    const float r = rel[m];
+    float dr = 0.f;
+    for (int c0 = lane * 8; c0 < C; c0 += 256) {
+      float v[8], d[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(row2 + c0), v);
+      unpack8(*reinterpret_cast<const bf16x8*>(dz + m * C + c0), d);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pf = fmaxf(bf16_round(v[j] * scale2[c0 + j] + shift2[c0 + j]), 0.f);
+        dr += d[j] * pf;
+        o[j] = pf > 0.f ? d[j] * r : 0.f;
+      }
+      *reinterpret_cast<bf16x8*>(g2 + m * C + c0) = pack8(o);
+    }
+    dr = warp_sum(dr);
+    const float dlogit = dr * r * (1.f - r);
+    for (int a = 0, c0 = lane * 8; c0 < C; c0 += 256, ++a) {
+      float v[8], o[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(row + c0), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float cf = fmaxf(bf16_round(v[j] * scale[c0 + j] + shift[c0 + j]), 0.f);
+        acc[a][j] += dlogit * cf;
+        o[j] = cf > 0.f ? dlogit * sf[n * C + c0 + j] : 0.f;
+      }
+      *reinterpret_cast<bf16x8*>(g1 + m * C + c0) = pack8(o);
+    }
+  }
+  for (int a = 0, c0 = lane * 8; c0 < C; c0 += 256, ++a)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(dsf + cur_n * C + c0 + j, acc[a][j]);
+}
+
+// ------------------------------------------------------------------------------------------------ tiny linears
+// y[n][o] = round_bf16( sum_i bf16(W[o][i]) * x[n][i] + b[o] ), optional ReLU.  One warp per (n, o).
+__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
+                                  float* __restrict__ y, int N, int I, int O, int relu) {
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= N * O) return;
+  const int n = wid / O, o = wid % O;
+  float s = 0.f;
+  for (int i = lane; i < I; i += 32) s += bf16_round(W[(long long)o * I + i]) * x[(long long)n * I + i];
+  s = warp_sum(s);
+  if (lane == 0) {
+    s = bf16_round(s + (b ? b[o] : 0.f));
+    y[wid] = relu ? fmaxf(s, 0.f) : s;
+  }
+}
+// dW[o][i] (+)= sum_n g[n][o] x[n][i];  db[o] (+)= sum_n g[n][o];  g = dy * (y>0 if relu)
+__global__ void linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
+                                    float* __restrict__ dW, float* __restrict__ db, int N, int I, int O, int relu,
+                                    int accumulate) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)O * I) return;
+  const int o = (int)(idx / I), i = (int)(idx % I);
+  float s = 0.f, sb = 0.f;
+  for (int n = 0; n < N; ++n) {
+    float g = dy[n * O + o];
+    if (relu && !(y[n * O + o] > 0.f)) g = 0.f;
+    g = bf16_round(g);
+    s += g * x[(long long)n * I + i];
+    sb += g;
+  }
+  dW[idx] = accumulate ? dW[idx] + s : s;
+  if (i == 0 && db) db[o] = accumulate ? db[o] + sb : sb;
+}
+// dx[n][i] (+)= sum_o g[n][o] bf16(W[o][i])
+__global__ void linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ W,
+                                    float* __restrict__ dx, int N, int I, int O, int relu, int accumulate) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * I) return;
+  const int n = (int)(idx / I), i = (int)(idx % I);
+  float s = 0.f;
+  for (int o = 0; o < O; ++o) {
+    float g = dy[n * O + o];
+    if (relu && !(y[n * O + o] > 0.f)) g = 0.f;
+    s += bf16_round(g) * bf16_round(W[(long long)o * I + i]);
+  }
+  s = bf16_round(s);
+  dx[idx] = accumulate ? dx[idx] + s : s;
+}
+
+// ------------------------------------------------------------------------------------------------ CE + Dice
+// logits: [P, LD] bf16 (NHWC, first K channels are classes), labels: int64 [P], 255 (ignore_index) = ignored.
+// stats layout (fp32): [0]=sum of -log p_t over valid, [1]=n_valid, [2..2+K)=I_c, [2+K..2+2K)=sum p_c, [2+2K..2+3K)=sum y_c
+constexpr int kMaxK = 32;
+
+template <int PASS>
+__global__ void __launch_bounds__(256)
+loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restrict__ labels, long long P, int K, int LD,
+            int ignore_index, float* __restrict__ partial, const float* __restrict__ coef,
+            __nv_bfloat16* __restrict__ dlogits) {
+  // PASS 0: statistics -> partial[block][2+3K];  PASS 1: dlogits from coef = {inv_nvalid, A_c[K], B_c[K]}
+  __shared__ float red[8][2 + 3 * kMaxK];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float acc[2 + 3 * kMaxK];
+  if (PASS == 0) {
+    for (int i = 0; i < 2 + 3 * K; ++i) acc[i] = 0.f;
+  }
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const long long t = labels[p];
+    const bool valid = t != ignore_index;
+    float z[kMaxK];
+    const __nv_bfloat16* row = logits + p * LD;
+    for (int c0 = 0; c0 < K; c0 += 8) {
+      float v[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(row + c0), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < K) z[c0 + j] = v[j];
+    }
+    float mx = z[0];
+    for (int c = 1; c < K; ++c) mx = fmaxf(mx, z[c]);
+    float se = 0.f;
+    for (int c = 0; c < K; ++c) se += expf(z[c] - mx);
+    const float lse = mx + logf(se);
+    if (PASS == 0) {
+      if (valid) {
+        acc[0] += lse - z[(int)t];
+        acc[1] += 1.f;
+        for (int c = 0; c < K; ++c) {
+          const float pc = expf(z[c] - lse);
+          acc[2 + K + c] += pc;
+          if (c == (int)t) { acc[2 + c] += pc; acc[2 + 2 * K + c] += 1.f; }
+        }
+      }
+    } else {
+      float d[kMaxK];
+      if (valid) {
+        const float inv_n = coef[0];
+        float pc[kMaxK], dot = 0.f;
+        for (int c = 0; c < K; ++c) {
+          pc[c] = expf(z[c] - lse);
+          const float gc = coef[1 + K + c] - (c == (int)t ? coef[1 + c] : 0.f);  // B_c - y_c * A_c
+          dot += pc[c] * gc;
+        }
+        for (int c = 0; c < K; ++c) {
+          const float gc = coef[1 + K + c] - (c == (int)t ? coef[1 + c] : 0.f);
+          const float dce = (pc[c] - (c == (int)t ? 1.f : 0.f)) * inv_n;
+          const float ddice = pc[c] * (gc - dot);
+          // the reference sums two bf16 gradient tensors (one per loss term)
+          d[c] = bf16_round(dce) + bf16_round(ddice);
+        }
+      } else {
+        for (int c = 0; c < K; ++c) d[c] = 0.f;
+      }
+      for (int c0 = 0; c0 < LD; c0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (c0 + j < K) ? d[c0 + j] : 0.f;
+        *reinterpret_cast<bf16x8*>(dlogits + p * LD + c0) = pack8(v);
+      }
+    }
+  }
+  if (PASS == 0) {
+    const int n = 2 + 3 * K;
+    for (int i = 0; i < n; ++i) {
+      const float v = warp_sum(acc[i]);
+      if (lane == 0) red[wid][i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += red[w][i];
+      partial[(long long)blockIdx.x * n + i] = s;
+    }
+  }
+}
+
+// stats[i] = sum_blocks partial (double accumulation, fixed order)
+__global__ void loss_reduce_kernel(const float* __restrict__ partial, int nblk, int n, float* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += partial[(long long)b * n + i];
+  stats[i] = (float)s;
+}
+
+// From (possibly all-reduced) statistics: losses[0]=ce, losses[1]=dice; coef = {ce_scale/n_valid, A_c, B_c}.
+// dice_stats may point to globally summed Dice statistics (I, sum p, sum y: 3K floats); dice_grad_scale
+// multiplies the Dice gradient (world size, see DESIGN.md: DDP averages what autograd's all-reduce summed).
+__global__ void loss_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ dice_stats, int K,
+                                     float smooth, float ce_weight, float dice_weight, float dice_grad_scale,
+                                     float* __restrict__ losses, float* __restrict__ coef) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float nvalid = stats[1];
+  losses[0] = nvalid > 0.f ? stats[0] / nvalid : 0.f;
+  coef[0] = nvalid > 0.f ? ce_weight / nvalid : 0.f;
+  float coeff_sum = 0.f;
+  for (int c = 0; c < K; ++c) {
+    const float I = dice_stats[c], Z = dice_stats[K + c] + dice_stats[2 * K + c] + smooth;
+    coeff_sum += (2.f * I + smooth) / Z;
+    coef[1 + c] = dice_weight * dice_grad_scale * 2.f / ((float)K * Z);
+    coef[1 + K + c] = dice_weight * dice_grad_scale * (2.f * I + smooth) / ((float)K * Z * Z);
+  }
+  losses[1] = 1.f - coeff_sum / (float)K;
+}
+
+// ------------------------------------------------------------------------------------------------ fused SGD
+// L2 norm partials of a flat fp32 gradient arena
+__global__ void __launch_bounds__(256) sqsum_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = g[i];
+    s += v * v;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void norm_finalize_kernel(const float* partial, int nblk, float* out /*[0]=norm,[1]=clip coef*/, float max_norm) {
+  if (threadIdx.x || blockIdx.x) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += partial[b];
+  const float norm = (float)sqrt(s);
+  out[0] = norm;
+  float coef = max_norm > 0.f ? max_norm / (norm + 1e-6f) : 1.f;
+  out[1] = coef < 1.f ? coef : 1.f;
+}
+// torch.optim.SGD (momentum, weight decay, dampening 0, no nesterov) + clip coefficient, in place
+__global__ void __launch_bounds__(256)
+sgd_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ mom, long long n, const float* __restrict__ lr_ptr,
+           float momentum, float wd, const float* __restrict__ clip, int first_step, int zero_grad) {
+  const float c = clip ? clip[1] : 1.f;
+  const float lr = *lr_ptr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float d = g[i] * c + wd * w[i];
+    float b = first_step ? d : momentum * mom[i] + d;
+    mom[i] = b;
+    w[i] -= lr * b;
+    if (zero_grad) g[i] = 0.f;
+  }
+}
+
+}  // namespace evb
+
+using namespace evb;
+#define ST ((cudaStream_t)stream)
+#define LAUNCH_OK() (cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA)
+
+extern "C" int evb_relation_fwd(const void* u1, const void* u2, const float* scale1, const float* shift1,
+                                const float* scale2, const float* shift2, const float* sf, void* z, float* rel, long long M,
+                                int HW, int C, void* stream) {
+  if (C % 8 || C > 1024) return EVB_ERR_ARG;
+  long long blocks = (M + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  relation_fwd_kernel<<<(int)blocks, 256, 0, ST>>>((const __nv_bfloat16*)u1, (const __nv_bfloat16*)u2, scale1, shift1, scale2,
+                                                   shift2, sf, (__nv_bfloat16*)z, rel, M, HW, C);
+  return LAUNCH_OK();
+}
+// dsf must be zeroed by the caller (it is accumulated with atomics).
+extern "C" int evb_relation_bwd(const void* dz, const void* u1, const void* u2, const float* scale1, const float* shift1,
+                                const float* scale2, const float* shift2, const float* sf, const float* rel, void* g1,
+                                void* g2, float* dsf, long long M, int HW, int C, void* stream) {
+  if (C % 8 || C > 1024) return EVB_ERR_ARG;
+  const int px_per_warp = 16;
+  const long long warps = (M + px_per_warp - 1) / px_per_warp;
+  const long long blocks = (warps + 7) / 8;
+  relation_bwd_kernel<<<(int)blocks, 256, 0, ST>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)u1, (const __nv_bfloat16*)u2,
+                                                   scale1, shift1, scale2, shift2, sf, rel, (__nv_bfloat16*)g1,
+                                                   (__nv_bfloat16*)g2, dsf, M, HW, C, px_per_warp);
+  return LAUNCH_OK();
+}
+
+extern "C" int evb_linear_fwd(const float* x, const float* W, const float* b, float* y, int N, int I, int O, int relu,
+                              void* stream) {
+  const int warps = N * O;
+  linear_fwd_kernel<<<(warps + 7) / 8, 256, 0, ST>>>(x, W, b, y, N, I, O, relu);
+  return LAUNCH_OK();
+}
+extern "C" int evb_linear_bwd(const float* dy, const float* y, const float* x, const float* W, float* dW, float* db,
+                              float* dx, int N, int I, int O, int relu, int acc_w, int acc_x, void* stream) {
+  linear_bwd_w_kernel<<<(int)(((long long)O * I + 255) / 256), 256, 0, ST>>>(dy, y, x, dW, db, N, I, O, relu, acc_w);
+  if (dx) linear_bwd_x_kernel<<<(int)(((long long)N * I + 255) / 256), 256, 0, ST>>>(dy, y, W, dx, N, I, O, relu, acc_x);
+  return LAUNCH_OK();
+}
+
+static int loss_blocks(long long P) {
+  long long b = (P + 256 * 4 - 1) / (256 * 4);
+  if (b > 148 * 4) b = 148 * 4;
+  return b < 1 ? 1 : (int)b;
+}
+extern "C" long long evb_loss_workspace(long long P, int K) { return (long long)loss_blocks(P) * (2 + 3 * K) * sizeof(float); }
+
+// Pass A: statistics of softmax-CE + Dice over valid pixels -> stats[2+3K] (device, fp32).
+extern "C" int evb_loss_stats(const void* logits, const void* labels, long long P, int K, int LD, int ignore_index,
+                              float* stats, void* ws, void* stream) {
+  if (K < 2 || K > kMaxK || LD % 8 || LD < K) return EVB_ERR_ARG;
+  const int nb = loss_blocks(P), n = 2 + 3 * K;
+  loss_kernel<0><<<nb, 256, 0, ST>>>((const __nv_bfloat16*)logits, (const long long*)labels, P, K, LD, ignore_index,
+                                     (float*)ws, nullptr, nullptr);
+  loss_reduce_kernel<<<(n + 127) / 128, 128, 0, ST>>>((const float*)ws, nb, n, stats);
+  return LAUNCH_OK();
+}
+// Between A and B the caller may all-reduce stats[2 : 2+3K] (Dice statistics) across ranks into dice_stats.
+extern "C" int evb_loss_finalize(const float* stats, const float* dice_stats, int K, float smooth, float ce_weight,
+                                 float dice_weight, float dice_grad_scale, float* losses, float* coef, void* stream) {
+  loss_finalize_kernel<<<1, 32, 0, ST>>>(stats, dice_stats ? dice_stats : stats + 2, K, smooth, ce_weight, dice_weight,
+                                         dice_grad_scale, losses, coef);
+  return LAUNCH_OK();
+}
+// Pass B: dlogits[P, LD] bf16 (padding channels zeroed).
+extern "C" int evb_loss_grad(const void* logits, const void* labels, long long P, int K, int LD, int ignore_index,
+                             const float* coef, void* dlogits, void* stream) {
+  if (K < 2 || K > kMaxK || LD % 8 || LD < K) return EVB_ERR_ARG;
+  loss_kernel<1><<<loss_blocks(P), 256, 0, ST>>>((const __nv_bfloat16*)logits, (const long long*)labels, P, K, LD,
+                                                 ignore_index, nullptr, coef, (__nv_bfloat16*)dlogits);
+  return LAUNCH_OK();
+}
+
+extern "C" long long evb_sgd_workspace(long long n) {
+  long long b = (n + 256 * 8 - 1) / (256 * 8);
+  if (b > 148 * 8) b = 148 * 8;
+  return (b + 2) * sizeof(float);
+}
+// Global L2 norm of the gradient arena -> norm_out[0], clip coefficient -> norm_out[1] (ERModule.clip_grad,
+// ever/interface/module.py:96-108: clip_grad_norm_(max_norm, norm_type=2)).
+extern "C" int evb_grad_norm(const float* g, long long n, float max_norm, float* norm_out, void* ws, void* stream) {
+  long long b = (n + 256 * 8 - 1) / (256 * 8);
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  sqsum_kernel<<<(int)b, 256, 0, ST>>>(g, n, (float*)ws);
+  norm_finalize_kernel<<<1, 32, 0, ST>>>((const float*)ws, (int)b, norm_out, max_norm);
+  return LAUNCH_OK();
+}
+// torch.optim.SGD step over a flat arena (ever/opt/optimizer.py:7-9), lr read from device memory.
+extern "C" int evb_sgd_step(float* w, float* g, float* mom, long long n, const float* lr, float momentum, float wd,
+                            const float* clip, int first_step, int zero_grad, void* stream) {
+  long long b = (n + 256 * 4 - 1) / (256 * 4);
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  sgd_kernel<<<(int)b, 256, 0, ST>>>(w, g, mom, n, lr, momentum, wd, clip, first_step, zero_grad);
+  return LAUNCH_OK();
+}
+
+// prob[N,K,H,W] fp32 = softmax over the K class channels of logits[P, LD] bf16 (eval path: logit.softmax(dim=1)),
+// mask[P] uint8 = argmax (lowest index wins ties, as torch.argmax on CUDA).
+namespace evb {
+__global__ void softmax_nchw_kernel(const __nv_bfloat16* __restrict__ logits, float* __restrict__ prob,
+                                    uint8_t* __restrict__ mask, long long P, int HW, int K, int LD) {
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const __nv_bfloat16* row = logits + p * LD;
+    float z[kMaxK];
+    for (int c = 0; c < K; ++c) z[c] = __bfloat162float(row[c]);
+    float mx = z[0];
+    int am = 0;
+    for (int c = 1; c < K; ++c)
+      if (z[c] > mx) { mx = z[c]; am = c; }
+    float se = 0.f;
+    for (int c = 0; c < K; ++c) { z[c] = expf(z[c] - mx); se += z[c]; }
+    const long long n = p / HW, hw = p % HW;
+    if (prob)
+      for (int c = 0; c < K; ++c) prob[(n * K + c) * HW + hw] = z[c] / se;
+    if (mask) mask[p] = (uint8_t)am;
+  }
+}
+}  // namespace evb
+extern "C" int evb_softmax_nchw(const void* logits, float* prob, void* mask, long long P, int HW, int K, int LD,
+                                void* stream) {
+  if (K < 1 || K > kMaxK) return EVB_ERR_ARG;
+  long long b = (P + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  softmax_nchw_kernel<<<(int)b, 256, 0, ST>>>((const __nv_bfloat16*)logits, prob, (uint8_t*)mask, P, HW, K, LD);
+  return LAUNCH_OK();
+}

@@ -1,0 +1,204 @@
+"""The drop-in models: ``FarSegB200`` registered in ``ever.registry.MODEL`` as 'FarSegB200' (and 'FarSeg').
+
+The module owns real ``nn.Parameter``s laid out under exactly the reference's ``state_dict`` keys
+(``en.resnet.layer1.0.conv1.weight`` ... ``head.fpn_decoder.classifier.0.bias``), so reference
+checkpoints load unchanged and torch optimizers / DDP / ``count_model_parameters`` see ordinary parameters.
+The ``nn.Conv2d`` / ``nn.BatchNorm2d`` objects are parameter containers only: their ``forward`` is never
+called.  All arithmetic runs in libevb200.so through ``ever_b200.engine.FarSegEngine``.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from ._ever_api import MODEL, ERModule
+from .engine import FarSegEngine
+
+RESNETS = {  # block kind, blocks per stage  (ever/module/_resnets.py:241-278)
+    'resnet18': ('basic', (2, 2, 2, 2)),
+    'resnet34': ('basic', (3, 4, 6, 3)),
+    'resnet50': ('bottleneck', (3, 4, 6, 3)),
+    'resnet101': ('bottleneck', (3, 4, 23, 3)),
+}
+
+
+class _Block(nn.Module):
+    """Parameter container with the attribute names of BasicBlock / Bottleneck (_resnets.py:32-112)."""
+
+    def __init__(self, kind, cin, planes, stride, down):
+        super().__init__()
+        self.kind, self.stride = kind, stride
+        if kind == 'basic':
+            self.conv1 = nn.Conv2d(cin, planes, 3, stride, 1, bias=False)
+            self.bn1 = nn.BatchNorm2d(planes)
+            self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+            self.bn2 = nn.BatchNorm2d(planes)
+        else:
+            self.conv1 = nn.Conv2d(cin, planes, 1, bias=False)
+            self.bn1 = nn.BatchNorm2d(planes)
+            self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
+            self.bn2 = nn.BatchNorm2d(planes)
+            self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+            self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.downsample = down
+
+
+class _ResNetParams(nn.Module):
+    def __init__(self, resnet_type, in_channels=3):
+        super().__init__()
+        kind, counts = RESNETS[resnet_type]
+        exp = 1 if kind == 'basic' else 4
+        self.kind = kind
+        self.conv1 = nn.Conv2d(in_channels, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        cin = 64
+        for li, (planes, n) in enumerate(zip((64, 128, 256, 512), counts), 1):
+            blocks = []
+            for b in range(n):
+                s = 2 if (b == 0 and li > 1) else 1
+                down = None
+                if b == 0 and (s != 1 or cin != planes * exp):
+                    down = nn.Sequential(nn.Conv2d(cin, planes * exp, 1, s, bias=False), nn.BatchNorm2d(planes * exp))
+                blocks.append(_Block(kind, cin, planes, s, down))
+                cin = planes * exp
+            setattr(self, 'layer%d' % li, nn.Sequential(*blocks))
+        self.out_channels = tuple(c * exp for c in (64, 128, 256, 512))
+        for m in self.modules():  # _resnets.py:163-169
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+
+
+class _Encoder(nn.Module):
+    def __init__(self, resnet_type, in_channels=3):
+        super().__init__()
+        self.resnet = _ResNetParams(resnet_type, in_channels)
+
+
+def _fpn_conv(cin, cout, k):  # ConvBlock(bn=False, relu=False), kaiming_uniform(a=1): fpn.py:18-35, ops.py:45-60
+    seq = nn.Sequential(nn.Conv2d(cin, cout, k, 1, (k - 1) // 2, bias=False), nn.Identity(), nn.Identity())
+    nn.init.kaiming_uniform_(seq[0].weight, a=1)
+    return seq
+
+
+class _FPN(nn.Module):
+    def __init__(self, in_channels_list, out_channels):
+        super().__init__()
+        for i, c in enumerate(in_channels_list, 1):
+            self.add_module('fpn_inner%d' % i, _fpn_conv(c, out_channels, 1))
+            self.add_module('fpn_layer%d' % i, _fpn_conv(out_channels, out_channels, 3))
+
+
+class _FSRelation(nn.Module):
+    def __init__(self, scene_embedding_channels, in_channels_list, out_channels, scale_aware_proj=True):
+        super().__init__()
+        if not scale_aware_proj:
+            raise NotImplementedError('FarSegB200 implements the default scale_aware_proj=True (fs_relation.py:193)')
+        self.scene_encoder = nn.ModuleList([
+            nn.Sequential(nn.Conv2d(scene_embedding_channels, out_channels, 1), nn.ReLU(True),
+                          nn.Conv2d(out_channels, out_channels, 1)) for _ in in_channels_list])
+        self.content_encoders = nn.ModuleList(
+            [nn.Sequential(nn.Conv2d(c, out_channels, 1), nn.BatchNorm2d(out_channels), nn.ReLU(True)) for c in in_channels_list])
+        self.feature_reencoders = nn.ModuleList(
+            [nn.Sequential(nn.Conv2d(c, out_channels, 1), nn.BatchNorm2d(out_channels), nn.ReLU(True)) for c in in_channels_list])
+
+
+class _Decoder(nn.Module):
+    def __init__(self, in_channels, out_channels, in_feat_output_strides=(4, 8, 16, 32), out_feat_output_stride=4,
+                 classifier_config=None):
+        super().__init__()
+        cc = dict(classifier_config or {})
+        self.num_classes = int(cc.get('num_classes', 1))
+        self.scale_factor = int(cc.get('scale_factor', 1))
+        ks = int(cc.get('kernel_size', 1))
+        if ks != 1:
+            raise NotImplementedError('classifier kernel_size 1 only')
+        self.num_upsample = []
+        self.blocks = nn.ModuleList()
+        for os_ in in_feat_output_strides:
+            nup = int(math.log2(int(os_))) - int(math.log2(int(out_feat_output_stride)))
+            self.num_upsample.append(nup)
+            nl = nup if nup != 0 else 1
+            self.blocks.append(nn.Sequential(*[
+                nn.Sequential(nn.Conv2d(in_channels if j == 0 else out_channels, out_channels, 3, 1, 1, bias=False),
+                              nn.BatchNorm2d(out_channels), nn.ReLU(True), nn.Identity()) for j in range(nl)]))
+        self.classifier = nn.Sequential(nn.Conv2d(out_channels, self.num_classes, 1), nn.Identity())
+
+
+class _Head(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.fpn = _FPN(tuple(cfg.fpn.in_channels_list), int(cfg.fpn.out_channels))
+        fs = cfg.fs_relation
+        self.fs_relation = _FSRelation(int(fs.scene_embedding_channels), tuple(fs.in_channels_list), int(fs.out_channels),
+                                       bool(fs.scale_aware_proj))
+        d = cfg.fpn_decoder
+        self.fpn_decoder = _Decoder(int(d.in_channels), int(d.out_channels), tuple(d.in_feat_output_strides),
+                                    int(d.out_feat_output_stride), d.classifier_config)
+
+
+@MODEL.register('FarSegB200')
+class FarSegB200(ERModule):
+    """FarSeg (ResNetEncoder -> FarSegHead -> CE + Dice), glue model of SURVEY.md Appendix E, computed by the
+    sm_100a engine.  forward(x, y): training -> {'ce_loss','dice_loss'}; eval -> softmax probabilities."""
+
+    def __init__(self, config=None):
+        super().__init__(config)
+        enc = self.config.encoder
+        self.en = _Encoder(enc.resnet_type, int(enc.in_channels))
+        chans = self.en.resnet.out_channels
+        head = self.config.head
+        if tuple(head.fpn.in_channels_list) != tuple(chans):
+            head.fpn.in_channels_list = tuple(chans)
+            head.fs_relation.scene_embedding_channels = chans[-1]
+        self.head = _Head(head)
+        self.engine = None
+
+    def set_default_config(self):
+        self.config.update(dict(
+            encoder=dict(resnet_type='resnet50', in_channels=3, pretrained=False, batchnorm_trainable=True, freeze_at=0,
+                         output_stride=32, include_conv5=True),
+            head=dict(
+                fpn=dict(in_channels_list=(256, 512, 1024, 2048), out_channels=256),
+                fs_relation=dict(scene_embedding_channels=2048, in_channels_list=(256, 256, 256, 256), out_channels=256,
+                                 scale_aware_proj=True),
+                fpn_decoder=dict(in_channels=256, out_channels=256, in_feat_output_strides=(4, 8, 16, 32),
+                                 out_feat_output_stride=4,
+                                 classifier_config=dict(scale_factor=4.0, num_classes=1, kernel_size=1))),
+            loss=dict(ce=dict(weight=1.0), dice=dict(weight=1.0, smooth=1.0, sync_statistics=True), ignore_index=255),
+        ))
+
+    # --------------------------------------------------------------------------------------------------
+    def _engine(self):
+        if self.engine is None:
+            dev = next(self.parameters()).device
+            if dev.type != 'cuda':
+                raise RuntimeError('FarSegB200 computes only on a CUDA (sm_100a) device: move the model with .cuda(); '
+                                   'there is no CPU path')
+            # bypass nn.Module.__setattr__ bookkeeping for a plain python object
+            object.__setattr__(self, 'engine', FarSegEngine(self))
+        return self.engine
+
+    def forward(self, x, y=None):
+        eng = self._engine()
+        if self.training:
+            if y is None:
+                raise ValueError('training forward needs y (dict with key "cls" or a label tensor)')
+            labels = y['cls'] if isinstance(y, dict) else y
+            return eng.forward_train(x, labels)
+        return eng.forward_eval(x)
+
+    def backward(self, loss_dict=None, amp=None, scaler=None, **kwargs):
+        """ERModule.backward hook (ever/interface/module.py:76-81): the native backward of the step whose losses
+        were returned by the last training forward (all '*loss' keys, unit weights as Launcher sums them)."""
+        self._engine().backward()
+
+    def clip_grad_info(self):
+        return dict()
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        object.__setattr__(self, 'engine', None)  # parameter storage moved: rebuild arenas lazily
+        return r
+
+
+MODEL.register('FarSeg', FarSegB200, override=True) if hasattr(MODEL, 'register') else None

@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: FarSeg-R50, 15 classes, 8 x 3 x 512 x 512 synthetic tiles per GPU (BASELINE.json
+configs[1]), one step = forward + CE/Dice loss + backward (+ NCCL gradient all-reduce at N>1) + fused clip/SGD.
+
+    python bench.py --gpus N --steps K --warmup W            # B200 engine (libevb200.so), prints ONE JSON line
+    python bench.py --impl reference --steps K --warmup W    # the reference's PyTorch-CPU path (oracle port)
+
+value  = whole-job tiles/s with inputs resident in HBM (CUDA-graph replay of the step, CUDA events, max over ranks)
+e2e    = the same metric through the plugin call model(x, y) / model.backward() with pinned HOST inputs:
+         H2D copies of the tile batch + labels and a D2H read of the losses inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_CLASSES, TILE, PER_GPU_BATCH = 15, 512, 8
+GFLOP_PER_TILE = 343.1  # fwd 114.8 + bwd 228.3, FlopCounterMode on the reference modules
+METRIC = 'FarSeg-R50 512x512 tiles/s fwd+bwd'
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sust=d['bf16_tflops_sustained'], src='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback')
+
+
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 8 and r[2].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower() == 'active'})
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def farseg_config():
+    return dict(encoder=dict(resnet_type='resnet50'),
+                head=dict(fpn_decoder=dict(out_channels=256, classifier_config=dict(num_classes=K_CLASSES))))
+
+
+def synthetic(n, seed=0):
+    g = torch.Generator().manual_seed(1234 + seed)
+    x = torch.randn(n, 3, TILE, TILE, generator=g)
+    g = torch.Generator().manual_seed(4321 + seed)
+    y = torch.randint(0, K_CLASSES, (n, TILE, TILE), generator=g)
+    g = torch.Generator().manual_seed(99 + seed)
+    y[torch.rand(n, TILE, TILE, generator=g) < 0.05] = 255
+    return x, y
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference
+def cpu_reference(n_tiles, iters, warmup):
+    """The reference's PyTorch-CPU path (fp32; Launcher cannot autocast on CPU, ever/core/launcher.py:194),
+    restated in oracle/farseg_oracle.py, on all host cores."""
+    from oracle.farseg_oracle import FarSegOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    m = FarSegOracle('resnet50', K_CLASSES, 256).train()
+    x, y = synthetic(n_tiles)
+    ts = []
+    for i in range(warmup + iters):
+        t0 = time.perf_counter()
+        m.zero_grad(set_to_none=True)
+        losses = m(x, dict(cls=y))
+        sum(losses.values()).backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            ts.append(dt)
+    sec = sum(ts) / len(ts)
+    return n_tiles / sec, sec, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n_tiles = 2
+    val, sec, cores = cpu_reference(n_tiles, max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
+    sample = '%d tiles of 3x512x512 per step (bounded sample of the 8-tile batch), fp32, torch CPU, %d threads' % (n_tiles, cores)
+    line = dict(metric=METRIC, value=val, unit='tiles/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                impl='reference',
+                config=dict(workload='FarSeg-R50 15-class 3x512x512 synthetic tiles, fwd+loss+bwd', tiles_per_step=n_tiles),
+                cpu_baseline=dict(value=val, unit='tiles/s', cores=cores, kind='port', sample=sample),
+                e2e=dict(value=val, unit='tiles/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ dominant-kernel roofline
+def conv_roofline(pk):
+    """3x3 256->256 conv on 8 x 128 x 128 (33.7 % of forward FLOPs), igemm_kernel<256>, timed alone
+    with CUDA events on the launch stream; operands rotate through > L2-size buffers."""
+    from ever_b200 import ops
+    n, h, w, c = 8, 128, 128, 256
+    nbuf = 6  # 6 x (67 MB in + 67 MB out) > 126 MB L2
+    xs = [torch.randn(n, h, w, c, device='cuda').bfloat16() for _ in range(nbuf)]
+    ys = [torch.empty(n, h, w, c, device='cuda', dtype=torch.bfloat16) for _ in range(nbuf)]
+    wt = torch.randn(c, c, 3, 3, device='cuda') * 0.02
+    wf, _ = ops.pack_conv_weight_torch(wt)
+    for i in range(nbuf):
+        ops.conv2d_fwd(xs[i], wf, 3, 1, c, out=ys[i])
+    torch.cuda.synchronize()
+    iters = 30
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for i in range(iters):
+        ops.conv2d_fwd(xs[i % nbuf], wf, 3, 1, c, out=ys[i % nbuf])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flop = 2.0 * n * h * w * c * c * 9
+    ach = flop / (ms * 1e-3) / 1e12
+    return dict(bound='tensor', kernel='igemm_kernel<256> conv3x3 256->256 @ 8x128x128', achieved=ach, peak=pk['tf_burst'],
+                unit='TFLOP/s', frac=ach / pk['tf_burst'], traffic=None, peak_source=pk['src'] + ' bf16_tflops (burst)',
+                ms_per_launch=ms, flop_per_launch=flop)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+    from ever_b200 import _lib
+    from ever_b200.module import FarSegB200
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    torch.manual_seed(0)
+    model = FarSegB200(farseg_config()).cuda().train()
+    eng = model._engine()
+    eng.set_distributed(rank, world)
+    if world > 1:  # same initial weights everywhere (DDP broadcasts rank 0's at construction)
+        dist.broadcast(eng.flat_w, 0)
+    xh, yh = synthetic(PER_GPU_BATCH, seed=rank)
+    xh, yh = xh.pin_memory(), yh.pin_memory()
+    x, y = xh.cuda(), yh.cuda()
+    lr = 0.007
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: CUDA-graph replay, inputs resident in HBM
+    use_graph = os.environ.get('EVB_NO_GRAPH', '0') != '1'
+    graph = None
+    l0 = _lib.launches[0]
+    if use_graph:
+        graph, out = eng.capture_step(x, y)
+        per_step_launches = (_lib.launches[0] - l0) // 3 + 3
+    else:
+        out = model(x, dict(cls=y))
+        model.backward(out, None, None)
+        per_step_launches = _lib.launches[0] - l0 + 3
+
+    def step():
+        nonlocal out
+        if graph is not None:
+            graph.replay()
+        else:
+            out = eng.forward_train(x, y)
+            eng.backward(allreduce=False)
+        eng.allreduce_grads()
+        eng.sgd_step(lr)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    value = world * PER_GPU_BATCH / (ms * 1e-3)
+    loss_now = {k: float(v) for k, v in out.items()}
+
+    # ---- e2e: plugin API with host buffers
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        x.copy_(xh, non_blocking=True)
+        y.copy_(yh, non_blocking=True)
+        if graph is not None:
+            graph.replay()
+            o = out
+        else:
+            o = model(x, dict(cls=y))
+            model.backward(o, None, None)
+        eng.allreduce_grads()
+        eng.sgd_step(lr)
+        return torch.stack([o['ce_loss'], o['dice_loss']]).cpu()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms2 = e0.elapsed_time(e1) / e2e_steps
+    t = torch.tensor([ms2], device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms2 = float(t)
+    e2e = dict(value=world * PER_GPU_BATCH / (ms2 * 1e-3), unit='tiles/s',
+               h2d_bytes_per_step=int(xh.numel() * 4 + yh.numel() * 8), d2h_bytes_per_step=8, ms_per_step=ms2,
+               api='FarSegB200.forward(x, y) + .backward() via libevb200.so C ABI, pinned host inputs')
+
+    if rank == 0:
+        pk = peaks()
+        roof = conv_roofline(pk)
+        cpu_val, cpu_sec, cores = cpu_reference(2, 1, 1) if world == 1 and not args.no_cpu else (None, None, None)
+        tfs = value / world * GFLOP_PER_TILE / 1e3
+        line = dict(metric=METRIC, value=value, unit='tiles/s', n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+                    ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic',
+                    config=dict(workload='FarSeg-R50 (ResNet-50 + FPN + FS-Relation + asymmetric decoder, 256-ch), 15-class, '
+                                         '8x3x512x512 synthetic tiles per GPU, fwd + CE/Dice loss + bwd + grad all-reduce + '
+                                         'clip/SGD', global_batch=world * PER_GPU_BATCH, tile=TILE,
+                                parallelism='dp%d' % world, cuda_graph=graph is not None,
+                                l2='step working set (~10 GB of activations) >> 126 MB L2; no explicit flush'),
+                    e2e=e2e, gpu_launches=int(per_step_launches * args.steps), clocks=clocks, roofline=roof,
+                    model_tflops_per_gpu=tfs, model_frac_of_sustained_peak=tfs / pk['tf_sust'], losses=loss_now)
+        if cpu_val is not None:
+            line['cpu_baseline'] = dict(value=cpu_val, unit='tiles/s', cores=cores, kind='port',
+                                        sample='2 tiles of 3x512x512, 1 warm-up + 1 timed fwd+loss+bwd, fp32 torch CPU')
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -25,7 +25,14 @@ def lib():
     return _lib
 
 
+# kernels launched per C-ABI call (lower bounds; evb_conv2d_dgrad stride 2 launches up to 4)
+_KERNELS = {'evb_conv2d_wgrad': 2, 'evb_conv2d_wgrad(stem)': 2, 'evb_bn_stats': 2, 'evb_bn_bwd': 3, 'evb_bias_grad': 2,
+            'evb_loss_stats': 2, 'evb_linear_bwd': 2, 'evb_grad_norm': 2}
+launches = [0]
+
+
 def check(rc, what):
+    launches[0] += _KERNELS.get(what, 1)
     if rc != 0:
         raise EvbError('%s failed: rc=%d cuda=%s' % (what, rc, lib().evb_last_cuda_error().decode()))
 

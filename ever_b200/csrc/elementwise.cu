@@ -94,18 +94,34 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
 
 // BN training statistics finalize: mean, biased var -> rstd, folded scale/shift, running-stat update
 // (momentum, unbiased var), reference semantics SURVEY.md Appendix D.
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// one warp per channel: lanes stride over the partial blocks, fixed-order tree -> deterministic
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s,
+                                                double& ss) {
+  const int lane = threadIdx.x & 31;
+  double a = 0.0, b = 0.0;
+  for (int k = lane; k < nblk; k += 32) {
+    a += partial[((size_t)k * 2) * C + c];
+    b += partial[((size_t)k * 2 + 1) * C + c];
+  }
+  s = warp_sum_d(a);
+  ss = warp_sum_d(b);
+}
+
 __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, long long M, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, float* __restrict__ mean, float* __restrict__ rstd,
                                    float* __restrict__ scale, float* __restrict__ shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s += partial[((size_t)b * 2) * C + c];
-    ss += partial[((size_t)b * 2 + 1) * C + c];
-  }
+  double s, ss;
+  reduce_partials(partial, nblk, C, c, s, ss);
+  if ((threadIdx.x & 31) != 0) return;
   const double mu = s / (double)M;
   double var = ss / (double)M - mu * mu;
   if (var < 0) var = 0;
@@ -136,13 +152,11 @@ __global__ void bn_fold_kernel(const float* gamma, const float* beta, const floa
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, int accumulate, float* __restrict__ fresh) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s += partial[((size_t)b * 2) * C + c];
-    ss += partial[((size_t)b * 2 + 1) * C + c];
-  }
+  double s, ss;
+  reduce_partials(partial, nblk, C, c, s, ss);
+  if ((threadIdx.x & 31) != 0) return;
   if (fresh) { fresh[c] = (float)s; fresh[C + c] = (float)ss; }  // this launch's own sums: [dbeta | dgamma]
   if (dgamma) { if (accumulate) dgamma[c] += (float)ss; else dgamma[c] = (float)ss; }
   if (dbeta) { if (accumulate) dbeta[c] += (float)s; else dbeta[c] = (float)s; }
@@ -355,55 +369,40 @@ bilinear_up_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __re
   const float sy = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
   const float sx = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
   const long long total = (long long)N * h * w * cg;
-  constexpr int kMaxCand = 12;  // f <= 4: at most 2f+2 candidates per axis
+  const float inv_sy = sy > 0.f ? 1.f / sy : 0.f, inv_sx = sx > 0.f ? 1.f / sx : 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(i % cg);
     long long p = i / cg;
     const int ix = (int)(p % w); p /= w;
     const int iy = (int)(p % h);
     const int n = (int)(p / h);
-    float wy[kMaxCand], wx[kMaxCand];
-    int cy0 = iy * f - f - 1, cx0 = ix * f - f - 1;
-    int ny = 0, nx = 0;
-    // weights along y for candidates cy0 .. cy0+2f+2
-    for (int k = 0; k < 2 * f + 3 && k < kMaxCand; ++k) {
-      const int oy = cy0 + k;
-      float wgt = 0.f;
-      if (oy >= 0 && oy < Ho) {
-        const float fy = sy * oy;
-        const int y0 = (int)fy;
-        const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
-        const float ly = fy - y0;
-        if (y0 == iy) wgt += 1.f - ly;
-        if (y1 == iy) wgt += ly;
-      }
-      wy[k] = wgt;
-      ny = k + 1;
-    }
-    for (int k = 0; k < 2 * f + 3 && k < kMaxCand; ++k) {
-      const int ox = cx0 + k;
-      float wgt = 0.f;
-      if (ox >= 0 && ox < Wo) {
+    // outputs whose source coordinate falls in (iy-1, iy+1): o in ((iy-1)/s, (iy+1)/s), widened by one for rounding;
+    // the exact membership test below uses the same float formula as the forward kernel.
+    int ylo = 0, yhi = Ho - 1, xlo = 0, xhi = Wo - 1;
+    if (sy > 0.f) { ylo = max(0, (int)floorf((iy - 1) * inv_sy) - 1); yhi = min(Ho - 1, (int)ceilf((iy + 1) * inv_sy) + 1); }
+    if (sx > 0.f) { xlo = max(0, (int)floorf((ix - 1) * inv_sx) - 1); xhi = min(Wo - 1, (int)ceilf((ix + 1) * inv_sx) + 1); }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int oy = ylo; oy <= yhi; ++oy) {
+      const float fy = sy * oy;
+      const int y0 = (int)fy;
+      const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+      const float ly = fy - y0;
+      float wy = 0.f;
+      if (y0 == iy) wy += 1.f - ly;
+      if (y1 == iy) wy += ly;
+      if (wy == 0.f) continue;
+      for (int ox = xlo; ox <= xhi; ++ox) {
         const float fx = sx * ox;
         const int x0 = (int)fx;
         const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
         const float lx = fx - x0;
-        if (x0 == ix) wgt += 1.f - lx;
-        if (x1 == ix) wgt += lx;
-      }
-      wx[k] = wgt;
-      nx = k + 1;
-    }
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int a = 0; a < ny; ++a) {
-      if (wy[a] == 0.f) continue;
-      const int oy = cy0 + a;
-      for (int b = 0; b < nx; ++b) {
-        const float wgt = wy[a] * wx[b];
-        if (wgt == 0.f) continue;
-        const int ox = cx0 + b;
+        float wx = 0.f;
+        if (x0 == ix) wx += 1.f - lx;
+        if (x1 == ix) wx += lx;
+        if (wx == 0.f) continue;
+        const float wgt = wy * wx;
         float gv[8];
         unpack8(*reinterpret_cast<const bf16x8*>(dy + (((long long)n * Ho + oy) * Wo + ox) * lddy + g * 8), gv);
 #pragma unroll
@@ -554,6 +553,38 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, 
   }
 }
 
+// All convolutions of the model in one launch.  desc[i] = {w, wf, wb, Co, Ci, kk, CoP, CiP, CiPb, CoPb, first_block, -}
+// (12 x int64); block_map[b] = index of the descriptor block b works on; 1024 elements per block.
+__global__ void __launch_bounds__(256)
+pack_weights_batched_kernel(const long long* __restrict__ desc, const int* __restrict__ block_map) {
+  const long long* d = desc + (long long)block_map[blockIdx.x] * 12;
+  const float* w = reinterpret_cast<const float*>(d[0]);
+  __nv_bfloat16* wf = reinterpret_cast<__nv_bfloat16*>(d[1]);
+  __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(d[2]);
+  const int Co = (int)d[3], Ci = (int)d[4], kk = (int)d[5], CoP = (int)d[6], CiP = (int)d[7], CiPb = (int)d[8],
+            CoPb = (int)d[9];
+  const long long nf = (long long)kk * CoP * CiP;
+  const long long nb = wb ? (long long)kk * CiPb * CoPb : 0;
+  const long long base = ((long long)blockIdx.x - d[10]) * 1024;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long long i = base + u * 256 + threadIdx.x;
+    if (i >= nf + nb) break;
+    if (i < nf) {
+      const int ci = (int)(i % CiP);
+      const int co = (int)((i / CiP) % CoP);
+      const int t = (int)(i / ((long long)CiP * CoP));
+      wf[i] = __float2bfloat16_rn((co < Co && ci < Ci) ? w[((long long)co * Ci + ci) * kk + t] : 0.f);
+    } else {
+      const long long k = i - nf;
+      const int co = (int)(k % CoPb);
+      const int ci = (int)((k / CoPb) % CiPb);
+      const int t = (int)(k / ((long long)CoPb * CiPb));
+      wb[k] = __float2bfloat16_rn((co < Co && ci < Ci) ? w[((long long)co * Ci + ci) * kk + t] : 0.f);
+    }
+  }
+}
+
 // generic strided fp32 2-D copy: dst[r*ldd + c] (+)= src[r*lds + c]
 __global__ void copy2d_kernel(const float* src, int lds, float* dst, int ldd, int rows, int cols, int accumulate) {
   const long long total = (long long)rows * cols;
@@ -590,7 +621,7 @@ extern "C" int evb_bn_stats(const void* x, long long M, int C, const float* gamm
   const int nb = colsum_blocks(M, C);
   colsum_kernel<0><<<nb, kEwThreads, kEwThreads * 16 * sizeof(float), ST>>>(
       (const __nv_bfloat16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, M, C, (float*)ws);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>((const float*)ws, nb, M, C, gamma, beta, running_mean, running_var,
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, ST>>>((const float*)ws, nb, M, C, gamma, beta, running_mean, running_var,
                                                       momentum, eps, mean, rstd, scale, shift);
   return LAUNCH_OK();
 }
@@ -624,7 +655,7 @@ extern "C" int evb_bn_bwd(const void* dy, const void* x, const void* ymask, cons
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)ymask, mean, rstd, scale, shift, mask_mode,
       M, C, (float*)ws);
   float* fresh = (float*)ws + (size_t)nb * 2 * C;
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>((const float*)ws, nb, C, dgamma, dbeta, param_acc, fresh);
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, ST>>>((const float*)ws, nb, C, dgamma, dbeta, param_acc, fresh);
   const long long nvec = M * C / 8;
   bn_bwd_apply_kernel<<<ew_blocks(nvec, kEwThreads * 4), kEwThreads, 0, ST>>>(
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ymask, mean, rstd, scale, shift, fresh + C,
@@ -640,7 +671,7 @@ extern "C" int evb_bias_grad(const void* dy, long long M, int C, float* db, floa
   colsum_kernel<0><<<nb, kEwThreads, kEwThreads * 16 * sizeof(float), ST>>>(
       (const __nv_bfloat16*)dy, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, M, C, (float*)ws);
   (void)scratch_sq;
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>((const float*)ws, nb, C, nullptr, db, accumulate, nullptr);
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, ST>>>((const float*)ws, nb, C, nullptr, db, accumulate, nullptr);
   return LAUNCH_OK();
 }
 
@@ -721,6 +752,11 @@ extern "C" int evb_pack_weight(const float* w, int Co, int Ci, int kk, void* wf,
   const long long total = (long long)kk * CoP * CiP + (wb ? (long long)kk * CiPb * CoPb : 0);
   pack_weight_kernel<<<ew_blocks(total, kEwThreads * 4), kEwThreads, 0, ST>>>(w, Co, Ci, kk, (__nv_bfloat16*)wf, CoP, CiP,
                                                                            (__nv_bfloat16*)wb, CiPb, CoPb);
+  return LAUNCH_OK();
+}
+
+extern "C" int evb_pack_weights_batched(const void* desc, const void* block_map, int nblocks, void* stream) {
+  pack_weights_batched_kernel<<<nblocks, 256, 0, ST>>>((const long long*)desc, (const int*)block_map);
   return LAUNCH_OK();
 }
 

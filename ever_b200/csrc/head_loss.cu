@@ -150,20 +150,30 @@ __global__ void linear_bwd_w_kernel(const float* __restrict__ dy, const float* _
   dW[idx] = accumulate ? dW[idx] + s : s;
   if (i == 0 && db) db[o] = accumulate ? db[o] + sb : sb;
 }
-// dx[n][i] (+)= sum_o g[n][o] bf16(W[o][i])
-__global__ void linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ W,
-                                    float* __restrict__ dx, int N, int I, int O, int relu, int accumulate) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)N * I) return;
-  const int n = (int)(idx / I), i = (int)(idx % I);
+// dx[n][i] (+)= sum_o g[n][o] bf16(W[o][i]).  block (128 i, 8 o-lanes), grid (I/128, N)
+__global__ void __launch_bounds__(1024)
+linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ W,
+                    float* __restrict__ dx, int N, int I, int O, int relu, int accumulate) {
+  __shared__ float red[8][129];
+  const int i = blockIdx.x * 128 + threadIdx.x, n = blockIdx.y;
   float s = 0.f;
-  for (int o = 0; o < O; ++o) {
-    float g = dy[n * O + o];
-    if (relu && !(y[n * O + o] > 0.f)) g = 0.f;
-    s += bf16_round(g) * bf16_round(W[(long long)o * I + i]);
+  if (i < I) {
+    for (int o = threadIdx.y; o < O; o += 8) {
+      float g = dy[n * O + o];
+      if (relu && !(y[n * O + o] > 0.f)) g = 0.f;
+      s += bf16_round(g) * bf16_round(W[(long long)o * I + i]);
+    }
   }
-  s = bf16_round(s);
-  dx[idx] = accumulate ? dx[idx] + s : s;
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < I) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+    t = bf16_round(t);
+    const long long idx = (long long)n * I + i;
+    dx[idx] = accumulate ? dx[idx] + t : t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ CE + Dice
@@ -363,7 +373,7 @@ extern "C" int evb_linear_fwd(const float* x, const float* W, const float* b, fl
 extern "C" int evb_linear_bwd(const float* dy, const float* y, const float* x, const float* W, float* dW, float* db,
                               float* dx, int N, int I, int O, int relu, int acc_w, int acc_x, void* stream) {
   linear_bwd_w_kernel<<<(int)(((long long)O * I + 255) / 256), 256, 0, ST>>>(dy, y, x, dW, db, N, I, O, relu, acc_w);
-  if (dx) linear_bwd_x_kernel<<<(int)(((long long)N * I + 255) / 256), 256, 0, ST>>>(dy, y, W, dx, N, I, O, relu, acc_x);
+  if (dx) linear_bwd_x_kernel<<<dim3((I + 127) / 128, N), dim3(128, 8), 0, ST>>>(dy, y, W, dx, N, I, O, relu, acc_x);
   return LAUNCH_OK();
 }
 

@@ -182,6 +182,29 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
   }
 }
 
+// split-parallel variant for many splits / few outputs: block (32 co, 8 split lanes), one ci per blockIdx.y
+__global__ void wgrad_reduce_splitpar_kernel(const float* __restrict__ ws, float* __restrict__ dw, int nsplit, int ntaps,
+                                             int Cin, int Cout, int CinP, int CoutP, int accumulate) {
+  __shared__ float red[8][33];
+  const int tap = blockIdx.z, ci = blockIdx.y;
+  const int co = blockIdx.x * 32 + threadIdx.x;
+  const long long ss = (long long)ntaps * CinP * CoutP;
+  float s = 0.f;
+  if (co < Cout) {
+    const float* src = ws + ((long long)tap * CinP + ci) * CoutP + co;
+    for (int k = threadIdx.y; k < nsplit; k += 8) s += src[k * ss];
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && co < Cout) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+    float* dst = dw + ((long long)co * Cin + ci) * ntaps + tap;
+    *dst = accumulate ? (*dst + t) : t;
+  }
+}
+
 static int pow2_le(int x, int cap) {
   int r = 1;
   while (r * 2 <= x && r * 2 <= cap) r *= 2;
@@ -238,7 +261,7 @@ static WgradPlan plan_wgrad(int N, int Ho, int Wo, int Cin, int Cout, int ntaps,
   pl.tn = (N + pl.bn - 1) / pl.bn;
   pl.nchunks = pl.tw * pl.th * pl.tn;
   const int base = ntaps * pl.tiles_ci * pl.tiles_co;
-  int split = force_split ? force_split : (2 * 148 + base - 1) / base;
+  int split = force_split ? force_split : (2 * 148) / base;  // round down: at most two full waves of CTAs
   if (split > pl.nchunks) split = pl.nchunks;
   if (!force_split) {
     const int max_by_work = (pl.nchunks + 7) / 8;  // at least ~8 chunks (512 pixels) per CTA
@@ -302,8 +325,14 @@ extern "C" int evb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, con
     default: rc = EVB_ERR_ARG;
   }
   if (rc) return rc;
-  dim3 grid((Cout + 31) / 32, (Cin + 31) / 32, ntaps), block(32, 8);
-  wgrad_reduce_kernel<<<grid, block, 0, st>>>((const float*)ws, dw, pl.nsplit, ntaps, Cin, Cout, pl.CinP, pl.CoutP,
-                                              accumulate);
+  if (pl.nsplit > 8) {
+    dim3 grid((Cout + 31) / 32, Cin, ntaps), block(32, 8);
+    wgrad_reduce_splitpar_kernel<<<grid, block, 0, st>>>((const float*)ws, dw, pl.nsplit, ntaps, Cin, Cout, pl.CinP,
+                                                         pl.CoutP, accumulate);
+  } else {
+    dim3 grid((Cout + 31) / 32, (Cin + 31) / 32, ntaps), block(32, 8);
+    wgrad_reduce_kernel<<<grid, block, 0, st>>>((const float*)ws, dw, pl.nsplit, ntaps, Cin, Cout, pl.CinP, pl.CoutP,
+                                                accumulate);
+  }
   return cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
 }

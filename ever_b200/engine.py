@@ -171,14 +171,28 @@ class FarSegEngine:
         self.scr_cls_db = torch.zeros(64, dtype=torch.float32, device=self.dev)
         self.scr_stem_dw = torch.zeros(64 * self.stem_kp, dtype=torch.float32, device=self.dev)
 
-    def pack_weights(self):
-        """fp32 master -> bf16 packs (run once per step, after the optimizer update)."""
-        st = stream()
-        for cp in self.convs:
+    def _build_pack_table(self):
+        rows, bmap, nblk = [], [], 0
+        for i, cp in enumerate(self.convs):
             kk = cp.k * cp.k
-            w = cp.weight
-            check(self.L.evb_pack_weight(ptr(w), c_int(cp.co), c_int(cp.ci), c_int(kk), ptr(cp.wf), c_int(cp.cop),
-                                         c_int(cp.cip), ptr(cp.wb), c_int(cp.cip), c_int(cp.cop), st), 'evb_pack_weight')
+            total = kk * cp.cop * cp.cip * (2 if cp.need_dgrad else 1)
+            nb = (total + 1023) // 1024
+            rows.append([cp.weight.data_ptr(), cp.wf.data_ptr(), cp.wb.data_ptr() if cp.need_dgrad else 0, cp.co, cp.ci, kk,
+                         cp.cop, cp.cip, cp.cip, cp.cop, nblk, 0])
+            bmap += [i] * nb
+            nblk += nb
+        self._pack_desc = torch.tensor(rows, dtype=torch.int64, device=self.dev)
+        self._pack_map = torch.tensor(bmap, dtype=torch.int32, device=self.dev)
+        self._pack_nblk = nblk
+        self._pack_ptrs = [cp.weight.data_ptr() for cp in self.convs]
+
+    def pack_weights(self):
+        """fp32 master -> bf16 packs for every convolution, one launch (once per step, after the optimizer)."""
+        st = stream()
+        if getattr(self, '_pack_desc', None) is None or self._pack_ptrs != [cp.weight.data_ptr() for cp in self.convs]:
+            self._build_pack_table()
+        check(self.L.evb_pack_weights_batched(ptr(self._pack_desc), ptr(self._pack_map), c_int(self._pack_nblk), st),
+              'evb_pack_weights_batched')
         check(self.L.evb_copy2d_f32(ptr(self.cls.bias), c_int(self.K), ptr(self.cls_bias_pad), c_int(64), c_int(1),
                                     c_int(self.K), c_int(0), st), 'evb_copy2d_f32')
 
@@ -312,7 +326,10 @@ class FarSegEngine:
             def bwd():
                 if y.grad is None:
                     return
-                self._bn_backward(y.grad, x, bp, fold, 1 if relu else 0, y.data if relu else None, res)
+                if relu and res is None:   # mask recomputed from x: one tensor read less per pass
+                    self._bn_backward(y.grad, x, bp, fold, 2, None, None)
+                else:
+                    self._bn_backward(y.grad, x, bp, fold, 1 if relu else 0, y.data if relu else None, res)
             self.tape.append(bwd)
         return y
 
@@ -573,12 +590,12 @@ class FarSegEngine:
                                   c_float(self.dice_w), c_float(scale), ptr(losses), ptr(coef), stream()),
               'evb_loss_finalize')
         self._saved_for_backward = (cls, logits, labels, coef, npx)
-        for bn in self._bn_tracked:
-            bn.num_batches_tracked += 1
+        if self._bn_tracked:
+            torch._foreach_add_([bn.num_batches_tracked for bn in self._bn_tracked], 1)
         return dict(ce_loss=losses[0] * self.ce_w if self.ce_w != 1.0 else losses[0],
                     dice_loss=losses[1] * self.dice_w if self.dice_w != 1.0 else losses[1])
 
-    def backward(self):
+    def backward(self, allreduce=True):
         L = self.L
         if self._saved_for_backward is None:
             raise RuntimeError('backward() without a preceding training forward')
@@ -597,9 +614,55 @@ class FarSegEngine:
         for fn in reversed(self.tape):
             fn()
         self.tape = []
+        if allreduce:
+            self.allreduce_grads()
+
+    def allreduce_grads(self):
+        """The one gradient exchange of the step: NCCL all-reduce (mean) of the flat fp32 gradient arena
+        (reference: DDP bucketed all-reduce, ever/trainer/th_ddp_trainer.py:25-30)."""
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.AVG)
+
+    # ------------------------------------------------------------------ fused optimizer (SURVEY 8f rank 1)
+    def sgd_step(self, lr, momentum=0.9, weight_decay=1e-4, max_norm=35.0):
+        """clip_grad_norm_(max_norm, 2) + torch.optim.SGD step + zero_grad over the flat arenas
+        (ever/interface/module.py:83-108, ever/opt/optimizer.py:7-9) as two kernels; lr lives on the device."""
+        L = self.L
+        n = self.flat_w.numel()
+        if not hasattr(self, '_mom'):
+            self._mom = torch.zeros_like(self.flat_w)
+            self._lr = torch.zeros(1, dtype=torch.float32, device=self.dev)
+            self._norm = torch.zeros(2, dtype=torch.float32, device=self.dev)
+            self._sgd_ws = torch.empty(L.evb_sgd_workspace(c_ll(n)) // 4 + 4, dtype=torch.float32, device=self.dev)
+            self._sgd_first = True
+        self._lr.fill_(float(lr))
+        check(L.evb_grad_norm(ptr(self.flat_g), c_ll(n), c_float(max_norm if max_norm else 0.0), ptr(self._norm),
+                              ptr(self._sgd_ws), stream()), 'evb_grad_norm')
+        check(L.evb_sgd_step(ptr(self.flat_w), ptr(self.flat_g), ptr(self._mom), c_ll(n), ptr(self._lr),
+                             c_float(momentum), c_float(weight_decay), ptr(self._norm), c_int(1 if self._sgd_first else 0),
+                             c_int(1), stream()), 'evb_sgd_step')
+        self._sgd_first = False
+        return self._norm
+
+    # ------------------------------------------------------------------ CUDA-graph step
+    def capture_step(self, x, labels):
+        """Capture forward + loss + backward for fixed-shape device inputs into one CUDA graph.
+        Returns (graph, losses dict).  The gradient all-reduce and the optimizer run after the replay."""
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm-up: sets kernel attributes, sizes the workspace
+                self.forward_train(x, labels)
+                self.backward(allreduce=False)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self.forward_train(x, labels)
+            self.backward(allreduce=False)
+        return g, out
 
     @torch.no_grad()
     def forward_eval(self, x, return_mask=False):

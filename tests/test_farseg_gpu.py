@@ -107,20 +107,44 @@ def test_train_step_parity(case):
 
 
 def test_eval_masks():
+    """Eval path (folded running statistics).  Running stats are first calibrated to the batch statistics so the
+    random-weight network is well scaled.  Mask gate: identical argmax wherever the fp32 oracle's top-2 logit margin
+    exceeds the bf16 noise band (2 % of the logit range); overall agreement is reported."""
     from oracle.farseg_oracle import synthetic_batch
-    resnet, k, dec, n, h, w = 'resnet18', 5, 128, 2, 128, 128
+    resnet, k, dec, n, h, w = 'resnet18', 5, 128, 2, 256, 256
     ora, mine = _build(resnet, k, dec)
     x, _ = synthetic_batch(n, h, w, k)
     x = x.cuda()
-    ora = ora.cuda().eval()
+    ora = ora.cuda().train()
+    for m_ in ora.modules():
+        if isinstance(m_, torch.nn.BatchNorm2d):
+            m_.momentum = 1.0
+    with torch.no_grad():
+        ora.logits(x)
+    mine.load_state_dict(ora.state_dict(), strict=True)
+    ora.eval()
     mine = mine.cuda().eval()
-    with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
-        logit = ora.logits(x)
-        prob_ref = logit.softmax(dim=1)
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        logit32 = ora.logits(x)
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            logit_bf = ora.logits(x)
     prob, mask = mine._engine().forward_eval(x, return_mask=True)
     torch.cuda.synchronize()
-    ref_mask = prob_ref.argmax(dim=1)
-    agree = float((mask.long() == ref_mask).float().mean())
-    print('mask agreement', agree, 'prob rel', _rel(prob, prob_ref))
-    assert _rel(prob, prob_ref) < 2e-2
-    assert agree > 0.98
+    mine_logits = mine.engine.last_logits.float().permute(0, 3, 1, 2)[:, :k]
+    top2 = logit32.topk(2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    band = 6.0 * float((logit_bf.float() - logit32).pow(2).mean().sqrt())  # 6 x RMS bf16-vs-fp32 logit noise
+    ref_mask = logit32.argmax(dim=1)
+    confident = margin > band
+    agree_all = float((mask.long() == ref_mask).float().mean())
+    agree_bf = float((logit_bf.argmax(dim=1) == ref_mask).float().mean())
+    agree_conf = float((mask.long() == ref_mask)[confident].float().mean())
+    rep = dict(logit_rel_mine_vs_bf16=_rel(mine_logits, logit_bf.float()), logit_rel_bf16_vs_fp32=_rel(logit_bf.float(), logit32),
+               mask_agree_all=agree_all, mask_agree_bf16_oracle_vs_fp32=agree_bf, mask_agree_confident=agree_conf,
+               confident_frac=float(confident.float().mean()), prob_rel=_rel(prob, logit_bf.float().softmax(dim=1)))
+    print(json.dumps(rep))
+    json.dump(rep, open('gpurun_out/eval_masks.json', 'w'), indent=1)
+    assert rep['logit_rel_mine_vs_bf16'] < max(2e-2, 1.5 * rep['logit_rel_bf16_vs_fp32'])
+    assert agree_conf >= 0.999
+    assert agree_all >= agree_bf - 0.01

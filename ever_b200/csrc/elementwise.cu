@@ -54,26 +54,44 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
           if (mask_mode == 2) { sc[j] = scale[gg * 8 + j]; sh[j] = shift[gg * 8 + j]; }
         }
       }
-      for (long long r = r0 + rsub; r < r1; r += rows_par) {
-        float xv[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(x + r * C + gg * 8), xv);
-        if (MODE == 0) {
+      constexpr int UN = MODE == 0 ? 4 : 2;
+      for (long long rb = r0 + rsub; rb < r1; rb += (long long)rows_par * UN) {
+        bf16x8 xq[UN], gq[UN], yq[UN];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { s0[j] += xv[j]; s1[j] += xv[j] * xv[j]; }
-        } else {
-          float gv[8];
-          unpack8(*reinterpret_cast<const bf16x8*>(dy + r * C + gg * 8), gv);
-          if (mask_mode == 1) {
-            float yv[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(ymask + r * C + gg * 8), yv);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
-          } else if (mask_mode == 2) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) gv[j] = bf16_round(xv[j] * sc[j] + sh[j]) > 0.f ? gv[j] : 0.f;
+        for (int u = 0; u < UN; ++u) {
+          const long long r = rb + (long long)u * rows_par;
+          if (r < r1) {
+            xq[u] = *reinterpret_cast<const bf16x8*>(x + r * C + gg * 8);
+            if (MODE == 1) {
+              gq[u] = *reinterpret_cast<const bf16x8*>(dy + r * C + gg * 8);
+              if (mask_mode == 1) yq[u] = *reinterpret_cast<const bf16x8*>(ymask + r * C + gg * 8);
+            }
           }
+        }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { s0[j] += gv[j]; s1[j] += gv[j] * (xv[j] - mu[j]) * rs[j]; }
+        for (int u = 0; u < UN; ++u) {
+          const long long r = rb + (long long)u * rows_par;
+          if (r >= r1) continue;
+          float xv[8];
+          unpack8(xq[u], xv);
+          if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s0[j] += xv[j]; s1[j] += xv[j] * xv[j]; }
+          } else {
+            float gv[8];
+            unpack8(gq[u], gv);
+            if (mask_mode == 1) {
+              float yv[8];
+              unpack8(yq[u], yv);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
+            } else if (mask_mode == 2) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) gv[j] = bf16_round(xv[j] * sc[j] + sh[j]) > 0.f ? gv[j] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s0[j] += gv[j]; s1[j] += gv[j] * (xv[j] - mu[j]) * rs[j]; }
+          }
         }
       }
     }
@@ -162,36 +180,55 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
   if (dbeta) { if (accumulate) dbeta[c] += (float)s; else dbeta[c] = (float)s; }
 }
 
-// y = act( bf16(x*scale+shift) [+ res] )
+// y = act( bf16(x*scale+shift) [+ res] ).  blockDim is a multiple of C/8, so a thread's channel group is fixed and
+// the per-channel constants are hoisted; UN vectors are kept in flight per thread.
 __global__ void __launch_bounds__(kEwThreads)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                 const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, long long nvec, int C, int relu) {
+  constexpr int UN = 4;
   const int cg = C / 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cg) * 8;
-    float v[8];
-    unpack8(reinterpret_cast<const bf16x8*>(x)[i], v);
-    const float4 a0 = *reinterpret_cast<const float4*>(scale + c0), a1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(shift + c0), b1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
-    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int c0 = (int)(tid % cg) * 8;
+  float a[8], b[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = v[j] * a[j] + b[j];
-    if (res) {
-      float rv[8];
-      unpack8(reinterpret_cast<const bf16x8*>(res)[i], rv);
+  for (int j = 0; j < 8; ++j) { a[j] = scale[c0 + j]; b[j] = shift[c0 + j]; }
+  for (long long i0 = tid; i0 < nvec; i0 += stride * UN) {
+    bf16x8 xv[UN], rv[UN];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = bf16_round(v[j]) + rv[j];
+    for (int u = 0; u < UN; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < nvec) {
+        xv[u] = reinterpret_cast<const bf16x8*>(x)[i];
+        if (res) rv[u] = reinterpret_cast<const bf16x8*>(res)[i];
+      }
     }
-    if (relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    for (int u = 0; u < UN; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < nvec) {
+        float v[8];
+        unpack8(xv[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = v[j] * a[j] + b[j];
+        if (res) {
+          float r[8];
+          unpack8(rv[u], r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = bf16_round(v[j]) + r[j];
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        reinterpret_cast<bf16x8*>(y)[i] = pack8(v);
+      }
     }
-    reinterpret_cast<bf16x8*>(y)[i] = pack8(v);
   }
 }
 
-// dx = scale * (g - (dbeta + xhat * dgamma) / M),  g = dy * mask ;  optional dres (+)= g
+// dx = scale * (g - (dbeta + xhat * dgamma) / M) = a*g + k0 - c2*x,  g = dy * mask ;  optional dres (+)= g
+//   c2 = a * rstd * dgamma / M,  k0 = c2 * mean - a * dbeta / M   (hoisted per channel)
 __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                     const __nv_bfloat16* __restrict__ ymask, const float* __restrict__ mean,
@@ -199,45 +236,69 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                     const float* __restrict__ dgamma, const float* __restrict__ dbeta, int mask_mode, int frozen,
                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres, int dres_acc, long long nvec, int C,
                     float inv_m) {
+  constexpr int UN = 2;
   const int cg = C / 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cg) * 8;
-    float g[8], xv[8];
-    unpack8(reinterpret_cast<const bf16x8*>(dy)[i], g);
-    unpack8(reinterpret_cast<const bf16x8*>(x)[i], xv);
-    if (mask_mode == 1) {
-      float yv[8];
-      unpack8(reinterpret_cast<const bf16x8*>(ymask)[i], yv);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int c0 = (int)(tid % cg) * 8;
+  float a[8], k0[8], c2[8], sh[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
-    } else if (mask_mode == 2) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = bf16_round(xv[j] * scale[c0 + j] + shift[c0 + j]) > 0.f ? g[j] : 0.f;
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    a[j] = scale[c];
+    sh[j] = shift[c];
+    if (frozen) { c2[j] = 0.f; k0[j] = 0.f; }
+    else {
+      c2[j] = a[j] * rstd[c] * dgamma[c] * inv_m;
+      k0[j] = c2[j] * mean[c] - a[j] * dbeta[c] * inv_m;
     }
-    if (dres) {
-      float d[8];
-      if (dres_acc) {
-        unpack8(reinterpret_cast<const bf16x8*>(dres)[i], d);
+  }
+  for (long long i0 = tid; i0 < nvec; i0 += stride * UN) {
+    bf16x8 gv[UN], xv[UN], yv[UN], dv[UN];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] += g[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = g[j];
-      }
-      reinterpret_cast<bf16x8*>(dres)[i] = pack8(d);
-    }
-    float o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      if (frozen) {
-        o[j] = g[j] * scale[c];
-      } else {
-        const float xh = (xv[j] - mean[c]) * rstd[c];
-        o[j] = scale[c] * (g[j] - (dbeta[c] + xh * dgamma[c]) * inv_m);
+    for (int u = 0; u < UN; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < nvec) {
+        gv[u] = reinterpret_cast<const bf16x8*>(dy)[i];
+        xv[u] = reinterpret_cast<const bf16x8*>(x)[i];
+        if (mask_mode == 1) yv[u] = reinterpret_cast<const bf16x8*>(ymask)[i];
+        if (dres && dres_acc) dv[u] = reinterpret_cast<const bf16x8*>(dres)[i];
       }
     }
-    reinterpret_cast<bf16x8*>(dx)[i] = pack8(o);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < nvec) {
+        float g[8], xf[8];
+        unpack8(gv[u], g);
+        unpack8(xv[u], xf);
+        if (mask_mode == 1) {
+          float yf[8];
+          unpack8(yv[u], yf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = yf[j] > 0.f ? g[j] : 0.f;
+        } else if (mask_mode == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = bf16_round(xf[j] * a[j] + sh[j]) > 0.f ? g[j] : 0.f;
+        }
+        if (dres) {
+          float d[8];
+          if (dres_acc) {
+            unpack8(dv[u], d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] += g[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] = g[j];
+          }
+          reinterpret_cast<bf16x8*>(dres)[i] = pack8(d);
+        }
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = a[j] * g[j] + k0[j] - c2[j] * xf[j];
+        reinterpret_cast<bf16x8*>(dx)[i] = pack8(o);
+      }
+    }
   }
 }
 
@@ -637,7 +698,10 @@ extern "C" int evb_bn_apply(const void* x, const float* scale, const float* shif
                             int C, int relu, void* stream) {
   if (C % 8) return EVB_ERR_ARG;
   const long long nvec = M * C / 8;
-  bn_apply_kernel<<<ew_blocks(nvec, kEwThreads * 4), kEwThreads, 0, ST>>>((const __nv_bfloat16*)x, scale, shift,
+  const int cg_ = C / 8;
+  if (cg_ > kEwThreads) return EVB_ERR_ARG;
+  const int bt = (kEwThreads / cg_) * cg_;
+  bn_apply_kernel<<<ew_blocks(nvec, bt * 4), bt, 0, ST>>>((const __nv_bfloat16*)x, scale, shift,
                                                                        (const __nv_bfloat16*)res, (__nv_bfloat16*)y, nvec,
                                                                        C, relu);
   return LAUNCH_OK();
@@ -657,7 +721,8 @@ extern "C" int evb_bn_bwd(const void* dy, const void* x, const void* ymask, cons
   float* fresh = (float*)ws + (size_t)nb * 2 * C;
   bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, ST>>>((const float*)ws, nb, C, dgamma, dbeta, param_acc, fresh);
   const long long nvec = M * C / 8;
-  bn_bwd_apply_kernel<<<ew_blocks(nvec, kEwThreads * 4), kEwThreads, 0, ST>>>(
+  const int bt = (kEwThreads / (C / 8)) * (C / 8);
+  bn_bwd_apply_kernel<<<ew_blocks(nvec, bt * 2), bt, 0, ST>>>(
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ymask, mean, rstd, scale, shift, fresh + C,
       fresh, mask_mode, frozen, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, dres_acc, nvec, C, 1.0f / (float)M);
   return LAUNCH_OK();

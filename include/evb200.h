@@ -1,0 +1,123 @@
+/* libevb200.so -- C ABI of the B200-native FarSeg/ChangeStar hot path.
+ *
+ * The reference (Z-Zheng/ever) is pure Python over PyTorch: it has no FFI of its own.  The boundary this
+ * library replaces is therefore the ATen op each reference nn.Module call dispatches to; every entry point
+ * below names the reference call site (file:line under the reference tree) it stands in for.  INTEGRATION.md
+ * shows the ctypes stub a maintainer binds these with from ever's own Python.
+ *
+ * Conventions
+ *   - return value: 0 = EVB_OK, 1 = bad argument, 2 = CUDA launch/runtime error, 3 = driver entry point missing.
+ *     Nothing throws across the boundary; evb_last_cuda_error() gives the CUDA error string.
+ *   - all buffers are caller-allocated DEVICE memory (raw pointers); no hidden allocation: kernels that need
+ *     scratch take a workspace pointer sized by the matching *_workspace() query.
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it (no synchronisation).
+ *   - activations: NHWC bf16 (channels contiguous), C % 8 == 0 (C % 64 == 0 for convolution operands);
+ *     parameters / statistics / gradients of parameters: fp32; labels: int64, ignore_index = 255.
+ *   - one host thread per GPU (one process per GPU); the library keeps no global state except cached
+ *     kernel attributes.
+ */
+#ifndef EVB200_H_
+#define EVB200_H_
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int evb_version(void);
+const char* evb_last_cuda_error(void);
+int evb_device_sync_check(void);
+
+/* ---- convolution (tcgen05 implicit GEMM).  Replaces nn.Conv2d forward/backward:
+ * ever/module/_resnets.py:21-29,139-150 (ResNet 3x3/1x1/stem), ever/module/ops.py:53-55 (ConvBlock),
+ * ever/module/fpn.py:165,179 (decoder, classifier), ever/module/fs_relation.py:25-27,42,49. */
+/* y[N,H/s,W/s,Cout] = conv(x[N,H,W,Cin]) (+bias[Cout] fp32) (+add).  ksize 1|3, pad ksize/2, stride 1|2.
+ * wpk: bf16 [ksize*ksize][w_rows>=Cout][Cin].  add_mode 0 none | 1 same-shape bf16 | 2 half-resolution bf16
+ * sampled nearest (FPN top-down add, ever/module/fpn.py:96-105).  force_nt: 0 = auto tile, else 64|128|256. */
+int evb_conv2d_fwd(const void* x, int N, int H, int W, int Cin, const void* wpk, int w_rows, int ksize, int stride,
+                   void* y, int Cout, const float* bias, const void* add, int add_mode, int force_nt, void* stream);
+/* dx[N,H,W,Cin] (+)= conv_transpose(dy[N,Ho,Wo,Cout]).  wpk_t: bf16 [ksize*ksize][w_rows>=Cin][Cout]. */
+int evb_conv2d_dgrad(const void* dy, int N, int Ho, int Wo, int Cout, const void* wpk_t, int w_rows, int ksize,
+                     int stride, void* dx, int H, int W, int Cin, int accumulate, int force_nt, void* stream);
+/* dw[Cout][Cin][k][k] fp32 (+)= x (*) dy, split-K over pixels with deterministic reduction. */
+long long evb_conv2d_wgrad_workspace(int N, int Ho, int Wo, int Cin, int Cout, int ksize, int force_nt, int force_split);
+int evb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, const void* dy, int Cout, int ksize, int stride,
+                     float* dw, int accumulate, void* ws, long long ws_bytes, int force_nt, int force_split, void* stream);
+/* fp32 OIHW master weights -> bf16 packs [kk][CoP][CiP] (forward) and [kk][CiPb][CoPb] (dgrad), zero padded. */
+int evb_pack_weight(const float* w, int Co, int Ci, int kk, void* wf, int CoP, int CiP, void* wb, int CiPb, int CoPb,
+                    void* stream);
+/* every convolution of a model in one launch; desc: int64[n][12], block_map: int32[nblocks] (see elementwise.cu) */
+int evb_pack_weights_batched(const void* desc, const void* block_map, int nblocks, void* stream);
+/* 7x7 stride-2 pad-3 stem lowered to a GEMM: x NCHW fp32 -> A[N*H/2*W/2][KP] bf16, k = c*49 + r*7 + s
+ * (ResNet.stem_forward, ever/module/_resnets.py:205-212). */
+int evb_stem_im2col(const float* x, void* a, int N, int Cin, int H, int W, int KP, void* stream);
+
+/* ---- BatchNorm2d (+ReLU, + residual add).  Replaces nn.BatchNorm2d / nn.ReLU / `out += identity`:
+ * ever/module/_resnets.py:46-49,58,66-67,83-87,97,101,109-110; fpn.py:166-167; fs_relation.py:43-44,50-51. */
+long long evb_bn_workspace(long long M, int C);
+/* training statistics of x[M,C] -> mean, rstd, folded scale/shift; running stats updated (momentum, unbiased var) */
+int evb_bn_stats(const void* x, long long M, int C, const float* gamma, const float* beta, float* running_mean,
+                 float* running_var, float momentum, float eps, float* mean, float* rstd, float* scale, float* shift,
+                 void* ws, void* stream);
+/* eval / frozen BN: fold running statistics (ever/module/resnet.py:155-160,227-234) */
+int evb_bn_fold(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C, float* scale,
+                float* shift, float* mean, float* rstd, void* stream);
+/* y = act(bf16(x*scale+shift) [+ res]) */
+int evb_bn_apply(const void* x, const float* scale, const float* shift, const void* res, void* y, long long M, int C,
+                 int relu, void* stream);
+/* backward of the above.  mask_mode 0 none | 1 (ymask>0) | 2 recomputed from x.  dres (+)= masked dy. */
+int evb_bn_bwd(const void* dy, const void* x, const void* ymask, const float* mean, const float* rstd, const float* scale,
+               const float* shift, int mask_mode, int frozen, void* dx, void* dres, int dres_acc, float* dgamma,
+               float* dbeta, int param_acc, long long M, int C, void* ws, void* stream);
+/* db[C] (+)= column sums of dy[M,C]  (conv bias gradient) */
+int evb_bias_grad(const void* dy, long long M, int C, float* db, float* unused, int accumulate, void* ws, void* stream);
+
+/* ---- pooling / resampling.  nn.MaxPool2d(3,2,1) ever/module/_resnets.py:153; nn.UpsamplingBilinear2d via
+ * Bf16compatible ever/module/ops.py:152-166, fpn.py:168,180; nearest x2 backward fpn.py:100;
+ * sum(list)/len fpn.py:189; F.adaptive_avg_pool2d fs_relation.py:177. */
+int evb_maxpool3x3s2_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, void* stream);
+int evb_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, void* stream);
+/* y[N,f*h,f*w,:C] = bilinear(align_corners)(act(x)); act = bf16(relu(x*scale+shift)) when scale != NULL.
+ * ldx / ldy: elements per pixel of the input / output rows. */
+int evb_bilinear_up(const void* x, const float* scale, const float* shift, void* y, int N, int h, int w, int C, int ldx,
+                    int ldy, int f, void* stream);
+int evb_bilinear_up_bwd(const void* dy, void* dx, int N, int h, int w, int C, int lddy, int lddx, int f, void* stream);
+int evb_sumpool2(const void* dfine, void* dcoarse, int N, int h, int w, int C, int accumulate, void* stream);
+int evb_merge4(const void* a, const void* b, const void* c, const void* d, void* out, long long numel, void* stream);
+int evb_scale_add(const void* x, float alpha, const void* z, void* y, long long numel, void* stream);
+int evb_gap_fwd(const void* x, float* out, int N, int HW, int C, void* stream);
+int evb_gap_bwd(const float* dscene, void* dx, int N, int HW, int C, void* stream);
+int evb_copy2d_f32(const float* src, int lds, float* dst, int ldd, int rows, int cols, int accumulate, void* stream);
+
+/* ---- FS-Relation (FSRelation.forward, ever/module/fs_relation.py:57-73) and the scene-embedding MLP (:22-28) */
+int evb_relation_fwd(const void* u1, const void* u2, const float* scale1, const float* shift1, const float* scale2,
+                     const float* shift2, const float* sf, void* z, float* rel, long long M, int HW, int C, void* stream);
+int evb_relation_bwd(const void* dz, const void* u1, const void* u2, const float* scale1, const float* shift1,
+                     const float* scale2, const float* shift2, const float* sf, const float* rel, void* g1, void* g2,
+                     float* dsf, long long M, int HW, int C, void* stream);
+int evb_linear_fwd(const float* x, const float* W, const float* b, float* y, int N, int I, int O, int relu, void* stream);
+int evb_linear_bwd(const float* dy, const float* y, const float* x, const float* W, float* dW, float* db, float* dx, int N,
+                   int I, int O, int relu, int acc_w, int acc_x, void* stream);
+
+/* ---- loss: F.cross_entropy(ignore_index=255) + dice_loss_with_logits (ever/module/loss.py:54-75, select :26-37,
+ * dice_coeff :40-51).  stats = {sum -log p_t, n_valid, I_c[K], sum p_c[K], sum y_c[K]}; the caller may all-reduce
+ * stats+2 (3K floats) across ranks between evb_loss_stats and evb_loss_finalize (all_reduce_sum, loss.py:20-23). */
+long long evb_loss_workspace(long long P, int K);
+int evb_loss_stats(const void* logits, const void* labels, long long P, int K, int LD, int ignore_index, float* stats,
+                   void* ws, void* stream);
+int evb_loss_finalize(const float* stats, const float* dice_stats, int K, float smooth, float ce_weight, float dice_weight,
+                      float dice_grad_scale, float* losses, float* coef, void* stream);
+int evb_loss_grad(const void* logits, const void* labels, long long P, int K, int LD, int ignore_index, const float* coef,
+                  void* dlogits, void* stream);
+/* eval: prob[N,K,H,W] fp32 = softmax, mask[P] uint8 = argmax (logit.softmax(dim=1)) */
+int evb_softmax_nchw(const void* logits, float* prob, void* mask, long long P, int HW, int K, int LD, void* stream);
+
+/* ---- optimizer step over flat fp32 arenas: clip_grad_norm_ + torch.optim.SGD + zero_grad
+ * (ERModule.apply_gradients / clip_grad, ever/interface/module.py:83-108; ever/opt/optimizer.py:7-9) */
+long long evb_sgd_workspace(long long n);
+int evb_grad_norm(const float* g, long long n, float max_norm, float* norm_out, void* ws, void* stream);
+int evb_sgd_step(float* w, float* g, float* mom, long long n, const float* lr, float momentum, float wd,
+                 const float* clip, int first_step, int zero_grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVB200_H_ */

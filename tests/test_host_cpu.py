@@ -1,0 +1,183 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports everything include/evb200.h declares, the plugin
+module mirrors the reference's state_dict / registry contract, the product path refuses to run without CUDA, and the
+multi-rank loss rule used by the engine (global Dice statistics, Dice gradient x world, gradient all-reduce AVG)
+reproduces the reference's DDP semantics on 2 gloo ranks."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_header_symbols():
+    import ctypes
+    from ever_b200 import build
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    hdr = open(os.path.join(ROOT, 'include', 'evb200.h')).read()
+    names = sorted(set(re.findall(r'\b(evb_[a-z0-9_]+)\s*\(', hdr)))
+    assert len(names) >= 35
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.evb_version() >= 100
+    # and nothing exported that the header does not declare
+    out = subprocess.check_output(['nm', '-D', '--defined-only', path], text=True)
+    exported = sorted(set(re.findall(r' T (evb_[a-z0-9_]+)$', out, flags=re.M)))
+    assert set(exported) <= set(names), set(exported) - set(names)
+
+
+def test_sass_has_tcgen05_and_tma():
+    """The built library really contains Blackwell tensor-core / TMA instructions (UTC*MMA, UTMALDG, LDTM)."""
+    from ever_b200 import build
+    path = build.build()
+    cuobjdump = '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    sass = subprocess.run([cuobjdump, '-sass', path], capture_output=True, text=True).stdout
+    assert 'UTCHMMA' in sass or 'UTCMMA' in sass
+    assert 'UTMALDG' in sass
+    assert 'LDTM' in sass
+
+
+@pytest.mark.parametrize('resnet,k,dec', [('resnet18', 5, 128), ('resnet50', 15, 256), ('resnet101', 7, 256)])
+def test_state_dict_contract(resnet, k, dec):
+    from ever_b200.module import FarSegB200
+    from oracle.farseg_oracle import FarSegOracle
+    m = FarSegB200(dict(encoder=dict(resnet_type=resnet),
+                        head=dict(fpn_decoder=dict(out_channels=dec, classifier_config=dict(num_classes=k)))))
+    o = FarSegOracle(resnet, k, dec)
+    a = [(n, tuple(v.shape), v.dtype) for n, v in m.state_dict().items()]
+    b = [(n, tuple(v.shape), v.dtype) for n, v in o.state_dict().items()]
+    assert a == b
+    assert [n for n, _ in m.named_parameters()] == [n for n, _ in o.named_parameters()]
+    m.load_state_dict(o.state_dict(), strict=True)
+
+
+def test_registry_and_config_merge():
+    from ever_b200._ever_api import MODEL, ERModule
+    from ever_b200.module import FarSegB200
+    assert MODEL['FarSegB200'] is FarSegB200 and MODEL['FarSeg'] is FarSegB200
+    assert issubclass(FarSegB200, ERModule)
+    m = FarSegB200(dict(encoder=dict(resnet_type='resnet18'),
+                        head=dict(fpn_decoder=dict(classifier_config=dict(num_classes=5)))))
+    # recursive merge keeps defaults the user did not override (ever/core/config.py:76-89)
+    assert m.config.head.fpn_decoder.out_channels == 256
+    assert m.config.head.fpn_decoder.classifier_config.scale_factor == 4.0
+    assert tuple(m.config.head.fpn.in_channels_list) == (64, 128, 256, 512)
+    assert 'GLOBAL' in m.config
+
+
+def test_no_cpu_fallback():
+    from ever_b200.module import FarSegB200
+    m = FarSegB200(dict(encoder=dict(resnet_type='resnet18'),
+                        head=dict(fpn_decoder=dict(classifier_config=dict(num_classes=5))))).train()
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        m(torch.zeros(1, 3, 64, 64), dict(cls=torch.zeros(1, 64, 64, dtype=torch.long)))
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/ever'), reason='reference tree only exists in the build container')
+def test_make_model_through_real_ever():
+    """With the real reference on the path the plugin registers into ever.registry.MODEL and
+    ever.core.builder.make_model builds it from a reference-style config dict."""
+    code = r'''
+import sys
+sys.path.insert(0, "/root/reference"); sys.path.insert(0, "%s/tests/golden/_stubs"); sys.path.insert(0, "%s")
+import ever as er
+from ever.core.builder import make_model
+import ever_b200.module as mod
+from ever_b200._ever_api import HAVE_EVER
+assert HAVE_EVER and issubclass(mod.FarSegB200, er.ERModule)
+cfg = dict(type="FarSegB200", params=dict(encoder=dict(resnet_type="resnet18"),
+           head=dict(fpn_decoder=dict(out_channels=128, classifier_config=dict(num_classes=5)))))
+m = make_model(cfg)
+assert isinstance(m, mod.FarSegB200)
+assert len(m.custom_param_groups()) == 1
+assert "en.resnet.layer1.0.conv1.weight" in m.state_dict()
+print("OK")
+''' % (ROOT, ROOT)
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
+    assert 'OK' in out.stdout, out.stderr[-2000:]
+
+
+# ---------------------------------------------------------------------------------------------- 2-rank gloo
+def _engine_loss_rule(logit, labels, k, world, dice_all_reduce):
+    """torch restatement of evb_loss_stats / evb_loss_finalize / evb_loss_grad (head_loss.cu): returns the per-rank
+    logit gradient the engine forms BEFORE the gradient all-reduce (AVG)."""
+    flat = logit.permute(0, 2, 3, 1).reshape(-1, k).float()
+    t = labels.reshape(-1)
+    valid = t != 255
+    p = flat.softmax(dim=1)
+    onehot = F.one_hot(t.clamp(max=k - 1), k).float() * valid[:, None]
+    pv = p * valid[:, None]
+    inter, sp, sy = (pv * onehot).sum(0), pv.sum(0), onehot.sum(0)
+    stats = torch.cat([inter, sp, sy])
+    stats = dice_all_reduce(stats)
+    inter, sp, sy = stats[:k], stats[k:2 * k], stats[2 * k:]
+    z = sp + sy + 1.0
+    a = world * 2.0 / (k * z)
+    b = world * (2 * inter + 1.0) / (k * z * z)
+    g = b[None, :] - onehot * a[None, :]
+    dot = (p * g).sum(1, keepdim=True)
+    d = (p - onehot) / valid.sum() + p * (g - dot)
+    d = d * valid[:, None]
+    return d.reshape(logit.shape[0], logit.shape[2], logit.shape[3], k).permute(0, 3, 1, 2)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from torch.distributed.nn import all_reduce as ar
+    from oracle.farseg_oracle import dice_loss_oracle
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    k = 4
+    conv = torch.nn.Conv2d(8, k, 1)
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randn(2, 8, 16, 16, generator=g)
+    y = torch.randint(0, k, (2, 16, 16), generator=g)
+    y[torch.rand(2, 16, 16, generator=g) < (0.05 + 0.2 * rank)] = 255   # different ignore counts per rank
+    # reference semantics: DDP (grad mean over ranks) + differentiable all-reduce inside Dice (loss.py:20-23,46-48)
+    logit = conv(x)
+    loss = F.cross_entropy(logit, y, ignore_index=255) + dice_loss_oracle(logit, y, all_reduce=lambda v: ar(v))
+    loss.backward()
+    ref = [p.grad.clone() for p in conv.parameters()]
+    for r in ref:
+        dist.all_reduce(r)
+        r /= world
+    # engine rule
+    conv.zero_grad()
+    logit = conv(x)
+
+    def red(v):
+        v = v.clone()
+        dist.all_reduce(v)
+        return v
+    d = _engine_loss_rule(logit.detach(), y, k, world, red)
+    logit.backward(d)
+    mine = [p.grad.clone() for p in conv.parameters()]
+    for m_ in mine:
+        dist.all_reduce(m_)
+        m_ /= world
+    err = max(float((a - b).abs().max() / (b.abs().max() + 1e-12)) for a, b in zip(mine, ref))
+    if rank == 0:
+        q.put(err)
+    dist.destroy_process_group()
+
+
+def test_two_rank_loss_rule_matches_ddp_reference():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) < 1e-5

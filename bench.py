@@ -161,10 +161,17 @@ def run_b200(args):
     import torch.distributed as dist
     from ever_b200 import _lib
     from ever_b200.module import FarSegB200
+    T0 = time.time()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
+
+    def log(msg):
+        if os.environ.get('EVB_BENCH_VERBOSE', '1') == '1':
+            sys.stderr.write('[bench rank %d %.1fs] %s\n' % (rank, time.time() - T0, msg))
+            sys.stderr.flush()
+
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.manual_seed(0)
@@ -173,6 +180,8 @@ def run_b200(args):
     eng.set_distributed(rank, world)
     if world > 1:  # same initial weights everywhere (DDP broadcasts rank 0's at construction)
         dist.broadcast(eng.flat_w, 0)
+        torch.cuda.synchronize()
+    log('model built, nccl ok')
     xh, yh = synthetic(PER_GPU_BATCH, seed=rank)
     xh, yh = xh.pin_memory(), yh.pin_memory()
     x, y = xh.cuda(), yh.cuda()
@@ -188,6 +197,7 @@ def run_b200(args):
     graph = None
     l0 = _lib.launches[0]
     if use_graph:
+        log('capturing step graph')
         graph, out = eng.capture_step(x, y)
         per_step_launches = (_lib.launches[0] - l0) // 3 + 3
     else:
@@ -198,16 +208,18 @@ def run_b200(args):
     def step():
         nonlocal out
         if graph is not None:
-            graph.replay()
+            graph()
         else:
             out = eng.forward_train(x, y)
             eng.backward(allreduce=False)
         eng.allreduce_grads()
         eng.sgd_step(lr)
 
+    log('graph ready, warm-up')
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
+    log('timing')
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -227,6 +239,7 @@ def run_b200(args):
     value = world * PER_GPU_BATCH / (ms * 1e-3)
     loss_now = {k: float(v) for k, v in out.items()}
 
+    log('value done: %.2f ms/step' % ms)
     # ---- e2e: plugin API with host buffers
     e2e_steps = max(3, min(args.steps, 10))
 
@@ -234,7 +247,7 @@ def run_b200(args):
         x.copy_(xh, non_blocking=True)
         y.copy_(yh, non_blocking=True)
         if graph is not None:
-            graph.replay()
+            graph()
             o = out
         else:
             o = model(x, dict(cls=y))

@@ -558,7 +558,8 @@ class FarSegEngine:
         return cls, logits
 
     # ------------------------------------------------------------------ public steps
-    def forward_train(self, x, labels):
+    def _forward_part1(self, x, labels):
+        """pack weights, encoder, head, loss statistics (everything before the Dice all-reduce)."""
         L = self.L
         self.tape = []
         self._bn_tracked = []
@@ -577,23 +578,40 @@ class FarSegEngine:
         ws = self._ws(L.evb_loss_workspace(c_ll(npx), c_int(k)))
         check(L.evb_loss_stats(ptr(logits), ptr(labels), c_ll(npx), c_int(k), c_int(16), c_int(self.ignore_index),
                                ptr(stats), ptr(ws), stream()), 'evb_loss_stats')
-        dice_stats = stats[2:]
-        scale = 1.0
+        if self._bn_tracked:
+            torch._foreach_add_([bn.num_batches_tracked for bn in self._bn_tracked], 1)
+        self._part1 = (cls, logits, labels, stats, npx)
+        if self.world > 1 and self.sync_dice:
+            if getattr(self, '_dice_global', None) is None:
+                self._dice_global = torch.zeros(3 * k, dtype=torch.float32, device=self.dev)
+
+    def _dice_allreduce(self):
+        """all_reduce_sum of the Dice statistics (ever/module/loss.py:20-23,46-48); eager NCCL, never graph-captured."""
         if self.world > 1 and self.sync_dice:
             import torch.distributed as dist
-            dice_stats = stats[2:].clone()
-            dist.all_reduce(dice_stats)
-            scale = float(self.world)
+            self._dice_global.copy_(self._part1[3][2:])
+            dist.all_reduce(self._dice_global)
+
+    def _forward_part2(self):
+        L = self.L
+        cls, logits, labels, stats, npx = self._part1
+        k = self.K
+        glob = self.world > 1 and self.sync_dice
+        dice_stats = self._dice_global if glob else stats[2:]
+        scale = float(self.world) if glob else 1.0
         losses = self._new(2, dtype=torch.float32)
         coef = self._new(1 + 2 * k, dtype=torch.float32)
         check(L.evb_loss_finalize(ptr(stats), ptr(dice_stats), c_int(k), c_float(self.smooth), c_float(self.ce_w),
                                   c_float(self.dice_w), c_float(scale), ptr(losses), ptr(coef), stream()),
               'evb_loss_finalize')
         self._saved_for_backward = (cls, logits, labels, coef, npx)
-        if self._bn_tracked:
-            torch._foreach_add_([bn.num_batches_tracked for bn in self._bn_tracked], 1)
         return dict(ce_loss=losses[0] * self.ce_w if self.ce_w != 1.0 else losses[0],
                     dice_loss=losses[1] * self.dice_w if self.dice_w != 1.0 else losses[1])
+
+    def forward_train(self, x, labels):
+        self._forward_part1(x, labels)
+        self._dice_allreduce()
+        return self._forward_part2()
 
     def backward(self, allreduce=True):
         L = self.L
@@ -647,8 +665,9 @@ class FarSegEngine:
 
     # ------------------------------------------------------------------ CUDA-graph step
     def capture_step(self, x, labels):
-        """Capture forward + loss + backward for fixed-shape device inputs into one CUDA graph.
-        Returns (graph, losses dict).  The gradient all-reduce and the optimizer run after the replay."""
+        """Capture forward + loss + backward for fixed-shape device inputs into CUDA graph(s).
+        Returns (replay_fn, losses dict).  NCCL is never captured: with world > 1 the step is two graphs with the
+        (eager) Dice-statistics all-reduce between them; the gradient all-reduce and the optimizer run after."""
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -658,11 +677,28 @@ class FarSegEngine:
                 self.backward(allreduce=False)
         cur.wait_stream(side)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            out = self.forward_train(x, labels)
+        split = self.world > 1 and self.sync_dice
+        pool = torch.cuda.graph_pool_handle()
+        g1 = torch.cuda.CUDAGraph()
+        if not split:
+            with torch.cuda.graph(g1, pool=pool):
+                out = self.forward_train(x, labels)
+                self.backward(allreduce=False)
+            return g1.replay, out
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1, pool=pool):
+            self._forward_part1(x, labels)
+        self._dice_allreduce()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g2, pool=pool):
+            out = self._forward_part2()
             self.backward(allreduce=False)
-        return g, out
+
+        def replay():
+            g1.replay()
+            self._dice_allreduce()
+            g2.replay()
+        return replay, out
 
     @torch.no_grad()
     def forward_eval(self, x, return_mask=False):

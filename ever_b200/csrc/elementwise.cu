@@ -12,6 +12,7 @@
 namespace evb {
 
 constexpr int kEwThreads = 256;
+constexpr int kNbPad = 320;   // stride of the per-channel partial rows; colsum grids are capped at 296 blocks (2 per SM)
 
 static inline int ew_blocks(long long work, int per_block, int cap = 148 * 16) {
   long long b = (work + per_block - 1) / per_block;
@@ -24,7 +25,8 @@ static inline int ew_blocks(long long work, int per_block, int cap = 148 * 16) {
 // Per-channel sums over M rows of an [M, C] bf16 matrix.  MODE 0: sum x, sum x^2.
 // MODE 1 (BN backward): g = dy * mask, sums g and g * xhat, xhat = (x - mean) * rstd.
 //   mask_mode 0: none; 1: (ymask > 0) from a stored post-activation tensor; 2: (x*scale+shift > 0) recomputed.
-// Output: partial[block][2][C] fp32 (reduced in fixed order by the finalize kernels -> deterministic).
+// Output: partial[which][C][kNbPad] fp32, one column per block (reduced in fixed order by the finalize kernels ->
+// deterministic; a warp reads a channel's partials coalesced).
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(kEwThreads)
@@ -106,7 +108,7 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
     const int gg = c / 8, j = c % 8;
     float acc = 0.f;
     for (int rs_ = 0; rs_ < rows_par; ++rs_) acc += sm[((size_t)rs_ * cg + gg) * 16 + which * 8 + j];
-    partial[((size_t)blockIdx.x * 2 + which) * C + c] = acc;
+    partial[((size_t)which * C + c) * kNbPad + blockIdx.x] = acc;
   }
 }
 
@@ -122,9 +124,12 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
                                                 double& ss) {
   const int lane = threadIdx.x & 31;
   double a = 0.0, b = 0.0;
-  for (int k = lane; k < nblk; k += 32) {
-    a += partial[((size_t)k * 2) * C + c];
-    b += partial[((size_t)k * 2 + 1) * C + c];
+  const float* pa = partial + (size_t)c * kNbPad;
+  const float* pb = partial + ((size_t)C + c) * kNbPad;
+#pragma unroll
+  for (int j = 0; j < kNbPad / 32; ++j) {
+    const int k = lane + 32 * j;
+    if (k < nblk) { a += pa[k]; b += pb[k]; }
   }
   s = warp_sum_d(a);
   ss = warp_sum_d(b);
@@ -307,10 +312,10 @@ __global__ void __launch_bounds__(kEwThreads)
 maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx, int N,
                    int H, int W, int C) {
   const int cg = C / 8, Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)N * Ho * Wo * cg;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const unsigned total = (unsigned) (long long)N * Ho * Wo * cg;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int g = (int)(i % cg);
-    long long p = i / cg;
+    unsigned p = i / cg;
     const int wo = (int)(p % Wo); p /= Wo;
     const int ho = (int)(p % Ho);
     const int n = (int)(p / Ho);
@@ -345,10 +350,10 @@ __global__ void __launch_bounds__(kEwThreads)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx, __nv_bfloat16* __restrict__ dx,
                    int N, int H, int W, int C) {
   const int cg = C / 8, Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)N * H * W * cg;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const unsigned total = (unsigned) (long long)N * H * W * cg;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int g = (int)(i % cg);
-    long long p = i / cg;
+    unsigned p = i / cg;
     const int w = (int)(p % W); p /= W;
     const int h = (int)(p % H);
     const int n = (int)(p / H);
@@ -384,41 +389,63 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
 __global__ void __launch_bounds__(kEwThreads)
 bilinear_up_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                    __nv_bfloat16* __restrict__ y, int N, int h, int w, int C, int ldx, int ldy, int f) {
+  // blockDim is a multiple of C/8: a thread's channel group is fixed, the BN fold is hoisted, UN pixels in flight
+  constexpr int UN = 2;
   const int cg = C / 8, Ho = h * f, Wo = w * f;
   const float sy = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
   const float sx = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
-  const long long total = (long long)N * Ho * Wo * cg;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    long long p = i / cg;
-    const int ox = (int)(p % Wo); p /= Wo;
-    const int oy = (int)(p % Ho);
-    const int n = (int)(p / Ho);
-    const float fy = sy * oy, fx = sx * ox;
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
-    const float ly = fy - y0, lx = fx - x0;
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    float v00[8], v01[8], v10[8], v11[8];
-    const __nv_bfloat16* base = x + (long long)n * h * w * ldx + g * 8;
-    unpack8(*reinterpret_cast<const bf16x8*>(base + ((long long)y0 * w + x0) * ldx), v00);
-    unpack8(*reinterpret_cast<const bf16x8*>(base + ((long long)y0 * w + x1) * ldx), v01);
-    unpack8(*reinterpret_cast<const bf16x8*>(base + ((long long)y1 * w + x0) * ldx), v10);
-    unpack8(*reinterpret_cast<const bf16x8*>(base + ((long long)y1 * w + x1) * ldx), v11);
-    float o[8];
+  const unsigned total = (unsigned)N * Ho * Wo * cg;
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned stride = gridDim.x * blockDim.x;
+  const int g = (int)(tid % cg);
+  float a[8], b[8];
+  if (scale) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (scale) {
-        const float a = scale[g * 8 + j], b = shift[g * 8 + j];
-        v00[j] = fmaxf(bf16_round(v00[j] * a + b), 0.f);
-        v01[j] = fmaxf(bf16_round(v01[j] * a + b), 0.f);
-        v10[j] = fmaxf(bf16_round(v10[j] * a + b), 0.f);
-        v11[j] = fmaxf(bf16_round(v11[j] * a + b), 0.f);
-      }
-      // same association as ATen upsample_bilinear2d: hy*(hx*v00 + lx*v01) + ly*(hx*v10 + lx*v11)
-      o[j] = hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]);
+    for (int j = 0; j < 8; ++j) { a[j] = scale[g * 8 + j]; b[j] = shift[g * 8 + j]; }
+  }
+  for (unsigned i0 = tid; i0 < total; i0 += stride * UN) {
+    bf16x8 q[UN][4];
+    float ly[UN], lx[UN];
+    long long oidx[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const unsigned i = i0 + u * stride;
+      if (i >= total) continue;
+      unsigned p = i / cg;
+      const int ox = (int)(p % Wo); p /= Wo;
+      const int oy = (int)(p % Ho);
+      const int n = (int)(p / Ho);
+      const float fy = sy * oy, fx = sx * ox;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+      ly[u] = fy - y0; lx[u] = fx - x0;
+      const __nv_bfloat16* base = x + (long long)n * h * w * ldx + g * 8;
+      q[u][0] = *reinterpret_cast<const bf16x8*>(base + ((long long)y0 * w + x0) * ldx);
+      q[u][1] = *reinterpret_cast<const bf16x8*>(base + ((long long)y0 * w + x1) * ldx);
+      q[u][2] = *reinterpret_cast<const bf16x8*>(base + ((long long)y1 * w + x0) * ldx);
+      q[u][3] = *reinterpret_cast<const bf16x8*>(base + ((long long)y1 * w + x1) * ldx);
+      oidx[u] = (((long long)n * Ho + oy) * Wo + ox) * ldy + g * 8;
     }
-    *reinterpret_cast<bf16x8*>(y + (((long long)n * Ho + oy) * Wo + ox) * ldy + g * 8) = pack8(o);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const unsigned i = i0 + u * stride;
+      if (i >= total) continue;
+      float v00[8], v01[8], v10[8], v11[8], o[8];
+      unpack8(q[u][0], v00); unpack8(q[u][1], v01); unpack8(q[u][2], v10); unpack8(q[u][3], v11);
+      const float hy = 1.f - ly[u], hx = 1.f - lx[u];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (scale) {
+          v00[j] = fmaxf(bf16_round(v00[j] * a[j] + b[j]), 0.f);
+          v01[j] = fmaxf(bf16_round(v01[j] * a[j] + b[j]), 0.f);
+          v10[j] = fmaxf(bf16_round(v10[j] * a[j] + b[j]), 0.f);
+          v11[j] = fmaxf(bf16_round(v11[j] * a[j] + b[j]), 0.f);
+        }
+        // same association as ATen upsample_bilinear2d: hy*(hx*v00 + lx*v01) + ly*(hx*v10 + lx*v11)
+        o[j] = hy * (hx * v00[j] + lx[u] * v01[j]) + ly[u] * (hx * v10[j] + lx[u] * v11[j]);
+      }
+      *reinterpret_cast<bf16x8*>(y + oidx[u]) = pack8(o);
+    }
   }
 }
 
@@ -429,11 +456,11 @@ bilinear_up_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __re
   const int cg = C / 8, Ho = h * f, Wo = w * f;
   const float sy = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
   const float sx = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
-  const long long total = (long long)N * h * w * cg;
+  const unsigned total = (unsigned) (long long)N * h * w * cg;
   const float inv_sy = sy > 0.f ? 1.f / sy : 0.f, inv_sx = sx > 0.f ? 1.f / sx : 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int g = (int)(i % cg);
-    long long p = i / cg;
+    unsigned p = i / cg;
     const int ix = (int)(p % w); p /= w;
     const int iy = (int)(p % h);
     const int n = (int)(p / h);
@@ -479,10 +506,10 @@ __global__ void __launch_bounds__(kEwThreads)
 sumpool2_kernel(const __nv_bfloat16* __restrict__ dfine, __nv_bfloat16* __restrict__ dcoarse, int N, int h, int w, int C,
                 int accumulate) {
   const int cg = C / 8;
-  const long long total = (long long)N * h * w * cg;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const unsigned total = (unsigned) (long long)N * h * w * cg;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int g = (int)(i % cg);
-    long long p = i / cg;
+    unsigned p = i / cg;
     const int x = (int)(p % w); p /= w;
     const int y = (int)(p % h);
     const int n = (int)(p / h);
@@ -568,11 +595,11 @@ __global__ void __launch_bounds__(kEwThreads)
 stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int N, int Cin, int H, int W, int KP) {
   const int Ho = H / 2, Wo = W / 2;
   const int kg = KP / 8;
-  const long long total = (long long)N * Ho * Wo * kg;
+  const unsigned total = (unsigned) (long long)N * Ho * Wo * kg;
   const int K = Cin * 49;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int g = (int)(i % kg);
-    long long p = i / kg;
+    unsigned p = i / kg;
     const int wo = (int)(p % Wo); p /= Wo;
     const int ho = (int)(p % Ho);
     const int n = (int)(p / Ho);
@@ -667,12 +694,12 @@ static int colsum_blocks(long long M, int C) {
   const int cg = C / 8;
   const int rows_par = kEwThreads / cg > 0 ? kEwThreads / cg : 1;
   long long b = (M + (long long)rows_par * 8 - 1) / ((long long)rows_par * 8);
-  if (b > 148 * 4) b = 148 * 4;
+  if (b > 296) b = 296;
   if (b < 1) b = 1;
   return (int)b;
 }
 
-extern "C" long long evb_bn_workspace(long long M, int C) { return ((long long)colsum_blocks(M, C) + 1) * 2 * C * sizeof(float); }
+extern "C" long long evb_bn_workspace(long long M, int C) { (void)M; return ((long long)kNbPad + 1) * 2 * C * sizeof(float); }
 
 // Training BN statistics of x[M,C] + folded scale/shift + running-stat update.
 extern "C" int evb_bn_stats(const void* x, long long M, int C, const float* gamma, const float* beta, float* running_mean,
@@ -718,7 +745,7 @@ extern "C" int evb_bn_bwd(const void* dy, const void* x, const void* ymask, cons
   colsum_kernel<1><<<nb, kEwThreads, kEwThreads * 16 * sizeof(float), ST>>>(
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)ymask, mean, rstd, scale, shift, mask_mode,
       M, C, (float*)ws);
-  float* fresh = (float*)ws + (size_t)nb * 2 * C;
+  float* fresh = (float*)ws + (size_t)kNbPad * 2 * C;
   bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, ST>>>((const float*)ws, nb, C, dgamma, dbeta, param_acc, fresh);
   const long long nvec = M * C / 8;
   const int bt = (kEwThreads / (C / 8)) * (C / 8);
@@ -758,7 +785,9 @@ extern "C" int evb_bilinear_up(const void* x, const float* scale, const float* s
                                int ldx, int ldy, int f, void* stream) {
   if (C % 8 || ldx % 8 || ldy % 8 || f < 1 || f > 4) return EVB_ERR_ARG;
   const long long total = (long long)N * h * f * w * f * (C / 8);
-  bilinear_up_kernel<<<ew_blocks(total, kEwThreads * 2), kEwThreads, 0, ST>>>((const __nv_bfloat16*)x, scale, shift,
+  if (C / 8 > kEwThreads) return EVB_ERR_ARG;
+  const int bt = (kEwThreads / (C / 8)) * (C / 8);
+  bilinear_up_kernel<<<ew_blocks(total, bt * 2), bt, 0, ST>>>((const __nv_bfloat16*)x, scale, shift,
                                                                            (__nv_bfloat16*)y, N, h, w, C, ldx, ldy, f);
   return LAUNCH_OK();
 }

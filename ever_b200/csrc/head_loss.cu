@@ -17,103 +17,167 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------------------------------------ FS-Relation
 // u1, u2: [M, C] bf16 = 1x1 conv outputs (+bias) of the content encoder / feature re-encoder, pre-BN.
 // cf = relu(bn1(u1)), pf = relu(bn2(u2)); r = sigmoid(sum_c bf16(sf_c * cf_c)); z = bf16(r * pf).
-// One warp per pixel; lane handles 8-channel groups lane, lane+32, ...
+// One warp per pixel, C = 256*NG: lane owns channel groups [lane*8 + 256*a, +8); the per-channel BN folds are hoisted
+// into registers and PX pixels are in flight per warp.
+template <int NG, int PX>
 __global__ void __launch_bounds__(256)
 relation_fwd_kernel(const __nv_bfloat16* __restrict__ u1, const __nv_bfloat16* __restrict__ u2,
                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ scale2,
-                    const float* __restrict__ shift2, const float* __restrict__ sf, __nv_bfloat16* __restrict__ z, float* __restrict__ rel, long long M,
-                    int HW, int C) {
+                    const float* __restrict__ shift2, const float* __restrict__ sf, __nv_bfloat16* __restrict__ z,
+                    float* __restrict__ rel, long long M, int HW) {
+  constexpr int C = 256 * NG;
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long m = warp0; m < M; m += nwarps) {
-    const int n = (int)(m / HW);
-    const __nv_bfloat16* row = u1 + m * C;
-    const __nv_bfloat16* row2 = u2 + m * C;
-    float dot = 0.f;
-    for (int c0 = lane * 8; c0 < C; c0 += 256) {
-      float v[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(row + c0), v);
+  float s1[NG][8], b1[NG][8], s2[NG][8], b2[NG][8], sfv[NG][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float cf = fmaxf(bf16_round(v[j] * scale[c0 + j] + shift[c0 + j]), 0.f);
-        dot += bf16_round(sf[n * C + c0 + j] * cf);
-      }
+  for (int a = 0; a < NG; ++a)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = lane * 8 + 256 * a + j;
+      s1[a][j] = scale[c]; b1[a][j] = shift[c]; s2[a][j] = scale2[c]; b2[a][j] = shift2[c];
     }
-    dot = warp_sum(dot);
-    const float r = 1.f / (1.f + __expf(-dot));
-    if (lane == 0) rel[m] = r;
-    for (int c0 = lane * 8; c0 < C; c0 += 256) {
-      float v[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(row2 + c0), v);
+  int cur_n = -1;
+  for (long long m0 = warp0 * PX; m0 < M; m0 += nwarps * PX) {
+    bf16x8 q1[PX][NG], q2[PX][NG];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = r * fmaxf(bf16_round(v[j] * scale2[c0 + j] + shift2[c0 + j]), 0.f);
-      *reinterpret_cast<bf16x8*>(z + m * C + c0) = pack8(v);
+    for (int p = 0; p < PX; ++p)
+      if (m0 + p < M) {
+#pragma unroll
+        for (int a = 0; a < NG; ++a) {
+          q1[p][a] = *reinterpret_cast<const bf16x8*>(u1 + (m0 + p) * C + lane * 8 + 256 * a);
+          q2[p][a] = *reinterpret_cast<const bf16x8*>(u2 + (m0 + p) * C + lane * 8 + 256 * a);
+        }
+      }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      const long long m = m0 + p;
+      if (m >= M) break;
+      const int n = (int)(m / HW);
+      if (n != cur_n) {
+        cur_n = n;
+#pragma unroll
+        for (int a = 0; a < NG; ++a)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sfv[a][j] = sf[n * C + lane * 8 + 256 * a + j];
+      }
+      float dot = 0.f;
+#pragma unroll
+      for (int a = 0; a < NG; ++a) {
+        float v[8];
+        unpack8(q1[p][a], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dot += bf16_round(sfv[a][j] * fmaxf(bf16_round(v[j] * s1[a][j] + b1[a][j]), 0.f));
+      }
+      dot = warp_sum(dot);
+      const float r = 1.f / (1.f + __expf(-dot));
+      if (lane == 0) rel[m] = r;
+#pragma unroll
+      for (int a = 0; a < NG; ++a) {
+        float v[8];
+        unpack8(q2[p][a], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = r * fmaxf(bf16_round(v[j] * s2[a][j] + b2[a][j]), 0.f);
+        *reinterpret_cast<bf16x8*>(z + m * C + lane * 8 + 256 * a) = pack8(v);
+      }
     }
   }
 }
 
-// g[M,2C] = gradient w.r.t. the two BN outputs (ReLU masks applied); dsf[n][c] += sum_pixels dlogit * cf.
+// g1/g2 [M,C] = gradient w.r.t. the two BN outputs (ReLU masks applied); dsf[n][c] += sum_pixels dlogit * cf.
+template <int NG, int PX>
 __global__ void __launch_bounds__(256)
 relation_bwd_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ u1,
                     const __nv_bfloat16* __restrict__ u2, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ scale2, const float* __restrict__ shift2, const float* __restrict__ sf,
                     const float* __restrict__ rel, __nv_bfloat16* __restrict__ g1, __nv_bfloat16* __restrict__ g2,
-                    float* __restrict__ dsf, long long M, int HW, int C, int px_per_warp) {
+                    float* __restrict__ dsf, long long M, int HW, int px_per_warp) {
+  constexpr int C = 256 * NG;
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long m0 = warp * px_per_warp;
-  if (m0 >= M) return;
-  // C <= 1024: each lane owns up to 4 groups of 8 channels
-  float acc[4][8];
+  const long long mbeg = warp * px_per_warp;
+  if (mbeg >= M) return;
+  const long long mend = mbeg + px_per_warp < M ? mbeg + px_per_warp : M;
+  float s1[NG][8], b1[NG][8], s2[NG][8], b2[NG][8], sfv[NG][8], acc[NG][8];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < NG; ++a)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
-  int cur_n = (int)(m0 / HW);
-  const long long m1 = m0 + px_per_warp < M ? m0 + px_per_warp : M;
-  for (long long m = m0; m < m1; ++m) {
-    const int n = (int)(m / HW);
-    if (n != cur_n) {  // flush per-image accumulators
-      for (int a = 0, c0 = lane * 8; c0 < C; c0 += 256, ++a)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { atomicAdd(dsf + cur_n * C + c0 + j, acc[a][j]); acc[a][j] = 0.f; }
-      cur_n = n;
+    for (int j = 0; j < 8; ++j) {
+      const int c = lane * 8 + 256 * a + j;
+      s1[a][j] = scale[c]; b1[a][j] = shift[c]; s2[a][j] = scale2[c]; b2[a][j] = shift2[c];
+      acc[a][j] = 0.f;
     }
-    const __nv_bfloat16* row = u1 + m * C;
-    const __nv_bfloat16* row2 = u2 + m * C;
-    const float r = rel[m];
-    float dr = 0.f;
-    for (int c0 = lane * 8; c0 < C; c0 += 256) {
-      float v[8], d[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(row2 + c0), v);
-      unpack8(*reinterpret_cast<const bf16x8*>(dz + m * C + c0), d);
-      float o[8];
+  int cur_n = -1;
+  for (long long m0 = mbeg; m0 < mend; m0 += PX) {
+    bf16x8 q1[PX][NG], q2[PX][NG], qd[PX][NG];
+    float rr[PX];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float pf = fmaxf(bf16_round(v[j] * scale2[c0 + j] + shift2[c0 + j]), 0.f);
-        dr += d[j] * pf;
-        o[j] = pf > 0.f ? d[j] * r : 0.f;
-      }
-      *reinterpret_cast<bf16x8*>(g2 + m * C + c0) = pack8(o);
-    }
-    dr = warp_sum(dr);
-    const float dlogit = dr * r * (1.f - r);
-    for (int a = 0, c0 = lane * 8; c0 < C; c0 += 256, ++a) {
-      float v[8], o[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(row + c0), v);
+    for (int p = 0; p < PX; ++p)
+      if (m0 + p < mend) {
+        rr[p] = rel[m0 + p];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float cf = fmaxf(bf16_round(v[j] * scale[c0 + j] + shift[c0 + j]), 0.f);
-        acc[a][j] += dlogit * cf;
-        o[j] = cf > 0.f ? dlogit * sf[n * C + c0 + j] : 0.f;
+        for (int a = 0; a < NG; ++a) {
+          const long long off = (m0 + p) * C + lane * 8 + 256 * a;
+          q1[p][a] = *reinterpret_cast<const bf16x8*>(u1 + off);
+          q2[p][a] = *reinterpret_cast<const bf16x8*>(u2 + off);
+          qd[p][a] = *reinterpret_cast<const bf16x8*>(dz + off);
+        }
       }
-      *reinterpret_cast<bf16x8*>(g1 + m * C + c0) = pack8(o);
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      const long long m = m0 + p;
+      if (m >= mend) break;
+      const int n = (int)(m / HW);
+      if (n != cur_n) {
+        if (cur_n >= 0) {
+#pragma unroll
+          for (int a = 0; a < NG; ++a)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { atomicAdd(dsf + cur_n * C + lane * 8 + 256 * a + j, acc[a][j]); acc[a][j] = 0.f; }
+        }
+        cur_n = n;
+#pragma unroll
+        for (int a = 0; a < NG; ++a)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sfv[a][j] = sf[n * C + lane * 8 + 256 * a + j];
+      }
+      const float r = rr[p];
+      float dr = 0.f;
+#pragma unroll
+      for (int a = 0; a < NG; ++a) {
+        float v[8], d[8], o[8];
+        unpack8(q2[p][a], v);
+        unpack8(qd[p][a], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float pf = fmaxf(bf16_round(v[j] * s2[a][j] + b2[a][j]), 0.f);
+          dr += d[j] * pf;
+          o[j] = pf > 0.f ? d[j] * r : 0.f;
+        }
+        *reinterpret_cast<bf16x8*>(g2 + m * C + lane * 8 + 256 * a) = pack8(o);
+      }
+      dr = warp_sum(dr);
+      const float dlogit = dr * r * (1.f - r);
+#pragma unroll
+      for (int a = 0; a < NG; ++a) {
+        float v[8], o[8];
+        unpack8(q1[p][a], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float cf = fmaxf(bf16_round(v[j] * s1[a][j] + b1[a][j]), 0.f);
+          acc[a][j] += dlogit * cf;
+          o[j] = cf > 0.f ? dlogit * sfv[a][j] : 0.f;
+        }
+        *reinterpret_cast<bf16x8*>(g1 + m * C + lane * 8 + 256 * a) = pack8(o);
+      }
     }
   }
-  for (int a = 0, c0 = lane * 8; c0 < C; c0 += 256, ++a)
+  if (cur_n >= 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(dsf + cur_n * C + c0 + j, acc[a][j]);
+    for (int a = 0; a < NG; ++a)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(dsf + cur_n * C + lane * 8 + 256 * a + j, acc[a][j]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ tiny linears
@@ -179,25 +243,30 @@ linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ y, c
 // ------------------------------------------------------------------------------------------------ CE + Dice
 // logits: [P, LD] bf16 (NHWC, first K channels are classes), labels: int64 [P], 255 (ignore_index) = ignored.
 // stats layout (fp32): [0]=sum of -log p_t over valid, [1]=n_valid, [2..2+K)=I_c, [2+K..2+2K)=sum p_c, [2+2K..2+3K)=sum y_c
-constexpr int kMaxK = 32;
+constexpr int kMaxK = 16;
 
-template <int PASS>
+template <int PASS, int KT>
 __global__ void __launch_bounds__(256)
-loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restrict__ labels, long long P, int K, int LD,
+loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restrict__ labels, long long P, int Krt, int LD,
             int ignore_index, float* __restrict__ partial, const float* __restrict__ coef,
             __nv_bfloat16* __restrict__ dlogits) {
   // PASS 0: statistics -> partial[block][2+3K];  PASS 1: dlogits from coef = {inv_nvalid, A_c[K], B_c[K]}
-  __shared__ float red[8][2 + 3 * kMaxK];
+  // KT > 0: K is a compile-time constant (arrays stay in registers); KT == 0: generic K <= kMaxK
+  const int K = KT > 0 ? KT : Krt;
+  constexpr int KA = KT > 0 ? KT : kMaxK;
+  __shared__ float red[8][2 + 3 * KA];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  float acc[2 + 3 * kMaxK];
+  float acc[2 + 3 * KA];
   if (PASS == 0) {
-    for (int i = 0; i < 2 + 3 * K; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2 + 3 * KA; ++i) acc[i] = 0.f;
   }
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
     const long long t = labels[p];
     const bool valid = t != ignore_index;
-    float z[kMaxK];
+    float z[KA];
     const __nv_bfloat16* row = logits + p * LD;
+#pragma unroll
     for (int c0 = 0; c0 < K; c0 += 8) {
       float v[8];
       unpack8(*reinterpret_cast<const bf16x8*>(row + c0), v);
@@ -206,14 +275,20 @@ loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restric
         if (c0 + j < K) z[c0 + j] = v[j];
     }
     float mx = z[0];
+#pragma unroll
     for (int c = 1; c < K; ++c) mx = fmaxf(mx, z[c]);
     float se = 0.f;
+#pragma unroll
     for (int c = 0; c < K; ++c) se += expf(z[c] - mx);
     const float lse = mx + logf(se);
     if (PASS == 0) {
       if (valid) {
-        acc[0] += lse - z[(int)t];
+        float zt = 0.f;
+#pragma unroll
+        for (int c = 0; c < K; ++c) zt = (c == (int)t) ? z[c] : zt;
+        acc[0] += lse - zt;
         acc[1] += 1.f;
+#pragma unroll
         for (int c = 0; c < K; ++c) {
           const float pc = expf(z[c] - lse);
           acc[2 + K + c] += pc;
@@ -221,15 +296,17 @@ loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restric
         }
       }
     } else {
-      float d[kMaxK];
+      float d[KA];
       if (valid) {
         const float inv_n = coef[0];
-        float pc[kMaxK], dot = 0.f;
+        float pc[KA], dot = 0.f;
+#pragma unroll
         for (int c = 0; c < K; ++c) {
           pc[c] = expf(z[c] - lse);
           const float gc = coef[1 + K + c] - (c == (int)t ? coef[1 + c] : 0.f);  // B_c - y_c * A_c
           dot += pc[c] * gc;
         }
+#pragma unroll
         for (int c = 0; c < K; ++c) {
           const float gc = coef[1 + K + c] - (c == (int)t ? coef[1 + c] : 0.f);
           const float dce = (pc[c] - (c == (int)t ? 1.f : 0.f)) * inv_n;
@@ -238,9 +315,12 @@ loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restric
           d[c] = bf16_round(dce) + bf16_round(ddice);
         }
       } else {
+#pragma unroll
         for (int c = 0; c < K; ++c) d[c] = 0.f;
       }
-      for (int c0 = 0; c0 < LD; c0 += 8) {
+#pragma unroll
+      for (int c0 = 0; c0 < 16; c0 += 8) {
+        if (c0 >= LD) break;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = (c0 + j < K) ? d[c0 + j] : 0.f;
@@ -250,7 +330,9 @@ loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restric
   }
   if (PASS == 0) {
     const int n = 2 + 3 * K;
-    for (int i = 0; i < n; ++i) {
+#pragma unroll
+    for (int i = 0; i < 2 + 3 * KA; ++i) {
+      if (i >= n) break;
       const float v = warp_sum(acc[i]);
       if (lane == 0) red[wid][i] = v;
     }
@@ -343,24 +425,32 @@ using namespace evb;
 extern "C" int evb_relation_fwd(const void* u1, const void* u2, const float* scale1, const float* shift1,
                                 const float* scale2, const float* shift2, const float* sf, void* z, float* rel, long long M,
                                 int HW, int C, void* stream) {
-  if (C % 8 || C > 1024) return EVB_ERR_ARG;
-  long long blocks = (M + 7) / 8;
+  if (C != 256 && C != 512 && C != 1024) return EVB_ERR_ARG;
+  long long blocks = (M + 31) / 32;  // 8 warps x 4 pixels
   if (blocks > 148 * 8) blocks = 148 * 8;
-  relation_fwd_kernel<<<(int)blocks, 256, 0, ST>>>((const __nv_bfloat16*)u1, (const __nv_bfloat16*)u2, scale1, shift1, scale2,
-                                                   shift2, sf, (__nv_bfloat16*)z, rel, M, HW, C);
+  const __nv_bfloat16 *a = (const __nv_bfloat16*)u1, *b = (const __nv_bfloat16*)u2;
+  __nv_bfloat16* zz = (__nv_bfloat16*)z;
+  if (C == 256) relation_fwd_kernel<1, 4><<<(int)blocks, 256, 0, ST>>>(a, b, scale1, shift1, scale2, shift2, sf, zz, rel, M, HW);
+  else if (C == 512) relation_fwd_kernel<2, 2><<<(int)blocks, 256, 0, ST>>>(a, b, scale1, shift1, scale2, shift2, sf, zz, rel, M, HW);
+  else relation_fwd_kernel<4, 1><<<(int)blocks, 256, 0, ST>>>(a, b, scale1, shift1, scale2, shift2, sf, zz, rel, M, HW);
   return LAUNCH_OK();
 }
 // dsf must be zeroed by the caller (it is accumulated with atomics).
 extern "C" int evb_relation_bwd(const void* dz, const void* u1, const void* u2, const float* scale1, const float* shift1,
                                 const float* scale2, const float* shift2, const float* sf, const float* rel, void* g1,
                                 void* g2, float* dsf, long long M, int HW, int C, void* stream) {
-  if (C % 8 || C > 1024) return EVB_ERR_ARG;
+  if (C != 256 && C != 512 && C != 1024) return EVB_ERR_ARG;
   const int px_per_warp = 16;
   const long long warps = (M + px_per_warp - 1) / px_per_warp;
   const long long blocks = (warps + 7) / 8;
-  relation_bwd_kernel<<<(int)blocks, 256, 0, ST>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)u1, (const __nv_bfloat16*)u2,
-                                                   scale1, shift1, scale2, shift2, sf, rel, (__nv_bfloat16*)g1,
-                                                   (__nv_bfloat16*)g2, dsf, M, HW, C, px_per_warp);
+  const __nv_bfloat16 *d = (const __nv_bfloat16*)dz, *a = (const __nv_bfloat16*)u1, *b = (const __nv_bfloat16*)u2;
+  __nv_bfloat16 *o1 = (__nv_bfloat16*)g1, *o2 = (__nv_bfloat16*)g2;
+  if (C == 256)
+    relation_bwd_kernel<1, 2><<<(int)blocks, 256, 0, ST>>>(d, a, b, scale1, shift1, scale2, shift2, sf, rel, o1, o2, dsf, M, HW, px_per_warp);
+  else if (C == 512)
+    relation_bwd_kernel<2, 1><<<(int)blocks, 256, 0, ST>>>(d, a, b, scale1, shift1, scale2, shift2, sf, rel, o1, o2, dsf, M, HW, px_per_warp);
+  else
+    relation_bwd_kernel<4, 1><<<(int)blocks, 256, 0, ST>>>(d, a, b, scale1, shift1, scale2, shift2, sf, rel, o1, o2, dsf, M, HW, px_per_warp);
   return LAUNCH_OK();
 }
 
@@ -387,10 +477,18 @@ extern "C" long long evb_loss_workspace(long long P, int K) { return (long long)
 // Pass A: statistics of softmax-CE + Dice over valid pixels -> stats[2+3K] (device, fp32).
 extern "C" int evb_loss_stats(const void* logits, const void* labels, long long P, int K, int LD, int ignore_index,
                               float* stats, void* ws, void* stream) {
-  if (K < 2 || K > kMaxK || LD % 8 || LD < K) return EVB_ERR_ARG;
+  if (K < 2 || K > kMaxK || LD != 16) return EVB_ERR_ARG;
   const int nb = loss_blocks(P), n = 2 + 3 * K;
-  loss_kernel<0><<<nb, 256, 0, ST>>>((const __nv_bfloat16*)logits, (const long long*)labels, P, K, LD, ignore_index,
-                                     (float*)ws, nullptr, nullptr);
+#define EVB_LOSS_LAUNCH(PASS_, GRID_, ...)                                                        \
+  switch (K) {                                                                                   \
+    case 15: loss_kernel<PASS_, 15><<<GRID_, 256, 0, ST>>>(__VA_ARGS__); break;                  \
+    case 7: loss_kernel<PASS_, 7><<<GRID_, 256, 0, ST>>>(__VA_ARGS__); break;                    \
+    case 5: loss_kernel<PASS_, 5><<<GRID_, 256, 0, ST>>>(__VA_ARGS__); break;                    \
+    case 2: loss_kernel<PASS_, 2><<<GRID_, 256, 0, ST>>>(__VA_ARGS__); break;                    \
+    default: loss_kernel<PASS_, 0><<<GRID_, 256, 0, ST>>>(__VA_ARGS__);                          \
+  }
+  EVB_LOSS_LAUNCH(0, nb, (const __nv_bfloat16*)logits, (const long long*)labels, P, K, LD, ignore_index, (float*)ws,
+                  nullptr, nullptr)
   loss_reduce_kernel<<<(n + 127) / 128, 128, 0, ST>>>((const float*)ws, nb, n, stats);
   return LAUNCH_OK();
 }
@@ -404,9 +502,9 @@ extern "C" int evb_loss_finalize(const float* stats, const float* dice_stats, in
 // Pass B: dlogits[P, LD] bf16 (padding channels zeroed).
 extern "C" int evb_loss_grad(const void* logits, const void* labels, long long P, int K, int LD, int ignore_index,
                              const float* coef, void* dlogits, void* stream) {
-  if (K < 2 || K > kMaxK || LD % 8 || LD < K) return EVB_ERR_ARG;
-  loss_kernel<1><<<loss_blocks(P), 256, 0, ST>>>((const __nv_bfloat16*)logits, (const long long*)labels, P, K, LD,
-                                                 ignore_index, nullptr, coef, (__nv_bfloat16*)dlogits);
+  if (K < 2 || K > kMaxK || LD != 16) return EVB_ERR_ARG;
+  EVB_LOSS_LAUNCH(1, loss_blocks(P), (const __nv_bfloat16*)logits, (const long long*)labels, P, K, LD, ignore_index,
+                  nullptr, coef, (__nv_bfloat16*)dlogits)
   return LAUNCH_OK();
 }
 

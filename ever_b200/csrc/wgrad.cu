@@ -167,7 +167,13 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
     if (ci < Cin && co < Cout) {
       const float* src = ws + ((long long)tap * CinP + ci) * CoutP + co;
       const long long ss = (long long)ntaps * CinP * CoutP;
-      for (int k = 0; k < nsplit; ++k) s += src[k * ss];
+      float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int k = 0;
+      for (; k + 3 < nsplit; k += 4) {
+        s += src[k * ss]; s1 += src[(k + 1) * ss]; s2 += src[(k + 2) * ss]; s3 += src[(k + 3) * ss];
+      }
+      for (; k < nsplit; ++k) s += src[k * ss];
+      s += s1 + s2 + s3;
     }
     tile[i][tx] = s;
   }
@@ -192,7 +198,13 @@ __global__ void wgrad_reduce_splitpar_kernel(const float* __restrict__ ws, float
   float s = 0.f;
   if (co < Cout) {
     const float* src = ws + ((long long)tap * CinP + ci) * CoutP + co;
-    for (int k = threadIdx.y; k < nsplit; k += 8) s += src[k * ss];
+    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = threadIdx.y;
+    for (; k + 24 < nsplit; k += 32) {  // 4 independent loads in flight
+      s += src[k * ss]; s1 += src[(k + 8) * ss]; s2 += src[(k + 16) * ss]; s3 += src[(k + 24) * ss];
+    }
+    for (; k < nsplit; k += 8) s += src[k * ss];
+    s += s1 + s2 + s3;
   }
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
@@ -263,6 +275,7 @@ static WgradPlan plan_wgrad(int N, int Ho, int Wo, int Cin, int Cout, int ntaps,
   const int base = ntaps * pl.tiles_ci * pl.tiles_co;
   int split = force_split ? force_split : (2 * 148) / base;  // round down: at most two full waves of CTAs
   if (split > pl.nchunks) split = pl.nchunks;
+  if (!force_split && split > 74) split = 74;   // bounds the reduction depth (and workspace) of small-channel convs
   if (!force_split) {
     const int max_by_work = (pl.nchunks + 7) / 8;  // at least ~8 chunks (512 pixels) per CTA
     if (split > max_by_work) split = max_by_work;
@@ -325,7 +338,7 @@ extern "C" int evb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, con
     default: rc = EVB_ERR_ARG;
   }
   if (rc) return rc;
-  if (pl.nsplit > 8) {
+  if (pl.nsplit > 8 && (long long)Cin * Cout * ntaps <= 131072) {   // few outputs, many splits
     dim3 grid((Cout + 31) / 32, Cin, ntaps), block(32, 8);
     wgrad_reduce_splitpar_kernel<<<grid, block, 0, st>>>((const float*)ws, dw, pl.nsplit, ntaps, Cin, Cout, pl.CinP,
                                                          pl.CoutP, accumulate);

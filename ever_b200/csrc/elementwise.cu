@@ -642,34 +642,38 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, 
 }
 
 // All convolutions of the model in one launch.  desc[i] = {w, wf, wb, Co, Ci, kk, CoP, CiP, CiPb, CoPb, first_block, -}
-// (12 x int64); block_map[b] = index of the descriptor block b works on; 1024 elements per block.
+// (12 x int64); block_map[b] = descriptor index of block b.  One block = a 32 co x 32 ci tile, all kk <= 9 taps, staged
+// through shared memory so that the OIHW read ((ci,tap) contiguous per co) and both packed writes
+// (wf[tap][co][ci]: ci contiguous; wb[tap][ci][co]: co contiguous) are coalesced.  Padding rows/columns of the packs are
+// never written (the pack arena is zero-initialised once).
 __global__ void __launch_bounds__(256)
 pack_weights_batched_kernel(const long long* __restrict__ desc, const int* __restrict__ block_map) {
+  __shared__ float tile[9][32][33];  // [tap][co][ci]
   const long long* d = desc + (long long)block_map[blockIdx.x] * 12;
   const float* w = reinterpret_cast<const float*>(d[0]);
   __nv_bfloat16* wf = reinterpret_cast<__nv_bfloat16*>(d[1]);
   __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(d[2]);
   const int Co = (int)d[3], Ci = (int)d[4], kk = (int)d[5], CoP = (int)d[6], CiP = (int)d[7], CiPb = (int)d[8],
             CoPb = (int)d[9];
-  const long long nf = (long long)kk * CoP * CiP;
-  const long long nb = wb ? (long long)kk * CiPb * CoPb : 0;
-  const long long base = ((long long)blockIdx.x - d[10]) * 1024;
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const long long i = base + u * 256 + threadIdx.x;
-    if (i >= nf + nb) break;
-    if (i < nf) {
-      const int ci = (int)(i % CiP);
-      const int co = (int)((i / CiP) % CoP);
-      const int t = (int)(i / ((long long)CiP * CoP));
-      wf[i] = __float2bfloat16_rn((co < Co && ci < Ci) ? w[((long long)co * Ci + ci) * kk + t] : 0.f);
-    } else {
-      const long long k = i - nf;
-      const int co = (int)(k % CoPb);
-      const int ci = (int)((k / CoPb) % CiPb);
-      const int t = (int)(k / ((long long)CoPb * CiPb));
-      wb[k] = __float2bfloat16_rn((co < Co && ci < Ci) ? w[((long long)co * Ci + ci) * kk + t] : 0.f);
-    }
+  const int t = blockIdx.x - (int)d[10];
+  const int tiles_ci = (Ci + 31) / 32;
+  const int co0 = (t / tiles_ci) * 32, ci0 = (t % tiles_ci) * 32;
+  const int nci = min(32, Ci - ci0);
+  const int run = nci * kk;  // contiguous floats per co
+  for (int idx = threadIdx.x; idx < 32 * run; idx += 256) {
+    const int c = idx / run, e = idx % run;
+    const int cil = e / kk, tap = e % kk;
+    if (co0 + c < Co) tile[tap][c][cil] = w[((long long)(co0 + c) * Ci + ci0) * kk + e];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kk * 32 * 32; idx += 256) {
+    const int tap = idx / 1024, r = (idx / 32) % 32, q = idx % 32;
+    // wf: row = co (r), fastest = ci (q)
+    if (co0 + r < Co && ci0 + q < Ci)
+      wf[((long long)tap * CoP + co0 + r) * CiP + ci0 + q] = __float2bfloat16_rn(tile[tap][r][q]);
+    // wb: row = ci (r), fastest = co (q)
+    if (wb && ci0 + r < Ci && co0 + q < Co)
+      wb[((long long)tap * CiPb + ci0 + r) * CoPb + co0 + q] = __float2bfloat16_rn(tile[tap][q][r]);
   }
 }
 

@@ -26,8 +26,9 @@ struct WgradParams {
   int tiles_w, tiles_h, tiles_n;  // chunk grid
   int nchunks, chunks_per_split, nsplit;
   int tiles_ci, tiles_co;
-  float* ws;  // [split][tap][CinP][CoutP]
-  int CinP, CoutP;
+  float* ws;   // deterministic mode: [split][tap][CinP][CoutP] partials, reduced by a second kernel
+  float* acc;  // atomic mode (ws == nullptr): [tap][CinP][CoutP] fp32 accumulated with red.global.add.v4.f32
+  int CinP, CoutP, Cin, Cout;
 };
 
 template <int NT>
@@ -127,22 +128,40 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;  // input channel within the tile
-    float* orow = p.ws + (((long long)split * p.ntaps + tap) * p.CinP + ci0 + r) * p.CoutP + co0;
     mbar_wait(tfull, 0, 0x600);
     tc_fence_after();
+    if (p.ws) {
+      float* orow = p.ws + (((long long)split * p.ntaps + tap) * p.CinP + ci0 + r) * p.CoutP + co0;
 #pragma unroll 1
-    for (int c = 0; c < NT / 32; ++c) {
-      uint32_t v[32];
-      if (niter > 0) {
-        tmem_ld32(taddr + (uint32_t(q * 32) << 16) + c * 32, v);
-        tmem_ld_wait();
-      } else {
+      for (int c = 0; c < NT / 32; ++c) {
+        uint32_t v[32];
+        if (niter > 0) {
+          tmem_ld32(taddr + (uint32_t(q * 32) << 16) + c * 32, v);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0;
+          for (int j = 0; j < 32; ++j) v[j] = 0;
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(orow + c * 32 + g * 4) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
       }
+    } else if (niter > 0) {
+      float* orow = p.acc + (((long long)tap) * p.CinP + ci0 + r) * p.CoutP + co0;
+      const bool row_ok = (ci0 + r) < p.Cin;
+#pragma unroll 1
+      for (int c = 0; c < NT / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t(q * 32) << 16) + c * 32, v);   // warp-collective: outside the row predicate
+        tmem_ld_wait();
+        if (row_ok && co0 + c * 32 < p.Cout) {
 #pragma unroll
-      for (int g = 0; g < 8; ++g)
-        *reinterpret_cast<uint4*>(orow + c * 32 + g * 4) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          for (int g = 0; g < 8; ++g)
+            atomicAdd(reinterpret_cast<float4*>(orow + c * 32 + g * 4),
+                      make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
+                                  __uint_as_float(v[g * 4 + 3])));
+        }
+      }
     }
   }
   tc_fence_before();
@@ -188,6 +207,55 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
   }
 }
 
+// Coalesced deterministic reduce + transpose to OIHW.  256 threads: tile of 32 co x CIT ci x all taps.
+//   read : ws[split][tap][ci][co] as float4 along co, splits summed in fixed order with 8 loads in flight
+//   write: dw[co][ci][tap]        -- for each co, CIT ci x NTAPS contiguous floats
+template <int NTAPS, int CIT>
+__global__ void __launch_bounds__(256)
+wgrad_reduce_oihw_kernel(const float* __restrict__ ws, float* __restrict__ dw, int nsplit, int Cin, int Cout, int CinP,
+                         int CoutP, int accumulate) {
+  __shared__ float tile[NTAPS][CIT][33];
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * CIT;
+  const long long ss = (long long)NTAPS * CinP * CoutP;
+  constexpr int ITEMS = NTAPS * CIT * 8;
+  for (int it = threadIdx.x; it < ITEMS; it += 256) {
+    const int quad = it & 7, cil = (it >> 3) % CIT, tap = it / (8 * CIT);
+    const int ci = ci0 + cil, co = co0 + quad * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ci < Cin && co < Cout) {   // CoutP is a multiple of 64: the float4 never leaves the padded row
+      const float* src = ws + ((long long)tap * CinP + ci) * CoutP + co;
+      int k = 0;
+      for (; k + 7 < nsplit; k += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(src + (k + u) * ss);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+      }
+      for (; k < nsplit; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(src + k * ss);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    tile[tap][cil][quad * 4 + 0] = acc.x;
+    tile[tap][cil][quad * 4 + 1] = acc.y;
+    tile[tap][cil][quad * 4 + 2] = acc.z;
+    tile[tap][cil][quad * 4 + 3] = acc.w;
+  }
+  __syncthreads();
+  constexpr int RUN = CIT * NTAPS;  // contiguous output floats per co
+  for (int idx = threadIdx.x; idx < 32 * RUN; idx += 256) {
+    const int c = idx / RUN, e = idx % RUN;
+    const int cil = e / NTAPS, tap = e % NTAPS;
+    const int oco = co0 + c, oci = ci0 + cil;
+    if (oco < Cout && oci < Cin) {
+      float* dst = dw + ((long long)oco * Cin + oci) * NTAPS + tap;
+      const float v = tile[tap][cil][c];
+      *dst = accumulate ? (*dst + v) : v;
+    }
+  }
+}
+
 // split-parallel variant for many splits / few outputs: block (32 co, 8 split lanes), one ci per blockIdx.y
 __global__ void wgrad_reduce_splitpar_kernel(const float* __restrict__ ws, float* __restrict__ dw, int nsplit, int ntaps,
                                              int Cin, int Cout, int CinP, int CoutP, int accumulate) {
@@ -214,6 +282,42 @@ __global__ void wgrad_reduce_splitpar_kernel(const float* __restrict__ ws, float
     for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
     float* dst = dw + ((long long)co * Cin + ci) * ntaps + tap;
     *dst = accumulate ? (*dst + t) : t;
+  }
+}
+
+// All convolutions in one launch: dw[co][ci][tap] (+)= acc[tap][ci][co]; acc = 0.
+// desc[i] = {acc, dw, Co, Ci, kk, CinP, CoutP, first_block, accumulate, -,-,-} (12 x int64); 32x32 (ci,co) tiles per block.
+__global__ void __launch_bounds__(256)
+wgrad_unstage_batched_kernel(const long long* __restrict__ desc, const int* __restrict__ block_map) {
+  __shared__ float tile[32][33];
+  const long long* d = desc + (long long)block_map[blockIdx.x] * 12;
+  float* acc = reinterpret_cast<float*>(d[0]);
+  float* dw = reinterpret_cast<float*>(d[1]);
+  const int Co = (int)d[2], Ci = (int)d[3], kk = (int)d[4], CinP = (int)d[5], CoutP = (int)d[6], accumulate = (int)d[8];
+  int t = blockIdx.x - (int)d[7];
+  const int tco = (Co + 31) / 32, tci = (Ci + 31) / 32;
+  const int bco = t % tco; t /= tco;
+  const int bci = t % tci;
+  const int tap = t / tci;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int ci = bci * 32 + i, co = bco * 32 + tx;
+    float v = 0.f;
+    if (ci < Ci && co < Co) {
+      float* src = acc + ((long long)tap * CinP + ci) * CoutP + co;
+      v = *src;
+      *src = 0.f;
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int co = bco * 32 + i, ci = bci * 32 + tx;
+    if (ci < Ci && co < Co) {
+      float* dst = dw + ((long long)co * Ci + ci) * kk + tap;
+      const float v = tile[tx][i];
+      *dst = accumulate ? (*dst + v) : v;
+    }
   }
 }
 
@@ -298,15 +402,15 @@ extern "C" long long evb_conv2d_wgrad_workspace(int N, int Ho, int Wo, int Cin, 
 }
 
 // dw[Cout][Cin][k][k] fp32 (+)= sum_pixels x (*) dy.  x: [N,H,W,Cin] bf16 (the conv input), dy: [N,Ho,Wo,Cout] bf16.
-extern "C" int evb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, const void* dy, int Cout, int ksize,
-                                int stride, float* dw, int accumulate, void* ws, long long ws_bytes, int force_nt,
-                                int force_split, void* stream) {
+static int wgrad_impl(const void* x, int N, int H, int W, int Cin, const void* dy, int Cout, int ksize, int stride,
+                      float* dw, int accumulate, void* ws, long long ws_bytes, float* acc, int cin_valid, int cout_valid,
+                      int force_nt, int force_split, void* stream) {
   if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return EVB_ERR_ARG;
   if (Cin % 64 || Cout % 64) return EVB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int Ho = H / stride, Wo = W / stride, ntaps = ksize * ksize;
   const WgradPlan pl = plan_wgrad(N, Ho, Wo, Cin, Cout, ntaps, force_nt, force_split);
-  if ((size_t)ws_bytes < pl.ws_bytes) return EVB_ERR_ARG;
+  if (!acc && (size_t)ws_bytes < pl.ws_bytes) return EVB_ERR_ARG;
   WgradParams p{};
   p.ntaps = ntaps;
   for (int r = 0; r < ksize; ++r)
@@ -325,7 +429,8 @@ extern "C" int evb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, con
   p.tiles_w = pl.tw; p.tiles_h = pl.th; p.tiles_n = pl.tn;
   p.nchunks = pl.nchunks; p.chunks_per_split = pl.cps; p.nsplit = pl.nsplit;
   p.tiles_ci = pl.tiles_ci; p.tiles_co = pl.tiles_co;
-  p.ws = (float*)ws; p.CinP = pl.CinP; p.CoutP = pl.CoutP;
+  p.ws = acc ? nullptr : (float*)ws; p.acc = acc; p.CinP = pl.CinP; p.CoutP = pl.CoutP;
+  p.Cin = cin_valid; p.Cout = cout_valid;
   CUtensorMap tmX, tmDY;
   int rc = make_act_map(&tmX, x, N, H, W, Cin, stride, pl.bw, pl.bh, pl.bn);
   if (rc) return rc;
@@ -338,14 +443,52 @@ extern "C" int evb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, con
     default: rc = EVB_ERR_ARG;
   }
   if (rc) return rc;
-  if (pl.nsplit > 8 && (long long)Cin * Cout * ntaps <= 131072) {   // few outputs, many splits
+  if (acc) return EVB_OK;
+  if (pl.nsplit > 16 && (long long)Cin * Cout * ntaps <= 65536) {   // few outputs, many splits
     dim3 grid((Cout + 31) / 32, Cin, ntaps), block(32, 8);
     wgrad_reduce_splitpar_kernel<<<grid, block, 0, st>>>((const float*)ws, dw, pl.nsplit, ntaps, Cin, Cout, pl.CinP,
                                                          pl.CoutP, accumulate);
   } else {
-    dim3 grid((Cout + 31) / 32, (Cin + 31) / 32, ntaps), block(32, 8);
-    wgrad_reduce_kernel<<<grid, block, 0, st>>>((const float*)ws, dw, pl.nsplit, ntaps, Cin, Cout, pl.CinP, pl.CoutP,
-                                                accumulate);
+    if (ntaps == 9) {
+      dim3 grid((Cout + 31) / 32, (Cin + 7) / 8);
+      wgrad_reduce_oihw_kernel<9, 8><<<grid, 256, 0, st>>>((const float*)ws, dw, pl.nsplit, Cin, Cout, pl.CinP, pl.CoutP,
+                                                           accumulate);
+    } else {
+      dim3 grid((Cout + 31) / 32, (Cin + 31) / 32);
+      wgrad_reduce_oihw_kernel<1, 32><<<grid, 256, 0, st>>>((const float*)ws, dw, pl.nsplit, Cin, Cout, pl.CinP, pl.CoutP,
+                                                            accumulate);
+    }
   }
+  return cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
+}
+
+// dw[Cout][Cin][k][k] fp32 (+)= sum_pixels x (*) dy, deterministic: split-K partials in `ws`, fixed-order reduction.
+extern "C" int evb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, const void* dy, int Cout, int ksize,
+                                int stride, float* dw, int accumulate, void* ws, long long ws_bytes, int force_nt,
+                                int force_split, void* stream) {
+  return wgrad_impl(x, N, H, W, Cin, dy, Cout, ksize, stride, dw, accumulate, ws, ws_bytes, nullptr, Cin, Cout, force_nt,
+                    force_split, stream);
+}
+
+// Padded staging layout used by evb_conv2d_wgrad_acc: acc is fp32 [k*k][CinP][CoutP].
+extern "C" int evb_conv2d_wgrad_layout(int Cin, int Cout, int* CinP, int* CoutP) {
+  const WgradPlan pl = plan_wgrad(1, 64, 64, Cin, Cout, 1, 0, 1);
+  *CinP = pl.CinP;
+  *CoutP = pl.CoutP;
+  return EVB_OK;
+}
+
+// Fast path: every split adds its tile into acc[tap][ci][co] with red.global.add.v4.f32 (no workspace, no reduce
+// launch; summation order is not fixed).  Rows >= cin_valid / columns >= cout_valid (zero padding) are skipped.
+// evb_wgrad_unstage_batched later moves acc into the OIHW gradients and re-zeroes it.
+extern "C" int evb_conv2d_wgrad_acc(const void* x, int N, int H, int W, int Cin, const void* dy, int Cout, int ksize,
+                                    int stride, float* acc, int cin_valid, int cout_valid, void* stream) {
+  if (!acc) return EVB_ERR_ARG;
+  return wgrad_impl(x, N, H, W, Cin, dy, Cout, ksize, stride, nullptr, 0, nullptr, 0, acc, cin_valid, cout_valid, 0, 0,
+                    stream);
+}
+
+extern "C" int evb_wgrad_unstage_batched(const void* desc, const void* block_map, int nblocks, void* stream) {
+  wgrad_unstage_batched_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>((const long long*)desc, (const int*)block_map);
   return cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
 }

@@ -175,8 +175,7 @@ class FarSegEngine:
         rows, bmap, nblk = [], [], 0
         for i, cp in enumerate(self.convs):
             kk = cp.k * cp.k
-            total = kk * cp.cop * cp.cip * (2 if cp.need_dgrad else 1)
-            nb = (total + 1023) // 1024
+            nb = ((cp.co + 31) // 32) * ((cp.ci + 31) // 32)   # one block per 32x32 (co, ci) tile, all taps
             rows.append([cp.weight.data_ptr(), cp.wf.data_ptr(), cp.wb.data_ptr() if cp.need_dgrad else 0, cp.co, cp.ci, kk,
                          cp.cop, cp.cip, cp.cip, cp.cop, nblk, 0])
             bmap += [i] * nb

@@ -41,6 +41,15 @@ int evb_conv2d_dgrad(const void* dy, int N, int Ho, int Wo, int Cout, const void
 long long evb_conv2d_wgrad_workspace(int N, int Ho, int Wo, int Cin, int Cout, int ksize, int force_nt, int force_split);
 int evb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, const void* dy, int Cout, int ksize, int stride,
                      float* dw, int accumulate, void* ws, long long ws_bytes, int force_nt, int force_split, void* stream);
+/* Fast path: split-K tiles are accumulated into acc (fp32 [k*k][CinP][CoutP], evb_conv2d_wgrad_layout gives the padded
+ * sizes) with red.global.add.v4.f32 -- no workspace, no reduce launch, summation order not fixed.  Rows >= cin_valid and
+ * columns >= cout_valid (zero padding) are skipped.  evb_wgrad_unstage_batched moves every conv's acc into its OIHW fp32
+ * gradient (dw[co][ci][tap] (+)= acc[tap][ci][co]) and re-zeroes acc; desc: int64[n][12] =
+ * {acc, dw, Co, Ci, kk, CinP, CoutP, first_block, accumulate, 0, 0, 0}, block_map: int32[nblocks] (32x32 tiles). */
+int evb_conv2d_wgrad_layout(int Cin, int Cout, int* CinP, int* CoutP);
+int evb_conv2d_wgrad_acc(const void* x, int N, int H, int W, int Cin, const void* dy, int Cout, int ksize, int stride,
+                         float* acc, int cin_valid, int cout_valid, void* stream);
+int evb_wgrad_unstage_batched(const void* desc, const void* block_map, int nblocks, void* stream);
 /* fp32 OIHW master weights -> bf16 packs [kk][CoP][CiP] (forward) and [kk][CiPb][CoPb] (dgrad), zero padded. */
 int evb_pack_weight(const float* w, int Co, int Ci, int kk, void* wf, int CoP, int CiP, void* wb, int CiPb, int CoPb,
                     void* stream);

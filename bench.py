@@ -25,6 +25,9 @@ sys.path.insert(0, ROOT)
 K_CLASSES, TILE, PER_GPU_BATCH = 15, 512, 8
 GFLOP_PER_TILE = 343.1  # fwd 114.8 + bwd 228.3, FlopCounterMode on the reference modules
 METRIC = 'FarSeg-R50 512x512 tiles/s fwd+bwd'
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the ncu --set full capture
+# summarised in profiles/ (None until captured)
+NCU_TRAFFIC_BYTES = None
 
 
 def peaks():
@@ -151,8 +154,8 @@ def conv_roofline(pk):
     ms = e0.elapsed_time(e1) / iters
     flop = 2.0 * n * h * w * c * c * 9
     ach = flop / (ms * 1e-3) / 1e12
-    return dict(bound='tensor', kernel='igemm_kernel<256> conv3x3 256->256 @ 8x128x128', achieved=ach, peak=pk['tf_burst'],
-                unit='TFLOP/s', frac=ach / pk['tf_burst'], traffic=None, peak_source=pk['src'] + ' bf16_tflops (burst)',
+    return dict(bound='tensor', kernel='igemm2_kernel<256,false> conv3x3 256->256 @ 8x128x128 (persistent, TMEM double-buffered, TMA store)', achieved=ach, peak=pk['tf_burst'],
+                unit='TFLOP/s', frac=ach / pk['tf_burst'], traffic=NCU_TRAFFIC_BYTES, peak_source=pk['src'] + ' bf16_tflops (burst)',
                 ms_per_launch=ms, flop_per_launch=flop)
 
 

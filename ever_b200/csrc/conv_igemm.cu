@@ -176,6 +176,215 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM loops over output tiles.  The fp32 accumulator is double-buffered in TMEM
+// (2 x NT columns) so the epilogue of tile i (tcgen05.ld -> bias/add -> bf16 -> 128B-swizzled smem -> TMA store)
+// overlaps the TMA/MMA main loop of tile i+1; the smem ring keeps streaming across tile boundaries.
+// ------------------------------------------------------------------------------------------------------------
+template <int NT>
+struct Igemm2Cfg {
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = NT * 128;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (NT == 256) ? 4 : (NT == 128) ? 4 : 5;
+  static constexpr int SLAB = 128 * 128;  // 128 rows x 64 channels bf16, one TMA store box
+  static constexpr int NSLAB_G = (NT == 256) ? 1 : 2;  // staging buffers per epilogue group
+  static constexpr int SMEM = STAGES * STAGE + 2 * NSLAB_G * SLAB + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * NT;
+  static constexpr int THREADS = 64 + 256;  // producer warp, MMA warp, 2 epilogue groups of 4 warps
+};
+
+// EPI: the epilogue applies a per-channel bias and/or adds a second tensor (compile-time so the plain path is branch-free)
+template <int NT, bool EPI>
+__global__ void __launch_bounds__(320, 1)
+igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ IgemmParams p) {
+  using Cfg = Igemm2Cfg<NT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* slab_base = smem + Cfg::STAGES * Cfg::STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(slab_base + 2 * Cfg::NSLAB_G * Cfg::SLAB);
+  uint64_t* empty = full + Cfg::STAGES;
+  uint64_t* tfull = empty + Cfg::STAGES;   // [2]
+  uint64_t* tempty = tfull + 2;            // [2]
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = p.tiles_c * p.tiles_w * p.tiles_h * p.tiles_n;
+  const int niter = p.ntaps * p.kblocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tslot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t taddr = *tslot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int t = tile;
+        const int tc = t % p.tiles_c; t /= p.tiles_c;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int tn = t / p.tiles_h;
+        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, cout0 = tc * NT;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const ConvTap tp = p.taps[tap];
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1, 0x700 + stage);
+            uint8_t* a_dst = smem + stage * Cfg::STAGE;
+            mbar_arrive_expect_tx(&full[stage], Cfg::STAGE);
+            tma_load_5d(a_dst, &tmA, &full[stage], tp.coff + kb * 64, w0 + tp.dw, h0 + tp.dh, n0, tp.phase);
+            tma_load_3d(a_dst + Cfg::A_BYTES, &tmB, &full[stage], kb * 64, cout0, tp.slab);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, NT, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++local) {
+        const int buf = local & 1;
+        const uint32_t use = (uint32_t)(local >> 1);
+        mbar_wait(&tempty[buf], (use & 1) ^ 1, 0x800 + buf);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = taddr + buf * NT;
+        for (int it = 0; it < niter; ++it) {
+          mbar_wait(&full[stage], phase, 0x900 + stage);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE);
+          const uint32_t b_base = a_base + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(tacc, make_smem_desc(a_base + k * 32, 0, 1024), make_smem_desc(b_base + k * 32, 0, 1024), idesc,
+                      (it | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else {
+    // ---- two epilogue groups of 4 warps (128 threads) alternate over the 64-channel slabs of a tile;
+    //      warp w touches TMEM lanes [32*(w%4), +32)
+    const int grp = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                 // row of the tile = TMEM lane
+    const int et = threadIdx.x - 64 - grp * 128; // 0..127 within the group
+    const int bar_id = 1 + grp;
+    uint8_t* my_slabs = slab_base + grp * Cfg::NSLAB_G * Cfg::SLAB;
+    const int wl = r % p.bw, hl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
+    const uint32_t sw_row = (uint32_t)(r * 128);
+    const uint32_t sw_x = (uint32_t)(r & 7);
+    int local = 0;
+    int nstore = 0;                              // slabs stored so far by this group
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++local) {
+      int t = tile;
+      const int tc = t % p.tiles_c; t /= p.tiles_c;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h;
+      const int tn = t / p.tiles_h;
+      const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, cout0 = tc * NT;
+      const __nv_bfloat16* arow = nullptr;
+      if (EPI) {
+        const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
+        const bool valid = (n < p.No) && (h < p.Ho) && (w < p.Wo);
+        if (p.add_mode && valid) arow = p.add + n * p.a_sn + (h >> p.add_shift) * p.a_sh + (w >> p.add_shift) * p.a_sw;
+      }
+      const int buf = local & 1;
+      const uint32_t use = (uint32_t)(local >> 1);
+      mbar_wait(&tfull[buf], use & 1, 0xA00 + buf);
+      tc_fence_after();
+      const uint32_t tacc = taddr + buf * NT + (uint32_t(q * 32) << 16);
+#pragma unroll 1
+      for (int sl = grp; sl < NT / 64; sl += 2) {
+        const int ch0 = cout0 + sl * 64;
+        if (ch0 >= p.Cout) break;                // uniform across the group
+        uint32_t v[64];
+        {
+          uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+          uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+          tmem_ld32(tacc + sl * 64, lo);
+          tmem_ld32(tacc + sl * 64 + 32, hi);
+        }
+        uint8_t* slab = my_slabs + (nstore % Cfg::NSLAB_G) * Cfg::SLAB;
+        // the TMA store that last read this staging buffer must have finished reading it
+        if (nstore >= Cfg::NSLAB_G) {
+          if (et == 0) tma_store_wait_read<Cfg::NSLAB_G - 1>();
+          named_bar_sync(bar_id, 128);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+          if (EPI) {
+            const int ch = ch0 + g * 8;
+            if (p.bias && ch < p.Cout) {
+              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + ch);
+              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + ch + 4);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (arow && ch < p.Cout) {
+              float a[8];
+              unpack8(*reinterpret_cast<const bf16x8*>(arow + ch), a);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j]) + a[j];
+            }
+          }
+          // 128B-swizzled staging: 16-byte chunk g of row r lives at chunk (g ^ (r & 7))
+          *reinterpret_cast<bf16x8*>(slab + sw_row + ((uint32_t(g) ^ sw_x) << 4)) = pack8(f);
+        }
+        fence_proxy_async();                     // generic-proxy smem writes -> visible to the TMA (async proxy)
+        named_bar_sync(bar_id, 128);
+        if (et == 0) {
+          tma_store_5d(&tmC, slab, ch0, w0, h0, n0, 0);
+          tma_store_commit();
+        }
+        ++nstore;
+      }
+      // all TMEM reads of this accumulator by this warp are complete: hand it back to the MMA warp
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+    if (et == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(taddr, Cfg::TMEM_COLS);
+  }
+}
+
+static int g_igemm_variant = 2;   // 2 = persistent + TMA store (default), 1 = one tile per CTA, direct stores
+static int g_num_sms = 0;
+
 static int pow2_le(int x, int cap) {
   int r = 1;
   while (r * 2 <= x && r * 2 <= cap) r *= 2;
@@ -217,6 +426,34 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
   return cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
 }
 
+template <int NT, bool EPI>
+static int launch_igemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const IgemmParams& p,
+                           cudaStream_t st) {
+  using Cfg = Igemm2Cfg<NT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(igemm2_kernel<NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
+      return EVB_ERR_CUDA;
+    attr_set = true;
+  }
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  const int ntiles = p.tiles_c * p.tiles_w * p.tiles_h * p.tiles_n;
+  const int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
+  igemm2_kernel<NT, EPI><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, tmC, p);
+  return cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
+}
+template <int NT>
+static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const IgemmParams& p,
+                         cudaStream_t st) {
+  if (p.bias || p.add_mode) return launch_igemm2_t<NT, true>(tmA, tmB, tmC, p, st);
+  return launch_igemm2_t<NT, false>(tmA, tmB, tmC, p, st);
+}
+
 // Core host entry: `a` is the tensor the A boxes are cut from, (To_n, To_h, To_w) the pixel grid the tiles
 // enumerate (output grid for fwd / stride-1 dgrad, per-phase grid for stride-2 dgrad).
 static int run_igemm(const ADesc& a, int a_stride, const void* wpk, int w_rows, int w_cin, int w_slabs,
@@ -251,6 +488,22 @@ static int run_igemm(const ADesc& a, int a_stride, const void* wpk, int w_rows, 
   uint32_t wb[3] = {64, (uint32_t)nt, 1};
   rc = evb_make_tmap_bf16(&tmB, wpk, 3, wd, ws, wb);
   if (rc) return rc;
+  if (g_igemm_variant == 2) {
+    // output tensor map for the TMA-store epilogue: (channel, w, h, n, 1) with the caller's strides (covers the strided
+    // per-phase outputs of the stride-2 dgrad); channels >= Cout and pixels outside the image are clipped by the TMA.
+    CUtensorMap tmC;
+    uint64_t od[5] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.No, 1};
+    uint64_t os[4] = {(uint64_t)p.o_sw * 2, (uint64_t)p.o_sh * 2, (uint64_t)p.o_sn * 2, (uint64_t)p.o_sn * p.No * 2};
+    uint32_t ob[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, 1};
+    rc = evb_make_tmap_bf16(&tmC, p.out, 5, od, os, ob);
+    if (rc) return rc;
+    switch (nt) {
+      case 256: return launch_igemm2<256>(tmA, tmB, tmC, p, st);
+      case 128: return launch_igemm2<128>(tmA, tmB, tmC, p, st);
+      case 64: return launch_igemm2<64>(tmA, tmB, tmC, p, st);
+    }
+    return EVB_ERR_ARG;
+  }
   switch (nt) {
     case 256: return launch_igemm<256>(tmA, tmB, p, st);
     case 128: return launch_igemm<128>(tmA, tmB, p, st);
@@ -262,6 +515,13 @@ static int run_igemm(const ADesc& a, int a_stride, const void* wpk, int w_rows, 
 }  // namespace evb
 
 using namespace evb;
+
+// 2 = persistent kernel with TMA-store epilogue (default), 1 = one tile per CTA with direct stores (kept for A/B tests)
+extern "C" int evb_set_igemm_variant(int v) {
+  if (v != 1 && v != 2) return EVB_ERR_ARG;
+  g_igemm_variant = v;
+  return EVB_OK;
+}
 
 // y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w) (+bias) (+add).  ksize in {1,3}, pad = ksize/2, stride in {1,2}.
 // wpk: bf16 [ksize*ksize][w_rows][Cin], w_rows >= Cout.  add_mode: 0 none, 1 same-shape bf16 tensor,

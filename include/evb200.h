@@ -34,6 +34,9 @@ int evb_device_sync_check(void);
  * sampled nearest (FPN top-down add, ever/module/fpn.py:96-105).  force_nt: 0 = auto tile, else 64|128|256. */
 int evb_conv2d_fwd(const void* x, int N, int H, int W, int Cin, const void* wpk, int w_rows, int ksize, int stride,
                    void* y, int Cout, const float* bias, const void* add, int add_mode, int force_nt, void* stream);
+/* kernel variant for evb_conv2d_fwd/dgrad: 2 = persistent, TMEM double-buffered, TMA-store epilogue (default);
+ * 1 = one tile per CTA with direct global stores (kept for A/B measurements). */
+int evb_set_igemm_variant(int v);
 /* dx[N,H,W,Cin] (+)= conv_transpose(dy[N,Ho,Wo,Cout]).  wpk_t: bf16 [ksize*ksize][w_rows>=Cin][Cout]. */
 int evb_conv2d_dgrad(const void* dy, int N, int Ho, int Wo, int Cout, const void* wpk_t, int w_rows, int ksize,
                      int stride, void* dx, int H, int W, int Cin, int accumulate, int force_nt, void* stream);

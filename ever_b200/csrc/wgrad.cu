@@ -377,7 +377,7 @@ static WgradPlan plan_wgrad(int N, int Ho, int Wo, int Cin, int Cout, int ntaps,
   pl.tn = (N + pl.bn - 1) / pl.bn;
   pl.nchunks = pl.tw * pl.th * pl.tn;
   const int base = ntaps * pl.tiles_ci * pl.tiles_co;
-  int split = force_split ? force_split : (2 * 148) / base;  // round down: at most two full waves of CTAs
+  int split = force_split ? force_split : 148 / base;  // round down: one full wave of CTAs (measured best, tools/exp_wgrad.py)
   if (split > pl.nchunks) split = pl.nchunks;
   if (!force_split && split > 74) split = 74;   // bounds the reduction depth (and workspace) of small-channel convs
   if (!force_split) {

@@ -333,13 +333,17 @@ class FarSegEngine:
         return y
 
     def bn_relu_up(self, x, bp, f=2, train=True):
-        """decoder stage: bilinear x f of relu(bn(x)) (fpn.py:163-169)."""
+        """decoder stage: bilinear x f of relu(bn(x)) (fpn.py:163-169).  BN+ReLU is applied once at the low resolution
+        (the tensor is f*f times smaller than the output), then a pure bilinear kernel writes the up-sampled map."""
         L = self.L
         fold = self._bn_fold(x, bp, train)
         n, h, w, c = x.data.shape
+        low_y = self._new(n, h, w, c)
+        check(L.evb_bn_apply(ptr(x.data), ptr(fold[2]), ptr(fold[3]), None, ptr(low_y), c_ll(n * h * w), c_int(c), c_int(1),
+                             stream()), 'evb_bn_apply')
         y = Act(self._new(n, h * f, w * f, c))
-        check(L.evb_bilinear_up(ptr(x.data), ptr(fold[2]), ptr(fold[3]), ptr(y.data), c_int(n), c_int(h), c_int(w),
-                                c_int(c), c_int(c), c_int(c), c_int(f), stream()), 'evb_bilinear_up')
+        check(L.evb_bilinear_up(ptr(low_y), None, None, ptr(y.data), c_int(n), c_int(h), c_int(w), c_int(c), c_int(c),
+                                c_int(c), c_int(f), stream()), 'evb_bilinear_up')
         if train:
             def bwd():
                 if y.grad is None:

@@ -51,7 +51,7 @@ def _oracle_step(ora, x, y, autocast):
     return logit.detach(), {k: float(v) for k, v in losses.items()}, feats
 
 
-CASES = [('resnet18', 5, 128, 2, 128, 128), ('resnet50', 15, 256, 2, 128, 128)]
+CASES = [('resnet18', 5, 128, 2, 128, 128), ('resnet50', 15, 256, 2, 128, 128), ('resnet18', 5, 128, 3, 96, 160)]
 
 
 @pytest.mark.parametrize('case', CASES)
@@ -95,7 +95,7 @@ def test_train_step_parity(case):
     worst = sorted(grads.items(), key=lambda kv: -kv[1])[:8]
     rep['worst'] = worst
     os.makedirs('gpurun_out', exist_ok=True)
-    json.dump(rep, open('gpurun_out/parity_%s.json' % resnet, 'w'), indent=1)
+    json.dump(rep, open('gpurun_out/parity_%s_%dx%dx%d.json' % (resnet, n, h, w), 'w'), indent=1)
     print(json.dumps(dict(losses=rep['loss_mine'], bf16=loss_bf, fp32=loss_32, worst=worst)))
     for kk in ('ce_loss', 'dice_loss'):
         assert abs(rep['loss_mine'][kk] - loss_bf[kk]) <= 1e-2 * abs(loss_bf[kk]), (kk, rep['loss_mine'], loss_bf)

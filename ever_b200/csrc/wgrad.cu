@@ -31,21 +31,23 @@ struct WgradParams {
   int CinP, CoutP, Cin, Cout;
 };
 
-template <int NT>
+// MT = number of 128-row input-channel tiles per CTA.  MT = 2 keeps two accumulators in TMEM that share every dY (B)
+// tile: one third less L2->SM traffic per FLOP (the wgrad main loop is L2-fed, see profiles/).
+template <int NT, int MT>
 struct WgradCfg {
-  static constexpr int A_BYTES = 2 * 64 * 128;
+  static constexpr int A_BYTES = MT * 2 * 64 * 128;
   static constexpr int B_BYTES = (NT / 64) * 64 * 128;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (NT == 256) ? 4 : (NT == 128) ? 6 : 8;
+  static constexpr int STAGES = (STAGE >= 65536) ? 3 : (STAGE >= 49152) ? 4 : (STAGE >= 32768) ? 6 : 8;
   static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
-  static constexpr int TMEM_COLS = NT;
+  static constexpr int TMEM_COLS = NT * MT;
 };
 
-template <int NT>
+template <int NT, int MT>
 __global__ void __launch_bounds__(192, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
              const __grid_constant__ WgradParams p) {
-  using Cfg = WgradCfg<NT>;
+  using Cfg = WgradCfg<NT, MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE);
@@ -59,7 +61,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   const int tci = t % p.tiles_ci; t /= p.tiles_ci;
   const int tap = t % p.ntaps;
   const int split = t / p.ntaps;
-  const int ci0 = tci * 128, co0 = tco * NT;
+  const int ci0 = tci * 128 * MT, co0 = tco * NT;
   const int c_begin = split * p.chunks_per_split;
   const int c_end = min(p.nchunks, c_begin + p.chunks_per_split);
   const int niter = max(0, c_end - c_begin);
@@ -96,7 +98,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         uint8_t* a_dst = smem + stage * Cfg::STAGE;
         mbar_arrive_expect_tx(&full[stage], Cfg::STAGE);
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+        for (int s = 0; s < 2 * MT; ++s)
           tma_load_5d(a_dst + s * 8192, &tmX, &full[stage], tp.coff + ci0 + s * 64, w0 + tp.dw, h0 + tp.dh, n0, tp.phase);
 #pragma unroll
         for (int s = 0; s < NT / 64; ++s)
@@ -117,8 +119,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // 16 pixels (K) per MMA = 2 swizzle atoms of 8 rows x 128 B; LBO = 64-channel slab stride
-          umma_bf16(taddr, make_smem_desc(a_base + k * 2048, 8192, 1024), make_smem_desc(b_base + k * 2048, 8192, 1024),
-                    idesc, (it | k) != 0);
+          const uint64_t bdesc = make_smem_desc(b_base + k * 2048, 8192, 1024);
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+            umma_bf16(taddr + m * NT, make_smem_desc(a_base + m * 16384 + k * 2048, 8192, 1024), bdesc, idesc,
+                      (it | k) != 0);
         }
         umma_commit(&empty[stage]);
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -130,36 +135,41 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     const int r = q * 32 + lane;  // input channel within the tile
     mbar_wait(tfull, 0, 0x600);
     tc_fence_after();
-    if (p.ws) {
-      float* orow = p.ws + (((long long)split * p.ntaps + tap) * p.CinP + ci0 + r) * p.CoutP + co0;
 #pragma unroll 1
-      for (int c = 0; c < NT / 32; ++c) {
-        uint32_t v[32];
-        if (niter > 0) {
-          tmem_ld32(taddr + (uint32_t(q * 32) << 16) + c * 32, v);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0;
-        }
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<uint4*>(orow + c * 32 + g * 4) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-      }
-    } else if (niter > 0) {
-      float* orow = p.acc + (((long long)tap) * p.CinP + ci0 + r) * p.CoutP + co0;
-      const bool row_ok = (ci0 + r) < p.Cin;
+    for (int m = 0; m < MT; ++m) {
+      const int ci = ci0 + m * 128 + r;
+      const uint32_t tm = taddr + (uint32_t(q * 32) << 16) + m * NT;
+      if (p.ws) {
+        float* orow = p.ws + (((long long)split * p.ntaps + tap) * p.CinP + ci) * p.CoutP + co0;
 #pragma unroll 1
-      for (int c = 0; c < NT / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t(q * 32) << 16) + c * 32, v);   // warp-collective: outside the row predicate
-        tmem_ld_wait();
-        if (row_ok && co0 + c * 32 < p.Cout) {
+        for (int c = 0; c < NT / 32; ++c) {
+          uint32_t v[32];
+          if (niter > 0) {
+            tmem_ld32(tm + c * 32, v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0;
+          }
 #pragma unroll
           for (int g = 0; g < 8; ++g)
-            atomicAdd(reinterpret_cast<float4*>(orow + c * 32 + g * 4),
-                      make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
-                                  __uint_as_float(v[g * 4 + 3])));
+            *reinterpret_cast<uint4*>(orow + c * 32 + g * 4) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        }
+      } else if (niter > 0) {
+        float* orow = p.acc + (((long long)tap) * p.CinP + ci) * p.CoutP + co0;
+        const bool row_ok = ci < p.Cin;
+#pragma unroll 1
+        for (int c = 0; c < NT / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tm + c * 32, v);   // warp-collective: outside the row predicate
+          tmem_ld_wait();
+          if (row_ok && co0 + c * 32 < p.Cout) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              atomicAdd(reinterpret_cast<float4*>(orow + c * 32 + g * 4),
+                        make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
+                                    __uint_as_float(v[g * 4 + 3])));
+          }
         }
       }
     }
@@ -343,31 +353,30 @@ static int make_act_map(CUtensorMap* m, const void* ptr, int N, int H, int W, in
   return evb_make_tmap_bf16(m, ptr, 5, dims, strides, box);
 }
 
-template <int NT>
+template <int NT, int MT>
 static int launch_wgrad(const CUtensorMap& a, const CUtensorMap& b, const WgradParams& p, cudaStream_t st) {
-  using Cfg = WgradCfg<NT>;
+  using Cfg = WgradCfg<NT, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(wgrad_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(wgrad_kernel<NT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
       return EVB_ERR_CUDA;
     attr_set = true;
   }
   const int grid = p.nsplit * p.ntaps * p.tiles_ci * p.tiles_co;
-  wgrad_kernel<NT><<<grid, 192, Cfg::SMEM, st>>>(a, b, p);
+  wgrad_kernel<NT, MT><<<grid, 192, Cfg::SMEM, st>>>(a, b, p);
   return cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
 }
 
 struct WgradPlan {
-  int nt, nsplit, cps, CinP, CoutP, tiles_ci, tiles_co, nchunks, bw, bh, bn, tw, th, tn;
+  int nt, mt, nsplit, cps, CinP, CoutP, tiles_ci, tiles_co, nchunks, bw, bh, bn, tw, th, tn;
   size_t ws_bytes;
 };
 
-static WgradPlan plan_wgrad(int N, int Ho, int Wo, int Cin, int Cout, int ntaps, int force_nt, int force_split) {
+static WgradPlan plan_wgrad(int N, int Ho, int Wo, int Cin, int Cout, int ntaps, int force_nt, int force_split,
+                            int allow_mt2 = 1) {
   WgradPlan pl{};
   pl.nt = force_nt ? force_nt : (Cout >= 256 ? 256 : (Cout >= 128 ? 128 : 64));
-  pl.tiles_ci = (Cin + 127) / 128;
   pl.tiles_co = (Cout + pl.nt - 1) / pl.nt;
-  pl.CinP = pl.tiles_ci * 128;
   pl.CoutP = pl.tiles_co * pl.nt;
   pl.bw = pow2_le(Wo, 64);
   pl.bh = pow2_le(Ho, 64 / pl.bw);
@@ -376,6 +385,16 @@ static WgradPlan plan_wgrad(int N, int Ho, int Wo, int Cin, int Cout, int ntaps,
   pl.th = (Ho + pl.bh - 1) / pl.bh;
   pl.tn = (N + pl.bn - 1) / pl.bn;
   pl.nchunks = pl.tw * pl.th * pl.tn;
+  // two M tiles per CTA when the channel count allows it and a full wave of CTAs can still be formed
+  pl.mt = 1;
+  if (allow_mt2 && pl.nt >= 128 && Cin >= 256) {
+    const int base2 = ntaps * ((Cin + 255) / 256) * pl.tiles_co;
+    int sp = 148 / base2 > 0 ? 148 / base2 : 1;
+    if (sp > (pl.nchunks + 7) / 8) sp = (pl.nchunks + 7) / 8;
+    if (base2 * sp >= 110) pl.mt = 2;
+  }
+  pl.tiles_ci = (Cin + 128 * pl.mt - 1) / (128 * pl.mt);
+  pl.CinP = pl.tiles_ci * 128 * pl.mt;
   const int base = ntaps * pl.tiles_ci * pl.tiles_co;
   int split = force_split ? force_split : 148 / base;  // round down: one full wave of CTAs (measured best, tools/exp_wgrad.py)
   if (split > pl.nchunks) split = pl.nchunks;
@@ -409,7 +428,7 @@ static int wgrad_impl(const void* x, int N, int H, int W, int Cin, const void* d
   if (Cin % 64 || Cout % 64) return EVB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int Ho = H / stride, Wo = W / stride, ntaps = ksize * ksize;
-  const WgradPlan pl = plan_wgrad(N, Ho, Wo, Cin, Cout, ntaps, force_nt, force_split);
+  const WgradPlan pl = plan_wgrad(N, Ho, Wo, Cin, Cout, ntaps, force_nt, force_split, acc ? 0 : 1);
   if (!acc && (size_t)ws_bytes < pl.ws_bytes) return EVB_ERR_ARG;
   WgradParams p{};
   p.ntaps = ntaps;
@@ -436,10 +455,12 @@ static int wgrad_impl(const void* x, int N, int H, int W, int Cin, const void* d
   if (rc) return rc;
   rc = make_act_map(&tmDY, dy, N, Ho, Wo, Cout, 1, pl.bw, pl.bh, pl.bn);
   if (rc) return rc;
-  switch (pl.nt) {
-    case 256: rc = launch_wgrad<256>(tmX, tmDY, p, st); break;
-    case 128: rc = launch_wgrad<128>(tmX, tmDY, p, st); break;
-    case 64: rc = launch_wgrad<64>(tmX, tmDY, p, st); break;
+  switch (pl.nt * 10 + pl.mt) {
+    case 2562: rc = launch_wgrad<256, 2>(tmX, tmDY, p, st); break;
+    case 2561: rc = launch_wgrad<256, 1>(tmX, tmDY, p, st); break;
+    case 1282: rc = launch_wgrad<128, 2>(tmX, tmDY, p, st); break;
+    case 1281: rc = launch_wgrad<128, 1>(tmX, tmDY, p, st); break;
+    case 641: rc = launch_wgrad<64, 1>(tmX, tmDY, p, st); break;
     default: rc = EVB_ERR_ARG;
   }
   if (rc) return rc;
@@ -472,7 +493,7 @@ extern "C" int evb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, con
 
 // Padded staging layout used by evb_conv2d_wgrad_acc: acc is fp32 [k*k][CinP][CoutP].
 extern "C" int evb_conv2d_wgrad_layout(int Cin, int Cout, int* CinP, int* CoutP) {
-  const WgradPlan pl = plan_wgrad(1, 64, 64, Cin, Cout, 1, 0, 1);
+  const WgradPlan pl = plan_wgrad(1, 64, 64, Cin, Cout, 1, 0, 1, 0);
   *CinP = pl.CinP;
   *CoutP = pl.CoutP;
   return EVB_OK;

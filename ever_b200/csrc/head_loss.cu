@@ -345,6 +345,58 @@ loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restric
   }
 }
 
+// Binary head (K == 1): masked BCE-with-logits (ever/module/loss.py:229-235, _masked_ignore :10-17) + sigmoid Dice
+// (dice_loss_with_logits K==1 branch, loss.py:66-68).  logits: channel 0 of [P, LD]; labels in {0, 1, ignore}.
+// stats = {sum softplus(z) - z*y, n_valid, I = sum p*y, sum p, sum y}; coef = {bce_w / n_valid, A, B}.
+template <int PASS>
+__global__ void __launch_bounds__(256)
+loss_binary_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restrict__ labels, long long P, int LD,
+                   int ignore_index, float* __restrict__ partial, const float* __restrict__ coef,
+                   __nv_bfloat16* __restrict__ dlogits) {
+  __shared__ float red[8][5];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const long long t = labels[p];
+    const bool valid = t != ignore_index;
+    const float z = __bfloat162float(logits[p * LD]);
+    const float y = (float)t;
+    const float pr = 1.f / (1.f + expf(-z));
+    if (PASS == 0) {
+      if (valid) {
+        acc[0] += fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));
+        acc[1] += 1.f;
+        acc[2] += pr * y;
+        acc[3] += pr;
+        acc[4] += y;
+      }
+    } else {
+      float d = 0.f;
+      if (valid) {
+        const float g = coef[2] - y * coef[1];  // B - y * A
+        d = bf16_round((pr - y) * coef[0]) + bf16_round(pr * (1.f - pr) * g);
+      }
+      float v[8] = {d, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      *reinterpret_cast<bf16x8*>(dlogits + p * LD) = pack8(v);
+      const float zz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int c0 = 8; c0 < LD; c0 += 8) *reinterpret_cast<bf16x8*>(dlogits + p * LD + c0) = pack8(zz);
+    }
+  }
+  if (PASS == 0) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const float v = warp_sum(acc[i]);
+      if (lane == 0) red[wid][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+      float s_ = 0.f;
+      for (int w = 0; w < 8; ++w) s_ += red[w][threadIdx.x];
+      partial[(long long)blockIdx.x * 5 + threadIdx.x] = s_;
+    }
+  }
+}
+
 // stats[i] = sum_blocks partial (double accumulation, fixed order)
 __global__ void loss_reduce_kernel(const float* __restrict__ partial, int nblk, int n, float* __restrict__ stats) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -477,8 +529,14 @@ extern "C" long long evb_loss_workspace(long long P, int K) { return (long long)
 // Pass A: statistics of softmax-CE + Dice over valid pixels -> stats[2+3K] (device, fp32).
 extern "C" int evb_loss_stats(const void* logits, const void* labels, long long P, int K, int LD, int ignore_index,
                               float* stats, void* ws, void* stream) {
-  if (K < 2 || K > kMaxK || LD != 16) return EVB_ERR_ARG;
+  if (K < 1 || K > kMaxK || LD != 16) return EVB_ERR_ARG;
   const int nb = loss_blocks(P), n = 2 + 3 * K;
+  if (K == 1) {
+    loss_binary_kernel<0><<<nb, 256, 0, ST>>>((const __nv_bfloat16*)logits, (const long long*)labels, P, LD, ignore_index,
+                                              (float*)ws, nullptr, nullptr);
+    loss_reduce_kernel<<<1, 128, 0, ST>>>((const float*)ws, nb, n, stats);
+    return LAUNCH_OK();
+  }
 #define EVB_LOSS_LAUNCH(PASS_, GRID_, ...)                                                        \
   switch (K) {                                                                                   \
     case 15: loss_kernel<PASS_, 15><<<GRID_, 256, 0, ST>>>(__VA_ARGS__); break;                  \
@@ -502,7 +560,12 @@ extern "C" int evb_loss_finalize(const float* stats, const float* dice_stats, in
 // Pass B: dlogits[P, LD] bf16 (padding channels zeroed).
 extern "C" int evb_loss_grad(const void* logits, const void* labels, long long P, int K, int LD, int ignore_index,
                              const float* coef, void* dlogits, void* stream) {
-  if (K < 2 || K > kMaxK || LD != 16) return EVB_ERR_ARG;
+  if (K < 1 || K > kMaxK || LD != 16) return EVB_ERR_ARG;
+  if (K == 1) {
+    loss_binary_kernel<1><<<loss_blocks(P), 256, 0, ST>>>((const __nv_bfloat16*)logits, (const long long*)labels, P, LD,
+                                                          ignore_index, nullptr, coef, (__nv_bfloat16*)dlogits);
+    return LAUNCH_OK();
+  }
   EVB_LOSS_LAUNCH(1, loss_blocks(P), (const __nv_bfloat16*)logits, (const long long*)labels, P, K, LD, ignore_index,
                   nullptr, coef, (__nv_bfloat16*)dlogits)
   return LAUNCH_OK();
@@ -540,6 +603,12 @@ __global__ void softmax_nchw_kernel(const __nv_bfloat16* __restrict__ logits, fl
                                     uint8_t* __restrict__ mask, long long P, int HW, int K, int LD) {
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
     const __nv_bfloat16* row = logits + p * LD;
+    if (K == 1) {  // binary head: sigmoid probability, mask = p > 0.5
+      const float pr = 1.f / (1.f + expf(-__bfloat162float(row[0])));
+      if (prob) prob[p] = pr;
+      if (mask) mask[p] = pr > 0.5f ? 1 : 0;
+      continue;
+    }
     float z[kMaxK];
     for (int c = 0; c < K; ++c) z[c] = __bfloat162float(row[c]);
     float mx = z[0];

@@ -81,8 +81,7 @@ class FarSegEngine:
         self.smooth = float(cfg.loss.dice.smooth)
         self.sync_dice = bool(cfg.loss.dice.sync_statistics)
         self.K = module.head.fpn_decoder.num_classes
-        if self.K < 2:
-            raise NotImplementedError('num_classes >= 2 (softmax CE + Dice); the binary sigmoid head is not built yet')
+        # K == 1: binary head -> masked BCE-with-logits + sigmoid Dice (ever/module/loss.py:66-68,229-235)
 
     # ------------------------------------------------------------------ parameters
     def _flatten_params(self):
@@ -285,7 +284,7 @@ class FarSegEngine:
         c = bp.c
         stats = self._new(4, c, dtype=torch.float32)
         mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
-        if train:
+        if train and bn.training:
             m_rows = x.data.numel() // c
             ws = self._ws(L.evb_bn_workspace(c_ll(m_rows), c_int(c)))
             mom = 0.1 if bn.momentum is None else bn.momentum
@@ -309,7 +308,7 @@ class FarSegEngine:
         if dres_act is not None and dres_act.needs_grad:
             dres, dres_acc = self._grad_into(dres_act)
         check(L.evb_bn_bwd(ptr(dy), ptr(x.data), ptr(ymask), ptr(mean), ptr(rstd), ptr(scale), ptr(shift),
-                           c_int(mask_mode), c_int(0), ptr(gx), ptr(dres), c_int(1 if dres_acc else 0),
+                           c_int(mask_mode), c_int(0 if bp.bn.training else 1), ptr(gx), ptr(dres), c_int(1 if dres_acc else 0),
                            ptr(bp.bn.weight.grad), ptr(bp.bn.bias.grad), c_int(1 if self.accumulate else 0),
                            c_ll(m_rows), c_int(c), ptr(ws), stream()), 'evb_bn_bwd')
 
@@ -422,9 +421,14 @@ class FarSegEngine:
         y = self.maxpool(y, train=train)
         self._dbg('pool', y)
         feats = []
+        freeze_at = int(self.m.config.encoder.freeze_at)
         for si, blocks in enumerate(self.stages):
+            if train and freeze_at >= si + 1:
+                y.needs_grad = False   # everything that produced y is frozen: no gradient flows further down
             for d in blocks:
                 y = self._block(y, d, train)
+            if train and freeze_at >= si + 2:
+                y.needs_grad = False   # this stage and everything below it are frozen
             feats.append(y)
             self._dbg('c%d' % (si + 2), y)
         return feats
@@ -608,8 +612,9 @@ class FarSegEngine:
                                   c_float(self.dice_w), c_float(scale), ptr(losses), ptr(coef), stream()),
               'evb_loss_finalize')
         self._saved_for_backward = (cls, logits, labels, coef, npx)
-        return dict(ce_loss=losses[0] * self.ce_w if self.ce_w != 1.0 else losses[0],
-                    dice_loss=losses[1] * self.dice_w if self.dice_w != 1.0 else losses[1])
+        first = 'bce_loss' if self.K == 1 else 'ce_loss'
+        return {first: losses[0] * self.ce_w if self.ce_w != 1.0 else losses[0],
+                'dice_loss': losses[1] * self.dice_w if self.dice_w != 1.0 else losses[1]}
 
     def forward_train(self, x, labels):
         self._forward_part1(x, labels)

@@ -152,6 +152,31 @@ class FarSegB200(ERModule):
             head.fs_relation.scene_embedding_channels = chans[-1]
         self.head = _Head(head)
         self.engine = None
+        if int(enc.output_stride) != 32:
+            raise NotImplementedError('FarSeg needs output_stride 32 (the FPN top-down x2 adds assume a /2 pyramid)')
+        self._freeze()
+
+    def _freeze(self):
+        """ResNetEncoder._frozen_res_bn / _freeze_at (ever/module/resnet.py:155-173,227-234): frozen BN layers run on their
+        running statistics and have frozen affine parameters; freeze_at >= k freezes the stem (1) and layer1..4 (2..5)."""
+        enc, r = self.config.encoder, self.en.resnet
+        if not bool(enc.batchnorm_trainable):
+            for m in r.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    for p in m.parameters():
+                        p.requires_grad = False
+                    m.eval()
+        groups = [[r.conv1, r.bn1], [r.layer1], [r.layer2], [r.layer3], [r.layer4]]
+        for i, g in enumerate(groups, 1):
+            if int(enc.freeze_at) >= i:
+                for m in g:
+                    for p in m.parameters():
+                        p.requires_grad = False
+
+    def train(self, mode=True):
+        super().train(mode)
+        self._freeze()
+        return self
 
     def set_default_config(self):
         self.config.update(dict(

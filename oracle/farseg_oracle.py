@@ -121,10 +121,34 @@ class ResNetEncoderOracle(nn.Module):
     """ResNetEncoder.forward, reference ever/module/resnet.py:183-211 (defaults :213-225:
     output_stride 32, include_conv5, trainable BN, freeze_at 0)."""
 
-    def __init__(self, resnet_type='resnet50', in_channels=3):
+    def __init__(self, resnet_type='resnet50', in_channels=3, freeze_at=0, batchnorm_trainable=True):
         super().__init__()
         self.resnet = _ResNetTrunk(resnet_type, in_channels)
         self.out_channels = tuple(c * RESNET_SPECS[resnet_type][0].expansion for c in (64, 128, 256, 512))
+        self.freeze_at, self.batchnorm_trainable = freeze_at, batchnorm_trainable
+        self._freeze()
+
+    def _freeze(self):
+        """_frozen_res_bn / _freeze_at, reference ever/module/resnet.py:155-173 (param_util.freeze_params sets
+        requires_grad=False; frozen BN additionally runs in eval mode, :227-234)."""
+        r = self.resnet
+        if not self.batchnorm_trainable:
+            for m in r.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    for p in m.parameters():
+                        p.requires_grad = False
+                    m.eval()
+        groups = [[r.conv1, r.bn1], [r.layer1], [r.layer2], [r.layer3], [r.layer4]]
+        for i, g in enumerate(groups, 1):
+            if self.freeze_at >= i:
+                for m in g:
+                    for p in m.parameters():
+                        p.requires_grad = False
+
+    def train(self, mode=True):
+        super().train(mode)
+        self._freeze()
+        return self
 
     def forward(self, x):
         r = self.resnet
@@ -295,9 +319,10 @@ class FarSegOracle(nn.Module):
     """The glue ERModule of SURVEY.md Appendix E: encoder -> FarSegHead -> {ce_loss, dice_loss}
     in training, softmax probabilities in eval."""
 
-    def __init__(self, resnet_type='resnet50', num_classes=15, decoder_channels=256, in_channels=3):
+    def __init__(self, resnet_type='resnet50', num_classes=15, decoder_channels=256, in_channels=3, freeze_at=0,
+                 batchnorm_trainable=True):
         super().__init__()
-        self.en = ResNetEncoderOracle(resnet_type, in_channels)
+        self.en = ResNetEncoderOracle(resnet_type, in_channels, freeze_at, batchnorm_trainable)
         self.head = FarSegHeadOracle(self.en.out_channels, 256, decoder_channels, num_classes)
         self.dice_all_reduce = None
 

@@ -19,11 +19,11 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-12))
 
 
-def _build(resnet, k, dec):
+def _build(resnet, k, dec, freeze_at=0, bn_trainable=True):
     from ever_b200.module import FarSegB200
     from oracle.farseg_oracle import FarSegOracle, deterministic_fill
-    ora = deterministic_fill(FarSegOracle(resnet, k, dec), 0)
-    mine = FarSegB200(dict(encoder=dict(resnet_type=resnet),
+    ora = deterministic_fill(FarSegOracle(resnet, k, dec, freeze_at=freeze_at, batchnorm_trainable=bn_trainable), 0)
+    mine = FarSegB200(dict(encoder=dict(resnet_type=resnet, freeze_at=freeze_at, batchnorm_trainable=bn_trainable),
                            head=dict(fpn_decoder=dict(out_channels=dec, classifier_config=dict(num_classes=k)))))
     mine.load_state_dict(ora.state_dict(), strict=True)
     return ora, mine
@@ -42,25 +42,42 @@ def _oracle_step(ora, x, y, autocast):
         hooks.append(mod.register_forward_hook(lambda m, i, o, name=name: feats.__setitem__(name, o.detach())))
     with torch.autocast('cuda', dtype=torch.bfloat16, enabled=autocast):
         logit = ora.logits(x)
-        from oracle.farseg_oracle import dice_loss_oracle
-        losses = dict(ce_loss=F.cross_entropy(logit, y.long(), ignore_index=255),
-                      dice_loss=dice_loss_oracle(logit, y, ignore_index=255))
+        from oracle.farseg_oracle import bce_loss_oracle, dice_loss_oracle
+        if logit.shape[1] == 1:
+            losses = dict(bce_loss=bce_loss_oracle(logit, y), dice_loss=dice_loss_oracle(logit, y, ignore_index=255))
+        else:
+            losses = dict(ce_loss=F.cross_entropy(logit, y.long(), ignore_index=255),
+                          dice_loss=dice_loss_oracle(logit, y, ignore_index=255))
     sum(losses.values()).backward()
     for h in hooks:
         h.remove()
     return logit.detach(), {k: float(v) for k, v in losses.items()}, feats
 
 
-CASES = [('resnet18', 5, 128, 2, 128, 128), ('resnet50', 15, 256, 2, 128, 128), ('resnet18', 5, 128, 3, 96, 160)]
+CASES = [('resnet18', 5, 128, 2, 128, 128), ('resnet50', 15, 256, 2, 128, 128), ('resnet18', 5, 128, 3, 96, 160),
+         ('resnet18', 1, 128, 2, 128, 128), ('resnet50', 5, 128, 2, 128, 128, dict(freeze_at=2, bn_trainable=False))]
 
 
 @pytest.mark.parametrize('case', CASES)
 def test_train_step_parity(case):
     from oracle.farseg_oracle import synthetic_batch
-    resnet, k, dec, n, h, w = case
-    ora, mine = _build(resnet, k, dec)
-    x, y = synthetic_batch(n, h, w, k)
+    resnet, k, dec, n, h, w = case[:6]
+    opts = case[6] if len(case) > 6 else {}
+    ora, mine = _build(resnet, k, dec, **opts)
+    x, y = synthetic_batch(n, h, w, max(k, 2))
     x, y = x.cuda(), y.cuda()
+    if opts.get('bn_trainable') is False:
+        # frozen BN runs on running statistics: calibrate them to the batch statistics first so the random-weight
+        # network is well scaled (otherwise sigmoids saturate and most reference gradients are ~0)
+        cal, _ = _build(resnet, k, dec)
+        cal = cal.cuda().train()
+        for m_ in cal.modules():
+            if isinstance(m_, torch.nn.BatchNorm2d):
+                m_.momentum = 1.0
+        with torch.no_grad():
+            cal.logits(x)
+        ora.load_state_dict(cal.state_dict())
+        mine.load_state_dict(cal.state_dict())
     ora = ora.cuda()
     mine = mine.cuda().train()
     torch.backends.cudnn.allow_tf32 = False
@@ -83,11 +100,19 @@ def test_train_step_parity(case):
                          _rel(feats_bf[name].float(), feats_32[name].float()))
     fwd['logits'] = (_rel(dbg['logits'].float().permute(0, 3, 1, 2)[:, :k], logit_bf.float()), _rel(logit_bf.float(), logit_32))
     print(json.dumps(fwd))
-    rep = dict(fwd=fwd, case=case, loss_mine={kk: float(v) for kk, v in out.items()}, loss_bf16=loss_bf, loss_fp32=loss_32)
+    rep = dict(fwd=fwd, case=[str(c) for c in case], loss_mine={kk: float(v) for kk, v in out.items()}, loss_bf16=loss_bf, loss_fp32=loss_32)
     # logits: engine keeps NHWC [.,16] bf16
     grads, ref_noise = {}, {}
     pm, pb, p32 = dict(mine.named_parameters()), dict(ora.named_parameters()), dict(ora32.named_parameters())
+    gmax = max(float(p_.grad.norm()) for p_ in pb.values() if p_.grad is not None)
     for name in pm:
+        if pb[name].grad is not None and float(pb[name].grad.norm()) < 1e-6 * gmax:
+            assert float(pm[name].grad.norm()) < 1e-4 * gmax, name   # numerically-zero gradient in the reference
+            continue
+        if pb[name].grad is None:   # frozen in the reference (freeze_at / frozen BN): must be frozen here too
+            assert not pm[name].requires_grad, name
+            continue
+        assert pm[name].requires_grad, name
         grads[name] = _rel(pm[name].grad, pb[name].grad)
         ref_noise[name] = _rel(pb[name].grad, p32[name].grad)
     rep['grad_rel_vs_bf16'] = grads
@@ -97,7 +122,7 @@ def test_train_step_parity(case):
     os.makedirs('gpurun_out', exist_ok=True)
     json.dump(rep, open('gpurun_out/parity_%s_%dx%dx%d.json' % (resnet, n, h, w), 'w'), indent=1)
     print(json.dumps(dict(losses=rep['loss_mine'], bf16=loss_bf, fp32=loss_32, worst=worst)))
-    for kk in ('ce_loss', 'dice_loss'):
+    for kk in loss_bf:
         assert abs(rep['loss_mine'][kk] - loss_bf[kk]) <= 1e-2 * abs(loss_bf[kk]), (kk, rep['loss_mine'], loss_bf)
     # per-tensor gradient gate: the engine must be as close to the bf16 reference as that reference is to
     # its own fp32 run (x3 slack), and within 5e-2 absolute relative-L2 everywhere

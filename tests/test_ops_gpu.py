@@ -280,3 +280,35 @@ def test_pack_im2col_sgd():
         assert abs(float(norm[0]) - float(tn)) < 1e-4 * float(tn)
         assert _rel(mine_w, p.data) < 1e-6
         assert float(gm.abs().max()) == 0
+
+
+def test_loss_binary():
+    """K == 1: masked BCE-with-logits + sigmoid Dice (ever/module/loss.py:66-68, 229-235) and their logit gradient."""
+    L, check, ptr, stream = _L()
+    g = _gen(9)
+    n, h, w = 2, 32, 48
+    npx = n * h * w
+    logits = torch.zeros(n, h, w, 16, device='cuda', dtype=torch.bfloat16)
+    logits[..., 0] = torch.randn(n, h, w, device='cuda', generator=g).bfloat16()
+    labels = torch.randint(0, 2, (n, h, w), device='cuda', generator=g)
+    labels[torch.rand(n, h, w, device='cuda', generator=g) < 0.1] = 255
+    stats = torch.empty(5, device='cuda')
+    ws = torch.empty(L.evb_loss_workspace(c_ll(npx), c_int(1)) // 4 + 64, device='cuda')
+    losses, coef = torch.empty(2, device='cuda'), torch.empty(3, device='cuda')
+    dl = torch.empty_like(logits)
+    check(L.evb_loss_stats(ptr(logits), ptr(labels), c_ll(npx), c_int(1), c_int(16), c_int(255), ptr(stats), ptr(ws),
+                           stream()), 'ls')
+    check(L.evb_loss_finalize(ptr(stats), None, c_int(1), c_float(1.0), c_float(1.0), c_float(1.0), c_float(1.0),
+                              ptr(losses), ptr(coef), stream()), 'lf')
+    check(L.evb_loss_grad(ptr(logits), ptr(labels), c_ll(npx), c_int(1), c_int(16), c_int(255), ptr(coef), ptr(dl),
+                          stream()), 'lg')
+    torch.cuda.synchronize()
+    from oracle.farseg_oracle import bce_loss_oracle, dice_loss_oracle
+    lr = logits[..., :1].float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    bce = bce_loss_oracle(lr, labels)
+    dice = dice_loss_oracle(lr, labels)
+    (bce + dice).backward()
+    assert abs(float(losses[0]) - float(bce)) < 1e-4 * abs(float(bce))
+    assert abs(float(losses[1]) - float(dice)) < 1e-4 * abs(float(dice))
+    assert _rel(dl[..., :1].float(), nhwc(lr.grad)) < 8e-3
+    assert float(dl[..., 1:].abs().max()) == 0.0

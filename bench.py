@@ -27,7 +27,7 @@ GFLOP_PER_TILE = 343.1  # fwd 114.8 + bwd 228.3, FlopCounterMode on the referenc
 METRIC = 'FarSeg-R50 512x512 tiles/s fwd+bwd'
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the ncu --set full capture
 # summarised in profiles/ (None until captured)
-NCU_TRAFFIC_BYTES = None
+NCU_TRAFFIC_BYTES = 68309248 + 24216576  # profiles/r01_ncu_full_prof_igemm2_3x3.txt
 
 
 def peaks():

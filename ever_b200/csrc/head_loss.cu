@@ -84,14 +84,15 @@ relation_fwd_kernel(const __nv_bfloat16* __restrict__ u1, const __nv_bfloat16* _
   }
 }
 
-// g1/g2 [M,C] = gradient w.r.t. the two BN outputs (ReLU masks applied); dsf[n][c] += sum_pixels dlogit * cf.
+// g1/g2 [M,C] = gradient w.r.t. the two BN outputs (ReLU masks applied); dsf_part[warp][c] = sum over the warp's pixels
+// of dlogit * cf (px_per_warp divides HW, so a warp never straddles two images; reduced deterministically afterwards).
 template <int NG, int PX>
 __global__ void __launch_bounds__(256)
 relation_bwd_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ u1,
                     const __nv_bfloat16* __restrict__ u2, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ scale2, const float* __restrict__ shift2, const float* __restrict__ sf,
                     const float* __restrict__ rel, __nv_bfloat16* __restrict__ g1, __nv_bfloat16* __restrict__ g2,
-                    float* __restrict__ dsf, long long M, int HW, int px_per_warp) {
+                    float* __restrict__ dsf_part, long long M, int HW, int px_per_warp) {
   constexpr int C = 256 * NG;
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -129,12 +130,6 @@ relation_bwd_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* _
       if (m >= mend) break;
       const int n = (int)(m / HW);
       if (n != cur_n) {
-        if (cur_n >= 0) {
-#pragma unroll
-          for (int a = 0; a < NG; ++a)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { atomicAdd(dsf + cur_n * C + lane * 8 + 256 * a + j, acc[a][j]); acc[a][j] = 0.f; }
-        }
         cur_n = n;
 #pragma unroll
         for (int a = 0; a < NG; ++a)
@@ -172,11 +167,27 @@ relation_bwd_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* _
       }
     }
   }
-  if (cur_n >= 0) {
 #pragma unroll
-    for (int a = 0; a < NG; ++a)
+  for (int a = 0; a < NG; ++a) {
+    float* dst = dsf_part + warp * C + lane * 8 + 256 * a;
+    *reinterpret_cast<float4*>(dst) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
+  }
+}
+
+// dsf[n][c] = sum_{j < wpi} part[n * wpi + j][c]  (fixed order).  block (32 c, 8 row lanes), grid (C/32, N)
+__global__ void relation_dsf_reduce_kernel(const float* __restrict__ part, float* __restrict__ dsf, int wpi, int C) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, n = blockIdx.y;
+  float s = 0.f;
+  for (int j = threadIdx.y; j < wpi; j += 8) s += part[((long long)n * wpi + j) * C + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float t = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(dsf + cur_n * C + lane * 8 + 256 * a + j, acc[a][j]);
+    for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
+    dsf[n * C + c] = t;
   }
 }
 
@@ -487,22 +498,32 @@ extern "C" int evb_relation_fwd(const void* u1, const void* u2, const float* sca
   else relation_fwd_kernel<4, 1><<<(int)blocks, 256, 0, ST>>>(a, b, scale1, shift1, scale2, shift2, sf, zz, rel, M, HW);
   return LAUNCH_OK();
 }
-// dsf must be zeroed by the caller (it is accumulated with atomics).
+static int relation_px_per_warp(int HW) {
+  int p = 16;
+  while (p > 1 && HW % p) p >>= 1;
+  return p;
+}
+extern "C" long long evb_relation_bwd_workspace(long long M, int HW, int C) {
+  return (M / relation_px_per_warp(HW)) * (long long)C * sizeof(float);
+}
+// dsf[N][C] is overwritten: per-warp partial sums go to `ws` and are reduced in a fixed order (deterministic).
 extern "C" int evb_relation_bwd(const void* dz, const void* u1, const void* u2, const float* scale1, const float* shift1,
                                 const float* scale2, const float* shift2, const float* sf, const float* rel, void* g1,
-                                void* g2, float* dsf, long long M, int HW, int C, void* stream) {
-  if (C != 256 && C != 512 && C != 1024) return EVB_ERR_ARG;
-  const int px_per_warp = 16;
-  const long long warps = (M + px_per_warp - 1) / px_per_warp;
+                                void* g2, float* dsf, long long M, int HW, int C, void* ws, void* stream) {
+  if ((C != 256 && C != 512 && C != 1024) || M % HW) return EVB_ERR_ARG;
+  const int px_per_warp = relation_px_per_warp(HW);
+  const long long warps = M / px_per_warp;
   const long long blocks = (warps + 7) / 8;
   const __nv_bfloat16 *d = (const __nv_bfloat16*)dz, *a = (const __nv_bfloat16*)u1, *b = (const __nv_bfloat16*)u2;
   __nv_bfloat16 *o1 = (__nv_bfloat16*)g1, *o2 = (__nv_bfloat16*)g2;
+  float* part = (float*)ws;
   if (C == 256)
-    relation_bwd_kernel<1, 2><<<(int)blocks, 256, 0, ST>>>(d, a, b, scale1, shift1, scale2, shift2, sf, rel, o1, o2, dsf, M, HW, px_per_warp);
+    relation_bwd_kernel<1, 2><<<(int)blocks, 256, 0, ST>>>(d, a, b, scale1, shift1, scale2, shift2, sf, rel, o1, o2, part, M, HW, px_per_warp);
   else if (C == 512)
-    relation_bwd_kernel<2, 1><<<(int)blocks, 256, 0, ST>>>(d, a, b, scale1, shift1, scale2, shift2, sf, rel, o1, o2, dsf, M, HW, px_per_warp);
+    relation_bwd_kernel<2, 1><<<(int)blocks, 256, 0, ST>>>(d, a, b, scale1, shift1, scale2, shift2, sf, rel, o1, o2, part, M, HW, px_per_warp);
   else
-    relation_bwd_kernel<4, 1><<<(int)blocks, 256, 0, ST>>>(d, a, b, scale1, shift1, scale2, shift2, sf, rel, o1, o2, dsf, M, HW, px_per_warp);
+    relation_bwd_kernel<4, 1><<<(int)blocks, 256, 0, ST>>>(d, a, b, scale1, shift1, scale2, shift2, sf, rel, o1, o2, part, M, HW, px_per_warp);
+  relation_dsf_reduce_kernel<<<dim3(C / 32, (unsigned)(M / HW)), dim3(32, 8), 0, ST>>>(part, dsf, HW / px_per_warp, C);
   return LAUNCH_OK();
 }
 

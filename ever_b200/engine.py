@@ -448,7 +448,7 @@ class FarSegEngine:
                                    c_int(1), stream()), 'evb_linear_fwd')
             check(L.evb_linear_fwd(ptr(hid), ptr(l2.weight), ptr(l2.bias), ptr(sf), c_int(n), c_int(co), c_int(co),
                                    c_int(0), stream()), 'evb_linear_fwd')
-            dsf = torch.zeros(n, co, dtype=torch.float32, device=self.dev) if train else None
+            dsf = self._new(n, co, dtype=torch.float32) if train else None
             outs.append((sf, dsf))
             if train:
                 def bwd(l1=l1, l2=l2, hid=hid, sf=sf, dsf=dsf, co=co):
@@ -519,9 +519,10 @@ class FarSegEngine:
                         return
                     g1 = self._new(*u1.data.shape)
                     g2 = self._new(*u2.data.shape)
+                    ws = self._ws(L.evb_relation_bwd_workspace(c_ll(m_rows), c_int(hh * ww), c_int(c)))
                     check(L.evb_relation_bwd(ptr(z.grad), ptr(u1.data), ptr(u2.data), ptr(f1[2]), ptr(f1[3]), ptr(f2[2]),
                                              ptr(f2[3]), ptr(sf), ptr(rel), ptr(g1), ptr(g2), ptr(dsf), c_ll(m_rows),
-                                             c_int(hh * ww), c_int(c), stream()), 'evb_relation_bwd')
+                                             c_int(hh * ww), c_int(c), ptr(ws), stream()), 'evb_relation_bwd')
                     self._bn_backward(g1, u1, cb, f1, 0, None, None)
                     self._bn_backward(g2, u2, rb, f2, 0, None, None)
                 # must run BEFORE the conv backward closures of u1/u2 (registered earlier => run later): ok

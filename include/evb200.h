@@ -102,9 +102,10 @@ int evb_copy2d_f32(const float* src, int lds, float* dst, int ldd, int rows, int
 /* ---- FS-Relation (FSRelation.forward, ever/module/fs_relation.py:57-73) and the scene-embedding MLP (:22-28) */
 int evb_relation_fwd(const void* u1, const void* u2, const float* scale1, const float* shift1, const float* scale2,
                      const float* shift2, const float* sf, void* z, float* rel, long long M, int HW, int C, void* stream);
+long long evb_relation_bwd_workspace(long long M, int HW, int C);
 int evb_relation_bwd(const void* dz, const void* u1, const void* u2, const float* scale1, const float* shift1,
                      const float* scale2, const float* shift2, const float* sf, const float* rel, void* g1, void* g2,
-                     float* dsf, long long M, int HW, int C, void* stream);
+                     float* dsf, long long M, int HW, int C, void* ws, void* stream);
 int evb_linear_fwd(const float* x, const float* W, const float* b, float* y, int N, int I, int O, int relu, void* stream);
 int evb_linear_bwd(const float* dy, const float* y, const float* x, const float* W, float* dW, float* db, float* dx, int N,
                    int I, int O, int relu, int acc_w, int acc_x, void* stream);

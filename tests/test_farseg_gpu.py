@@ -173,3 +173,59 @@ def test_eval_masks():
     assert rep['logit_rel_mine_vs_bf16'] < max(2e-2, 1.5 * rep['logit_rel_bf16_vs_fp32'])
     assert agree_conf >= 0.999
     assert agree_all >= agree_bf - 0.01
+
+
+def test_full_size_step_properties():
+    """BASELINE configs[1] at full size (FarSeg-R50, 15 classes, 8 x 3 x 512 x 512): losses against the bf16-autocast
+    oracle on the GPU, plus size-independent properties -- run-to-run determinism of the step (bit-identical losses and
+    gradients), CUDA-graph replay ==
+    eager, and gradient accumulation (two identical micro-steps with accumulate=True == 2 x one step)."""
+    from oracle.farseg_oracle import synthetic_batch
+    resnet, k, dec, n, h, w = 'resnet50', 15, 256, 8, 512, 512
+    ora, mine = _build(resnet, k, dec)
+    x, y = synthetic_batch(n, h, w, k)
+    x, y = x.cuda(), y.cuda()
+    ora = ora.cuda()
+    mine = mine.cuda().train()
+    logit_bf, loss_bf, _ = _oracle_step(ora, x, y, True)
+    state0 = {kk: v.clone() for kk, v in mine.state_dict().items()}
+
+    def run():
+        mine.load_state_dict(state0)
+        out = mine(x, dict(cls=y))
+        mine.backward(out, None, None)
+        torch.cuda.synchronize()
+        return {kk: float(v) for kk, v in out.items()}, mine.engine.flat_g.clone()
+    l1, g1 = run()
+    l2, g2 = run()
+    for kk in loss_bf:
+        assert abs(l1[kk] - loss_bf[kk]) <= 1e-2 * abs(loss_bf[kk]), (kk, l1, loss_bf)
+    assert l1 == l2
+    pm = dict(mine.named_parameters())
+    eng = mine.engine
+    # gradients of the oracle (bf16) vs engine on the well-conditioned tensors (last decoder BNs / classifier)
+    pb = dict(ora.named_parameters())
+    for name in ['head.fpn_decoder.classifier.0.weight', 'head.fpn_decoder.blocks.0.0.1.weight',
+                 'head.fpn_decoder.blocks.3.2.1.bias']:
+        assert _rel(pm[name].grad, pb[name].grad) < 5e-2, name
+    # every kernel reduces in a fixed order (no float atomics): the step is bit-reproducible
+    assert torch.equal(g1, g2)
+    # gradient accumulation: second micro-step with accumulate=True doubles the gradient
+    mine.load_state_dict(state0)
+    out = mine(x, dict(cls=y))
+    mine.backward(out, None, None)
+    eng.accumulate = True
+    mine.load_state_dict(state0)   # undo the BN running-stat update only (weights unchanged by backward)
+    out = mine(x, dict(cls=y))
+    mine.backward(out, None, None)
+    eng.accumulate = False
+    torch.cuda.synchronize()
+    assert _rel(eng.flat_g, 2 * g1) < 1e-3
+    # CUDA-graph replay reproduces the eager step
+    mine.load_state_dict(state0)
+    replay, gout = eng.capture_step(x, y)
+    mine.load_state_dict(state0)
+    replay()
+    torch.cuda.synchronize()
+    assert abs(float(gout['ce_loss']) - l1['ce_loss']) < 1e-6 and abs(float(gout['dice_loss']) - l1['dice_loss']) < 1e-6
+    assert torch.equal(eng.flat_g, g1)

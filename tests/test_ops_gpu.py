@@ -166,9 +166,10 @@ def test_relation_fwd_bwd():
                              c_ll(m_rows), c_int(h * w), c_int(c), stream()), 'rel')
     dz = torch.randn(n, h, w, c, device='cuda', generator=g).bfloat16()
     g1, g2 = torch.empty_like(u1), torch.empty_like(u2)
-    dsf = torch.zeros(n, c, device='cuda')
+    dsf = torch.full((n, c), 7.0, device='cuda')   # overwritten, not accumulated
+    ws = torch.empty(L.evb_relation_bwd_workspace(c_ll(m_rows), c_int(h * w), c_int(c)) // 4, device='cuda')
     check(L.evb_relation_bwd(ptr(dz), ptr(u1), ptr(u2), ptr(s1), ptr(b1), ptr(s2), ptr(b2), ptr(sf), ptr(rel), ptr(g1),
-                             ptr(g2), ptr(dsf), c_ll(m_rows), c_int(h * w), c_int(c), stream()), 'relb')
+                             ptr(g2), ptr(dsf), c_ll(m_rows), c_int(h * w), c_int(c), ptr(ws), stream()), 'relb')
     torch.cuda.synchronize()
     # reference: fs_relation.py:57-73 on BN-folded inputs
     a1 = (u1.float() * s1 + b1).requires_grad_(True)

@@ -641,7 +641,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, 
   }
 }
 
-// All convolutions of the model in one launch.  desc[i] = {w, wf, wb, Co, Ci, kk, CoP, CiP, CiPb, CoPb, first_block, -}
+// All convolutions of the model in one launch.  desc[i] = {w, wf, wb, Co, Ci, kk, CoP, CiP, CiPb, CoPb, first_block, w_ld}
+// (w_ld = floats between consecutive output-channel rows of w, 0 -> Ci*kk; lets a conv use a Cin sub-range of a weight)
 // (12 x int64); block_map[b] = descriptor index of block b.  One block = a 32 co x 32 ci tile, all kk <= 9 taps, staged
 // through shared memory so that the OIHW read ((ci,tap) contiguous per co) and both packed writes
 // (wf[tap][co][ci]: ci contiguous; wb[tap][ci][co]: co contiguous) are coalesced.  Padding rows/columns of the packs are
@@ -656,6 +657,7 @@ pack_weights_batched_kernel(const long long* __restrict__ desc, const int* __res
   const int Co = (int)d[3], Ci = (int)d[4], kk = (int)d[5], CoP = (int)d[6], CiP = (int)d[7], CiPb = (int)d[8],
             CoPb = (int)d[9];
   const int t = blockIdx.x - (int)d[10];
+  const long long w_ld = d[11] ? d[11] : (long long)Ci * kk;
   const int tiles_ci = (Ci + 31) / 32;
   const int co0 = (t / tiles_ci) * 32, ci0 = (t % tiles_ci) * 32;
   const int nci = min(32, Ci - ci0);
@@ -663,7 +665,7 @@ pack_weights_batched_kernel(const long long* __restrict__ desc, const int* __res
   for (int idx = threadIdx.x; idx < 32 * run; idx += 256) {
     const int c = idx / run, e = idx % run;
     const int cil = e / kk, tap = e % kk;
-    if (co0 + c < Co) tile[tap][c][cil] = w[((long long)(co0 + c) * Ci + ci0) * kk + e];
+    if (co0 + c < Co) tile[tap][c][cil] = w[(long long)(co0 + c) * w_ld + (long long)ci0 * kk + e];
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < kk * 32 * 32; idx += 256) {

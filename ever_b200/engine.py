@@ -37,25 +37,60 @@ class Act:
 
 
 class ConvP:
-    """One convolution's parameters + bf16 packs."""
+    """One convolution's parameters + bf16 packs.
 
-    def __init__(self, conv, cout_pad=None, cin_pad=None, as_matrix=False):
-        self.weight, self.bias = conv.weight, conv.bias
-        co, ci, kh, kw = conv.weight.shape
-        self.stride = conv.stride[0]
-        if as_matrix:  # 7x7 stem lowered to a GEMM over im2col rows: [Co][Ci*49]
-            ci, kh, kw = ci * kh * kw, 1, 1
-        self.co, self.ci, self.k = co, ci, kh
-        self.cop = cout_pad or _ceil(co, 64)   # rows of the forward pack / channels of dy
-        self.cip = cin_pad or _ceil(ci, 64)
+    The conv may use a Cin sub-range of its weight tensor (w_off / w_ld, e.g. the two halves of ChangeMixin's first
+    conv) and may be zero-padded to the 64-channel granularity of the tensor-core kernel (cop / cip > co / ci): then
+    the weight gradient goes through a dense scratch [cop][cip*k*k] and only the valid block is copied out, and the
+    bias lives in a padded fp32 buffer."""
+
+    def __init__(self, weight, bias=None, stride=1, co=None, ci=None, k=None, cout_pad=None, cin_pad=None, w_off=0, w_ld=0):
+        self.weight, self.bias = weight, bias
+        wco, wci, kh, kw = weight.shape
+        self.stride = stride
+        self.co = wco if co is None else co
+        self.ci = wci if ci is None else ci
+        self.k = kh if k is None else k
+        self.kk = self.k * self.k
+        self.cop = cout_pad or _ceil(self.co, 64)   # rows of the forward pack / channels of dy
+        self.cip = cin_pad or _ceil(self.ci, 64)
+        self.w_off, self.w_ld = w_off, w_ld
+        self.direct_grad = (self.cop == self.co and self.cip == self.ci and w_off == 0 and w_ld == 0)
         self.wf = self.wb = None
         self.need_dgrad = True
+        self.gscr = self.bias_pad = self.dbias_scr = None
+        self._gw = False   # weight/bias gradient already written in this step (shared convs accumulate)
+
+    @staticmethod
+    def from_conv(conv, cout_pad=None, as_matrix=False):
+        if as_matrix:  # 7x7 stem lowered to a GEMM over im2col rows: [Co][Ci*49]
+            co, ci, kh, kw = conv.weight.shape
+            return ConvP(conv.weight, conv.bias, 1, co=co, ci=ci * kh * kw, k=1, cout_pad=cout_pad)
+        return ConvP(conv.weight, conv.bias, conv.stride[0], cout_pad=cout_pad)
 
 
 class BNP:
-    def __init__(self, bn):
+    """BatchNorm parameters; cpad > C gives zero-padded shadow buffers (padded channels: gamma 1, beta 0 -> stay 0)."""
+
+    def __init__(self, bn, cpad=None):
         self.bn = bn
-        self.c = bn.num_features
+        self.c_real = bn.num_features
+        self.c = cpad or bn.num_features
+        self.padded = self.c != self.c_real
+        self._gw = False
+        if self.padded:
+            dev = bn.weight.device
+            self.gamma_p = torch.ones(self.c, device=dev)
+            self.beta_p = torch.zeros(self.c, device=dev)
+            self.rm_p = torch.zeros(self.c, device=dev)
+            self.rv_p = torch.ones(self.c, device=dev)
+            self.dgamma_p = torch.zeros(self.c, device=dev)
+            self.dbeta_p = torch.zeros(self.c, device=dev)
+
+    gamma = property(lambda self: self.gamma_p if self.padded else self.bn.weight)
+    beta = property(lambda self: self.beta_p if self.padded else self.bn.bias)
+    rm = property(lambda self: self.rm_p if self.padded else self.bn.running_mean)
+    rv = property(lambda self: self.rv_p if self.padded else self.bn.running_var)
 
 
 class FarSegEngine:
@@ -117,23 +152,33 @@ class FarSegEngine:
         self.kind = r.kind
         self.convs = []
 
+        self.bns, self.bns_padded = [], []
+
+        def BNP_(bn, **kw):
+            bp = BNP(bn, **kw)
+            self.bns.append(bp)
+            if bp.padded:
+                self.bns_padded.append(bp)
+            return bp
+        self._mk_bn = BNP_
+
         def C(conv, **kw):
-            cp = ConvP(conv, **kw)
+            cp = ConvP.from_conv(conv, **kw)
             self.convs.append(cp)
             return cp
         self.stem_kp = _ceil(r.conv1.in_channels * 49, 64)
-        self.stem = C(r.conv1, as_matrix=True)
+        self.stem = C(r.conv1, as_matrix=True)   # [64][Cin*49] GEMM; Cin*49 padded to stem_kp
         self.stem.need_dgrad = False
-        self.stem_bn = BNP(r.bn1)
+        self.stem_bn = BNP_(r.bn1)
         self.stages = []
         for li in range(1, 5):
             blocks = []
             for b in getattr(r, 'layer%d' % li):
-                d = dict(stride=b.stride, c1=C(b.conv1), b1=BNP(b.bn1), c2=C(b.conv2), b2=BNP(b.bn2))
+                d = dict(stride=b.stride, c1=C(b.conv1), b1=BNP_(b.bn1), c2=C(b.conv2), b2=BNP_(b.bn2))
                 if self.kind == 'bottleneck':
-                    d.update(c3=C(b.conv3), b3=BNP(b.bn3))
+                    d.update(c3=C(b.conv3), b3=BNP_(b.bn3))
                 if b.downsample is not None:
-                    d.update(cd=C(b.downsample[0]), bd=BNP(b.downsample[1]))
+                    d.update(cd=C(b.downsample[0]), bd=BNP_(b.downsample[1]))
                 blocks.append(d)
             self.stages.append(blocks)
         h = m.head
@@ -141,13 +186,20 @@ class FarSegEngine:
         self.fpn_layer = [C(getattr(h.fpn, 'fpn_layer%d' % i)[0]) for i in range(1, 5)]
         fs = h.fs_relation
         self.scene = [(s[0], s[2]) for s in fs.scene_encoder]  # (conv 2048->256, conv 256->256) as linears
-        self.content = [(C(s[0]), BNP(s[1])) for s in fs.content_encoders]
-        self.reenc = [(C(s[0]), BNP(s[1])) for s in fs.feature_reencoders]
+        self.content = [(C(s[0]), BNP_(s[1])) for s in fs.content_encoders]
+        self.reenc = [(C(s[0]), BNP_(s[1])) for s in fs.feature_reencoders]
         dec = h.fpn_decoder
-        self.dec_blocks = [[(C(layer[0]), BNP(layer[1])) for layer in blk] for blk in dec.blocks]
+        self.dec_blocks = [[(C(layer[0]), BNP_(layer[1])) for layer in blk] for blk in dec.blocks]
         self.dec_nup = list(dec.num_upsample)
         self.cls = C(dec.classifier[0], cout_pad=64)
         self.cls_scale = dec.scale_factor
+        self._collect_extra()
+        self._alloc_packs()
+
+    def _collect_extra(self):
+        """hook for derived engines (extra heads): append their ConvP objects to self.convs here"""
+
+    def _alloc_packs(self):
         # bf16 pack arena
         tot = 0
         for cp in self.convs:
@@ -164,19 +216,21 @@ class FarSegEngine:
             cp.wf = self.pack[cp._off_f:cp._off_f + kk * cp.cop * cp.cip].view(kk, cp.cop, cp.cip)
             if cp.need_dgrad:
                 cp.wb = self.pack[cp._off_b:cp._off_b + kk * cp.cip * cp.cop].view(kk, cp.cip, cp.cop)
-        # padded classifier bias (64 floats) and scratch for padded wgrad outputs
-        self.cls_bias_pad = torch.zeros(64, dtype=torch.float32, device=self.dev)
-        self.scr_cls_dw = torch.zeros(64 * self.cls.ci, dtype=torch.float32, device=self.dev)
-        self.scr_cls_db = torch.zeros(64, dtype=torch.float32, device=self.dev)
-        self.scr_stem_dw = torch.zeros(64 * self.stem_kp, dtype=torch.float32, device=self.dev)
+        # padded convs: dense scratch for the weight gradient, padded bias + bias-gradient buffers
+        for cp in self.convs:
+            if not cp.direct_grad:
+                cp.gscr = torch.zeros(cp.cop * cp.cip * cp.kk, dtype=torch.float32, device=self.dev)
+            if cp.bias is not None and cp.cop != cp.co:
+                cp.bias_pad = torch.zeros(cp.cop, dtype=torch.float32, device=self.dev)
+                cp.dbias_scr = torch.zeros(cp.cop, dtype=torch.float32, device=self.dev)
 
     def _build_pack_table(self):
         rows, bmap, nblk = [], [], 0
         for i, cp in enumerate(self.convs):
             kk = cp.k * cp.k
             nb = ((cp.co + 31) // 32) * ((cp.ci + 31) // 32)   # one block per 32x32 (co, ci) tile, all taps
-            rows.append([cp.weight.data_ptr(), cp.wf.data_ptr(), cp.wb.data_ptr() if cp.need_dgrad else 0, cp.co, cp.ci, kk,
-                         cp.cop, cp.cip, cp.cip, cp.cop, nblk, 0])
+            rows.append([cp.weight.data_ptr() + 4 * cp.w_off, cp.wf.data_ptr(), cp.wb.data_ptr() if cp.need_dgrad else 0,
+                         cp.co, cp.ci, kk, cp.cop, cp.cip, cp.cip, cp.cop, nblk, cp.w_ld])
             bmap += [i] * nb
             nblk += nb
         self._pack_desc = torch.tensor(rows, dtype=torch.int64, device=self.dev)
@@ -191,8 +245,19 @@ class FarSegEngine:
             self._build_pack_table()
         check(self.L.evb_pack_weights_batched(ptr(self._pack_desc), ptr(self._pack_map), c_int(self._pack_nblk), st),
               'evb_pack_weights_batched')
-        check(self.L.evb_copy2d_f32(ptr(self.cls.bias), c_int(self.K), ptr(self.cls_bias_pad), c_int(64), c_int(1),
-                                    c_int(self.K), c_int(0), st), 'evb_copy2d_f32')
+        for cp in self.convs:
+            cp._gw = False
+            if cp.bias_pad is not None:
+                check(self.L.evb_copy2d_f32(ptr(cp.bias), c_int(cp.co), ptr(cp.bias_pad), c_int(cp.cop), c_int(1),
+                                            c_int(cp.co), c_int(0), st), 'evb_copy2d_f32')
+        for bp in self.bns:
+            bp._gw = False
+        for bp in self.bns_padded:   # refresh the zero-padded shadow BN parameters
+            bn = bp.bn
+            for src, dst in ((bn.weight, bp.gamma_p), (bn.bias, bp.beta_p), (bn.running_mean, bp.rm_p),
+                             (bn.running_var, bp.rv_p)):
+                check(self.L.evb_copy2d_f32(ptr(src), c_int(bp.c_real), ptr(dst), c_int(bp.c), c_int(1), c_int(bp.c_real),
+                                            c_int(0), st), 'evb_copy2d_f32')
 
     # ------------------------------------------------------------------ workspace
     def _ws(self, nbytes):
@@ -217,15 +282,53 @@ class FarSegEngine:
         act.has_grad = True
         return act.grad, acc
 
-    def conv(self, x, cp, stride=None, bias=None, add=None, add_mode=0, out_channels=None, train=True):
+    def _wgrad(self, cp, x_data, dy, n, h, w, cin, cout, stride):
+        """weight gradient of one conv use; shared convs (used twice in a step) accumulate."""
+        L = self.L
+        st = stream()
+        if cp.weight.grad is None:
+            return
+        ho, wo = h // stride, w // stride
+        nbytes = L.evb_conv2d_wgrad_workspace(c_int(n), c_int(ho), c_int(wo), c_int(cin), c_int(cout), c_int(cp.k), c_int(0),
+                                              c_int(0))
+        ws = self._ws(nbytes)
+        acc = self.accumulate or cp._gw
+        target = cp.weight.grad if cp.direct_grad else cp.gscr
+        check(L.evb_conv2d_wgrad(ptr(x_data), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(dy), c_int(cout), c_int(cp.k),
+                                 c_int(stride), ptr(target), c_int(1 if (acc and cp.direct_grad) else 0), ptr(ws),
+                                 c_ll(self.ws_bytes), c_int(0), c_int(0), st), 'evb_conv2d_wgrad')
+        if not cp.direct_grad:   # copy the valid [co][ci*kk] block of the dense scratch [cop][cip*kk] into the OIHW grad
+            dst = ctypes.c_void_p(cp.weight.grad.data_ptr() + 4 * cp.w_off)
+            check(L.evb_copy2d_f32(ptr(cp.gscr), c_int(cp.cip * cp.kk), dst, c_int(cp.w_ld or cp.ci * cp.kk), c_int(cp.co),
+                                   c_int(cp.ci * cp.kk), c_int(1 if acc else 0), st), 'evb_copy2d_f32')
+
+    def _bias_grad(self, cp, dy, m_rows, cout):
+        L = self.L
+        st = stream()
+        if cp.bias is None or cp.bias.grad is None:
+            return
+        acc = self.accumulate or cp._gw
+        ws = self._ws(L.evb_bn_workspace(c_ll(m_rows), c_int(cout)))
+        if cp.bias_pad is not None:
+            check(L.evb_bias_grad(ptr(dy), c_ll(m_rows), c_int(cout), ptr(cp.dbias_scr), None, c_int(0), ptr(ws), st),
+                  'evb_bias_grad')
+            check(L.evb_copy2d_f32(ptr(cp.dbias_scr), c_int(cp.cop), ptr(cp.bias.grad), c_int(cp.co), c_int(1), c_int(cp.co),
+                                   c_int(1 if acc else 0), st), 'evb_copy2d_f32')
+        else:
+            check(L.evb_bias_grad(ptr(dy), c_ll(m_rows), c_int(cout), ptr(cp.bias.grad), None, c_int(1 if acc else 0), ptr(ws),
+                                  st), 'evb_bias_grad')
+
+    def conv(self, x, cp, stride=None, bias=False, add=None, add_mode=0, train=True, dgrad=True):
+        """y = conv(x) (+bias) (+add).  bias=True uses cp.bias (padded copy when the conv is channel-padded)."""
         L = self.L
         stride = cp.stride if stride is None else stride
         n, h, w, cin = x.data.shape
         ho, wo = h // stride, w // stride
-        cout = out_channels or cp.co
+        cout = cp.cop
+        bias_t = (cp.bias_pad if cp.bias_pad is not None else cp.bias) if bias else None
         y = Act(self._new(n, ho, wo, cout))
         check(L.evb_conv2d_fwd(ptr(x.data), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(cp.wf), c_int(cp.cop),
-                               c_int(cp.k), c_int(stride), ptr(y.data), c_int(cout), ptr(bias),
+                               c_int(cp.k), c_int(stride), ptr(y.data), c_int(cout), ptr(bias_t),
                                ptr(add.data if add is not None else None), c_int(add_mode), c_int(0), stream()),
               'evb_conv2d_fwd')
         if train:
@@ -234,33 +337,10 @@ class FarSegEngine:
                     return
                 dy = y.grad
                 st = stream()
-                wgrad_target, copy_rows = cp.weight.grad, None
-                if cp is self.cls:
-                    wgrad_target, copy_rows = self.scr_cls_dw, self.K
-                nbytes = L.evb_conv2d_wgrad_workspace(c_int(n), c_int(ho), c_int(wo), c_int(cin), c_int(cout),
-                                                      c_int(cp.k), c_int(0), c_int(0))
-                ws = self._ws(nbytes)
-                acc = self.accumulate and copy_rows is None
-                if cp.weight.grad is not None:
-                  check(L.evb_conv2d_wgrad(ptr(x.data), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(dy), c_int(cout),
-                                         c_int(cp.k), c_int(stride), ptr(wgrad_target), c_int(1 if acc else 0), ptr(ws),
-                                         c_ll(self.ws_bytes), c_int(0), c_int(0), st), 'evb_conv2d_wgrad')
-                if copy_rows is not None and cp.weight.grad is not None:
-                    check(L.evb_copy2d_f32(ptr(wgrad_target), c_int(cp.ci), ptr(cp.weight.grad), c_int(cp.ci),
-                                           c_int(copy_rows), c_int(cp.ci), c_int(1 if self.accumulate else 0), st),
-                          'evb_copy2d_f32')
-                if cp.bias is not None and cp.bias.grad is not None:
-                    m_rows = n * ho * wo
-                    ws = self._ws(L.evb_bn_workspace(c_ll(m_rows), c_int(cout)))
-                    if cp is self.cls:
-                        check(L.evb_bias_grad(ptr(dy), c_ll(m_rows), c_int(cout), ptr(self.scr_cls_db), None, c_int(0),
-                                              ptr(ws), st), 'evb_bias_grad')
-                        check(L.evb_copy2d_f32(ptr(self.scr_cls_db), c_int(64), ptr(cp.bias.grad), c_int(self.K),
-                                               c_int(1), c_int(self.K), c_int(1 if self.accumulate else 0), st),
-                              'evb_copy2d_f32')
-                    else:
-                        check(L.evb_bias_grad(ptr(dy), c_ll(m_rows), c_int(cout), ptr(cp.bias.grad), None,
-                                              c_int(1 if self.accumulate else 0), ptr(ws), st), 'evb_bias_grad')
+                self._wgrad(cp, x.data, dy, n, h, w, cin, cout, stride)
+                if bias:
+                    self._bias_grad(cp, dy, n * ho * wo, cout)
+                cp._gw = True
                 if add is not None and add.needs_grad:
                     g, acc2 = self._grad_into(add)
                     if add_mode == 2:
@@ -269,7 +349,7 @@ class FarSegEngine:
                     else:
                         check(L.evb_scale_add(ptr(dy), c_float(1.0), ptr(g if acc2 else None), ptr(g),
                                               c_ll(dy.numel()), st), 'evb_scale_add')
-                if x.needs_grad and cp.need_dgrad:
+                if x.needs_grad and cp.need_dgrad and dgrad:
                     g, acc2 = self._grad_into(x)
                     check(L.evb_conv2d_dgrad(ptr(dy), c_int(n), c_int(ho), c_int(wo), c_int(cout), ptr(cp.wb),
                                              c_int(cp.cip), c_int(cp.k), c_int(stride), ptr(g), c_int(h), c_int(w),
@@ -288,13 +368,17 @@ class FarSegEngine:
             m_rows = x.data.numel() // c
             ws = self._ws(L.evb_bn_workspace(c_ll(m_rows), c_int(c)))
             mom = 0.1 if bn.momentum is None else bn.momentum
-            check(L.evb_bn_stats(ptr(x.data), c_ll(m_rows), c_int(c), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
-                                 ptr(bn.running_var), c_float(mom), c_float(bn.eps), ptr(mean), ptr(rstd), ptr(scale),
-                                 ptr(shift), ptr(ws), stream()), 'evb_bn_stats')
+            check(L.evb_bn_stats(ptr(x.data), c_ll(m_rows), c_int(c), ptr(bp.gamma), ptr(bp.beta), ptr(bp.rm), ptr(bp.rv),
+                                 c_float(mom), c_float(bn.eps), ptr(mean), ptr(rstd), ptr(scale), ptr(shift), ptr(ws),
+                                 stream()), 'evb_bn_stats')
+            if bp.padded:   # running statistics back into the module's (unpadded) buffers
+                for src, dst in ((bp.rm_p, bn.running_mean), (bp.rv_p, bn.running_var)):
+                    check(L.evb_copy2d_f32(ptr(src), c_int(bp.c), ptr(dst), c_int(bp.c_real), c_int(1), c_int(bp.c_real),
+                                           c_int(0), stream()), 'evb_copy2d_f32')
             self._bn_tracked.append(bn)
         else:
-            check(L.evb_bn_fold(ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var), c_float(bn.eps),
-                                c_int(c), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), stream()), 'evb_bn_fold')
+            check(L.evb_bn_fold(ptr(bp.gamma), ptr(bp.beta), ptr(bp.rm), ptr(bp.rv), c_float(bn.eps), c_int(c), ptr(scale),
+                                ptr(shift), ptr(mean), ptr(rstd), stream()), 'evb_bn_fold')
         return mean, rstd, scale, shift
 
     def _bn_backward(self, dy, x, bp, fold, mask_mode, ymask, dres_act):
@@ -307,10 +391,18 @@ class FarSegEngine:
         dres, dres_acc = (None, False)
         if dres_act is not None and dres_act.needs_grad:
             dres, dres_acc = self._grad_into(dres_act)
+        acc = self.accumulate or bp._gw
+        dgam = bp.dgamma_p if bp.padded else bp.bn.weight.grad
+        dbet = bp.dbeta_p if bp.padded else bp.bn.bias.grad
         check(L.evb_bn_bwd(ptr(dy), ptr(x.data), ptr(ymask), ptr(mean), ptr(rstd), ptr(scale), ptr(shift),
                            c_int(mask_mode), c_int(0 if bp.bn.training else 1), ptr(gx), ptr(dres), c_int(1 if dres_acc else 0),
-                           ptr(bp.bn.weight.grad), ptr(bp.bn.bias.grad), c_int(1 if self.accumulate else 0),
+                           ptr(dgam), ptr(dbet), c_int(1 if (acc and not bp.padded) else 0),
                            c_ll(m_rows), c_int(c), ptr(ws), stream()), 'evb_bn_bwd')
+        if bp.padded and bp.bn.weight.grad is not None:
+            for src, dst in ((bp.dgamma_p, bp.bn.weight.grad), (bp.dbeta_p, bp.bn.bias.grad)):
+                check(L.evb_copy2d_f32(ptr(src), c_int(bp.c), ptr(dst), c_int(bp.c_real), c_int(1), c_int(bp.c_real),
+                                       c_int(1 if acc else 0), stream()), 'evb_copy2d_f32')
+        bp._gw = True
 
     def bn_act(self, x, bp, relu=True, res=None, train=True):
         L = self.L
@@ -404,15 +496,8 @@ class FarSegEngine:
             def stem_bwd():
                 if y0.grad is None:
                     return
-                nbytes = L.evb_conv2d_wgrad_workspace(c_int(n), c_int(ho), c_int(wo), c_int(self.stem_kp), c_int(64),
-                                                      c_int(1), c_int(0), c_int(0))
-                ws = self._ws(nbytes)
-                check(L.evb_conv2d_wgrad(ptr(a), c_int(n), c_int(ho), c_int(wo), c_int(self.stem_kp), ptr(y0.grad),
-                                         c_int(64), c_int(1), c_int(1), ptr(self.scr_stem_dw), c_int(0), ptr(ws),
-                                         c_ll(self.ws_bytes), c_int(0), c_int(0), stream()), 'evb_conv2d_wgrad(stem)')
-                check(L.evb_copy2d_f32(ptr(self.scr_stem_dw), c_int(self.stem_kp), ptr(stem.weight.grad), c_int(stem.ci),
-                                       c_int(64), c_int(stem.ci), c_int(1 if self.accumulate else 0), stream()),
-                      'evb_copy2d_f32')
+                self._wgrad(stem, a, y0.grad, n, ho, wo, self.stem_kp, 64, 1)
+                stem._gw = True
             self.tape.append(stem_bwd)
         y = y0
         self._dbg('stem_conv', y)
@@ -500,8 +585,8 @@ class FarSegEngine:
         for i in range(4):
             p = ps[i]
             (cc, cb), (rc, rb) = self.content[i], self.reenc[i]
-            u1 = self.conv(p, cc, bias=cc.bias, train=train)
-            u2 = self.conv(p, rc, bias=rc.bias, train=train)
+            u1 = self.conv(p, cc, bias=True, train=train)
+            u2 = self.conv(p, rc, bias=True, train=train)
             f1 = self._bn_fold(u1, cb, train)
             f2 = self._bn_fold(u2, rb, train)
             nn_, hh, ww, c = u1.data.shape
@@ -553,69 +638,96 @@ class FarSegEngine:
                 for o in outs:
                     o.grad, o.has_grad = dq, True
             self.tape.append(bwd)
-        # ---- classifier (Cout padded to 64) + bilinear x4 on the K class channels (channel stride 16)
-        cls = self.conv(merged, self.cls, bias=self.cls_bias_pad, out_channels=64, train=train)
+        self._dbg('merged', merged)
+        return merged
+
+    def _classify(self, feat, cp, f, train, name='logits'):
+        """1x1 / 3x3 classifier conv (Cout zero-padded to 64) + bilinear x f on the first 16 channels -> logits
+        [N, f*h, f*w, 16] (AssymetricDecoder classifier, fpn.py:178-181)."""
+        L = self.L
+        cls = self.conv(feat, cp, bias=True, train=train)
         n, h4, w4, _ = cls.data.shape
-        f = self.cls_scale
         logits = self._new(n, h4 * f, w4 * f, 16)
         check(L.evb_bilinear_up(ptr(cls.data), None, None, ptr(logits), c_int(n), c_int(h4), c_int(w4), c_int(16),
                                 c_int(64), c_int(16), c_int(f), stream()), 'evb_bilinear_up(logits)')
-        self._dbg('merged', merged)
-        self._dbg('cls', cls)
-        self._dbg('logits', logits)
+        self._dbg('cls' if name == 'logits' else name + '_cls', cls)
+        self._dbg(name, logits)
         return cls, logits
 
-    # ------------------------------------------------------------------ public steps
-    def _forward_part1(self, x, labels):
-        """pack weights, encoder, head, loss statistics (everything before the Dice all-reduce)."""
+    # ------------------------------------------------------------------ loss groups
+    def _loss_stats(self, cls, logits, labels, k, f, names, weight=1.0):
+        """Pass A of one loss group (CE+Dice for k >= 2, BCE+Dice for k == 1) on logits [N,H,W,16]."""
         L = self.L
-        self.tape = []
-        self._bn_tracked = []
-        x = x.contiguous().float()
         labels = labels.contiguous()
         if labels.dtype != torch.int64:
             labels = labels.long()
-        self.pack_weights()
-        self.attach_grads()
-        feats = self._encoder(x, True)
-        cls, logits = self._head(feats, True)
         n, hh, ww, _ = logits.shape
         npx = n * hh * ww
-        k = self.K
         stats = self._new(2 + 3 * k, dtype=torch.float32)
         ws = self._ws(L.evb_loss_workspace(c_ll(npx), c_int(k)))
         check(L.evb_loss_stats(ptr(logits), ptr(labels), c_ll(npx), c_int(k), c_int(16), c_int(self.ignore_index),
                                ptr(stats), ptr(ws), stream()), 'evb_loss_stats')
+        g = dict(cls=cls, logits=logits, labels=labels, stats=stats, npx=npx, k=k, f=f, names=names, weight=weight)
+        self._groups.append(g)
+        return g
+
+    def _network_losses(self, x, labels):
+        """encoder + head + loss statistics of every loss group (overridden by derived engines)."""
+        feats = self._encoder(x, True)
+        merged = self._head(feats, True)
+        cls, logits = self._classify(merged, self.cls, self.cls_scale, True)
+        first = 'bce_loss' if self.K == 1 else 'ce_loss'
+        self._loss_stats(cls, logits, labels, self.K, self.cls_scale, (first, 'dice_loss'))
+
+    # ------------------------------------------------------------------ public steps
+    def _forward_part1(self, x, labels):
+        """pack weights, encoder, head, loss statistics (everything before the Dice all-reduce)."""
+        self.tape = []
+        self._bn_tracked = []
+        self._groups = []
+        x = x.contiguous().float()
+        self.pack_weights()
+        self.attach_grads()
+        self._network_losses(x, labels)
         if self._bn_tracked:
             torch._foreach_add_([bn.num_batches_tracked for bn in self._bn_tracked], 1)
-        self._part1 = (cls, logits, labels, stats, npx)
         if self.world > 1 and self.sync_dice:
-            if getattr(self, '_dice_global', None) is None:
-                self._dice_global = torch.zeros(3 * k, dtype=torch.float32, device=self.dev)
+            tot = sum(3 * g['k'] for g in self._groups)
+            if getattr(self, '_dice_global', None) is None or self._dice_global.numel() != tot:
+                self._dice_global = torch.zeros(tot, dtype=torch.float32, device=self.dev)
 
     def _dice_allreduce(self):
-        """all_reduce_sum of the Dice statistics (ever/module/loss.py:20-23,46-48); eager NCCL, never graph-captured."""
+        """all_reduce_sum of the Dice statistics of every loss group in one message (ever/module/loss.py:20-23,46-48);
+        eager NCCL, never graph-captured."""
         if self.world > 1 and self.sync_dice:
             import torch.distributed as dist
-            self._dice_global.copy_(self._part1[3][2:])
+            off = 0
+            for g in self._groups:
+                self._dice_global[off:off + 3 * g['k']].copy_(g['stats'][2:])
+                off += 3 * g['k']
             dist.all_reduce(self._dice_global)
 
     def _forward_part2(self):
         L = self.L
-        cls, logits, labels, stats, npx = self._part1
-        k = self.K
         glob = self.world > 1 and self.sync_dice
-        dice_stats = self._dice_global if glob else stats[2:]
-        scale = float(self.world) if glob else 1.0
-        losses = self._new(2, dtype=torch.float32)
-        coef = self._new(1 + 2 * k, dtype=torch.float32)
-        check(L.evb_loss_finalize(ptr(stats), ptr(dice_stats), c_int(k), c_float(self.smooth), c_float(self.ce_w),
-                                  c_float(self.dice_w), c_float(scale), ptr(losses), ptr(coef), stream()),
-              'evb_loss_finalize')
-        self._saved_for_backward = (cls, logits, labels, coef, npx)
-        first = 'bce_loss' if self.K == 1 else 'ce_loss'
-        return {first: losses[0] * self.ce_w if self.ce_w != 1.0 else losses[0],
-                'dice_loss': losses[1] * self.dice_w if self.dice_w != 1.0 else losses[1]}
+        out, off = {}, 0
+        for g in self._groups:
+            k = g['k']
+            dice_stats = self._dice_global[off:off + 3 * k] if glob else g['stats'][2:]
+            off += 3 * k
+            scale = float(self.world) if glob else 1.0
+            losses = self._new(2, dtype=torch.float32)
+            coef = self._new(1 + 2 * k, dtype=torch.float32)
+            wt = g['weight']
+            check(L.evb_loss_finalize(ptr(g['stats']), ptr(dice_stats), c_int(k), c_float(self.smooth),
+                                      c_float(self.ce_w * wt), c_float(self.dice_w * wt), c_float(scale), ptr(losses),
+                                      ptr(coef), stream()), 'evb_loss_finalize')
+            g['coef'] = coef
+            w0, w1 = self.ce_w * wt, self.dice_w * wt
+            out[g['names'][0]] = losses[0] * w0 if w0 != 1.0 else losses[0]
+            out[g['names'][1]] = losses[1] * w1 if w1 != 1.0 else losses[1]
+        self._saved_for_backward = self._groups
+        return out
 
     def forward_train(self, x, labels):
         self._forward_part1(x, labels)
@@ -626,18 +738,18 @@ class FarSegEngine:
         L = self.L
         if self._saved_for_backward is None:
             raise RuntimeError('backward() without a preceding training forward')
-        cls, logits, labels, coef, npx = self._saved_for_backward
+        groups = self._saved_for_backward
         self._saved_for_backward = None
-        k = self.K
-        n, hh, ww, _ = logits.shape
-        dlogits = self._new(n, hh, ww, 16)
-        check(L.evb_loss_grad(ptr(logits), ptr(labels), c_ll(npx), c_int(k), c_int(16), c_int(self.ignore_index),
-                              ptr(coef), ptr(dlogits), stream()), 'evb_loss_grad')
-        f = self.cls_scale
-        cls.grad = torch.zeros_like(cls.data)   # padding channels 16..63 stay zero
-        cls.has_grad = True
-        check(L.evb_bilinear_up_bwd(ptr(dlogits), ptr(cls.grad), c_int(n), c_int(hh // f), c_int(ww // f), c_int(16),
-                                    c_int(16), c_int(64), c_int(f), stream()), 'evb_bilinear_up_bwd(logits)')
+        for g in groups:
+            logits, cls, k, f = g['logits'], g['cls'], g['k'], g['f']
+            n, hh, ww, _ = logits.shape
+            dlogits = self._new(n, hh, ww, 16)
+            check(L.evb_loss_grad(ptr(logits), ptr(g['labels']), c_ll(g['npx']), c_int(k), c_int(16),
+                                  c_int(self.ignore_index), ptr(g['coef']), ptr(dlogits), stream()), 'evb_loss_grad')
+            cls.grad = torch.zeros_like(cls.data)   # padding channels 16..63 stay zero
+            cls.has_grad = True
+            check(L.evb_bilinear_up_bwd(ptr(dlogits), ptr(cls.grad), c_int(n), c_int(hh // f), c_int(ww // f), c_int(16),
+                                        c_int(16), c_int(64), c_int(f), stream()), 'evb_bilinear_up_bwd(logits)')
         for fn in reversed(self.tape):
             fn()
         self.tape = []
@@ -716,7 +828,8 @@ class FarSegEngine:
         x = x.contiguous().float()
         self.pack_weights()
         feats = self._encoder(x, False)
-        cls, logits = self._head(feats, False)
+        merged = self._head(feats, False)
+        cls, logits = self._classify(merged, self.cls, self.cls_scale, False)
         n, hh, ww, _ = logits.shape
         prob = self._new(n, self.K, hh, ww, dtype=torch.float32)
         mask = self._new(n, hh, ww, dtype=torch.uint8)

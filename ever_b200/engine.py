@@ -839,3 +839,83 @@ class FarSegEngine:
         if return_mask:
             return prob, mask
         return prob
+
+
+class ChangeStarEngine(FarSegEngine):
+    """FarSeg features of both temporal images (one batch of 2N) + ChangeMixin on (f1,f2) and (f2,f1).
+
+    The 16-channel ChangeMixin convolutions run on the tensor-core kernel zero-padded to 64 channels; the first conv
+    over cat(fa, fb) is computed as conv(fa, W[:, :C]) + conv(fb, W[:, C:]) (second conv accumulates in its epilogue), so
+    the concatenation is never materialised.  Both directions share the parameters: their gradients accumulate."""
+
+    def _collect_extra(self):
+        cm = self.m.changemixin.convs
+        w0 = cm[0][0].weight
+        inner, cdec = w0.shape[0], w0.shape[1] // 2
+        ld = 2 * cdec * 9
+        self.cm_a = ConvP(w0, None, 1, co=inner, ci=cdec, k=3, cout_pad=64, w_off=0, w_ld=ld)
+        self.cm_b = ConvP(w0, None, 1, co=inner, ci=cdec, k=3, cout_pad=64, w_off=cdec * 9, w_ld=ld)
+        self.cm_bn0 = self._mk_bn(cm[0][1], cpad=64)
+        self.cm_mid = [(ConvP(cm[i][0].weight, None, 1, cout_pad=64, cin_pad=64), self._mk_bn(cm[i][1], cpad=64))
+                       for i in (1, 2, 3)]
+        self.cm_cls = ConvP(cm[4].weight, cm[4].bias, 1, cout_pad=64, cin_pad=64)
+        self.convs += [self.cm_a, self.cm_b] + [c for c, _ in self.cm_mid] + [self.cm_cls]
+
+    def _split(self, merged, n, train):
+        """views of the t1 / t2 halves of the feature batch; their gradients land in the halves of one buffer"""
+        f1, f2 = Act(merged.data[:n]), Act(merged.data[n:])
+        if train:
+            g = torch.zeros_like(merged.data)
+            f1.grad, f2.grad = g[:n], g[n:]
+
+            def bwd():
+                merged.grad, merged.has_grad = g, True
+            self.tape.append(bwd)
+        return f1, f2
+
+    def _changemixin(self, fa, fb, train, name):
+        u = self.conv(fa, self.cm_a, train=train)
+        u = self.conv(fb, self.cm_b, add=u, add_mode=1, train=train)
+        y = self.bn_act(u, self.cm_bn0, True, train=train)
+        for cp, bp in self.cm_mid:
+            y = self.bn_act(self.conv(y, cp, train=train), bp, True, train=train)
+        return self._classify(y, self.cm_cls, 4, train, name=name)
+
+    @staticmethod
+    def _reorder(x):
+        n, c2, h, w = x.shape
+        return x.view(n, 2, c2 // 2, h, w).transpose(0, 1).reshape(2 * n, c2 // 2, h, w).contiguous().float()
+
+    def _network_losses(self, x, labels):
+        n = x.shape[0]
+        feats = self._encoder(self._reorder(x), True)
+        merged = self._head(feats, True)
+        f1, f2 = self._split(merged, n, True)
+        cls, logits = self._classify(f1, self.cls, self.cls_scale, True)
+        first = 'bce_loss' if self.K == 1 else 'ce_loss'
+        self._loss_stats(cls, logits, labels['cls'], self.K, self.cls_scale, (first, 'dice_loss'))
+        for name, (fa, fb) in (('c12', (f1, f2)), ('c21', (f2, f1))):
+            c, lg = self._changemixin(fa, fb, True, name)
+            self._loss_stats(c, lg, labels['change'], 1, 4, (name + '_bce_loss', name + '_dice_loss'))
+
+    @torch.no_grad()
+    def forward_eval(self, x, return_mask=False):
+        L = self.L
+        self.tape = []
+        n = x.shape[0]
+        self.pack_weights()
+        feats = self._encoder(self._reorder(x), False)
+        merged = self._head(feats, False)
+        f1, f2 = self._split(merged, n, False)
+        cls, logits = self._classify(f1, self.cls, self.cls_scale, False)
+        _, clog = self._changemixin(f1, f2, False, 'c12')
+        out = {}
+        for key, lg, k in (('seg', logits, self.K), ('change', clog, 1)):
+            nn_, hh, ww, _ = lg.shape
+            prob = self._new(nn_, k, hh, ww, dtype=torch.float32)
+            mask = self._new(nn_, hh, ww, dtype=torch.uint8)
+            check(L.evb_softmax_nchw(ptr(lg), ptr(prob), ptr(mask), c_ll(nn_ * hh * ww), c_int(hh * ww), c_int(k), c_int(16),
+                                     stream()), 'evb_softmax_nchw')
+            out[key] = prob
+            out[key + '_mask'] = mask
+        return out

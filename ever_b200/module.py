@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from ._ever_api import MODEL, ERModule
-from .engine import FarSegEngine
+from .engine import ChangeStarEngine, FarSegEngine
 
 RESNETS = {  # block kind, blocks per stage  (ever/module/_resnets.py:241-278)
     'resnet18': ('basic', (2, 2, 2, 2)),
@@ -227,3 +227,55 @@ class FarSegB200(ERModule):
 
 
 MODEL.register('FarSeg', FarSegB200, override=True) if hasattr(MODEL, 'register') else None
+
+
+class _ChangeMixin(nn.Module):
+    """Parameter container of ChangeMixin (Z-Zheng/ChangeStar; not in the reference tree, see oracle/changestar_oracle.py)."""
+
+    def __init__(self, in_channels, inner_channels=16, num_convs=4):
+        super().__init__()
+        layers = [nn.Sequential(nn.Conv2d(in_channels, inner_channels, 3, 1, 1, bias=False), nn.BatchNorm2d(inner_channels),
+                                nn.ReLU(True))]
+        layers += [nn.Sequential(nn.Conv2d(inner_channels, inner_channels, 3, 1, 1, bias=False),
+                                 nn.BatchNorm2d(inner_channels), nn.ReLU(True)) for _ in range(num_convs - 1)]
+        layers += [nn.Conv2d(inner_channels, 1, 3, 1, 1), nn.Identity()]
+        self.convs = nn.Sequential(*layers)
+
+
+@MODEL.register('ChangeStarB200')
+class ChangeStarB200(FarSegB200):
+    """ChangeStar = FarSeg feature extractor on both temporal images + ChangeMixin (bitemporal, temporally symmetric)
+    change head.  forward(x[N, 2*Cin, H, W], y={'cls': t1 labels, 'change': binary change labels}) ->
+    {'ce_loss'|'bce_loss', 'dice_loss', 'c12_bce_loss', 'c12_dice_loss', 'c21_bce_loss', 'c21_dice_loss'};
+    eval -> {'seg': probabilities of t1, 'change': sigmoid(c12)}."""
+
+    def __init__(self, config=None):
+        super().__init__(config)
+        cdec = int(self.config.head.fpn_decoder.out_channels)
+        cm = self.config.changemixin
+        if int(cm.num_convs) != 4 or float(cm.scale_factor) != 4.0:
+            raise NotImplementedError('ChangeMixin with num_convs=4, scale_factor=4')
+        self.changemixin = _ChangeMixin(2 * cdec, int(cm.inner_channels), int(cm.num_convs))
+
+    def set_default_config(self):
+        super().set_default_config()
+        self.config.update(dict(changemixin=dict(inner_channels=16, num_convs=4, scale_factor=4.0)))
+
+    def _engine(self):
+        if self.engine is None:
+            dev = next(self.parameters()).device
+            if dev.type != 'cuda':
+                raise RuntimeError('ChangeStarB200 computes only on a CUDA (sm_100a) device; there is no CPU path')
+            object.__setattr__(self, 'engine', ChangeStarEngine(self))
+        return self.engine
+
+    def forward(self, x, y=None):
+        eng = self._engine()
+        if self.training:
+            if not isinstance(y, dict) or 'cls' not in y or 'change' not in y:
+                raise ValueError("training forward needs y = {'cls': ..., 'change': ...}")
+            return eng.forward_train(x, y)
+        return eng.forward_eval(x)
+
+
+MODEL.register('ChangeStar', ChangeStarB200, override=True) if hasattr(MODEL, 'register') else None

@@ -13,6 +13,9 @@
 
 namespace evb {
 
+// stride of the per-channel rows of the BatchNorm partial-sum buffers [which][C][kNbPad] (column = producing block / CTA)
+constexpr int kNbPad = 320;
+
 // Device-side watchdog: a pipeline wait that spins longer than this many clocks records a code in
 // g_watchdog and traps instead of hanging the GPU (a hang on a shared box is a lost box).
 static __device__ unsigned int g_watchdog[4];

@@ -37,6 +37,7 @@ struct IgemmParams {
   const __nv_bfloat16* add;
   long long a_sn, a_sh, a_sw;
   int add_shift, add_mode;
+  float* stats;   // STATS kernels: BN partial sums [2][Cout][kNbPad], column = blockIdx / tiles_c
 };
 
 template <int NT>
@@ -195,7 +196,9 @@ struct Igemm2Cfg {
 };
 
 // EPI: the epilogue applies a per-channel bias and/or adds a second tensor (compile-time so the plain path is branch-free)
-template <int NT, bool EPI>
+// STATS: the epilogue also accumulates per-channel sum / sum of squares of the bf16-rounded outputs (BatchNorm batch
+//        statistics, fused: no separate read pass over the conv output); requires gridDim.x % tiles_c == 0.
+template <int NT, bool EPI, bool STATS>
 __global__ void __launch_bounds__(320, 1)
 igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ IgemmParams p) {
@@ -208,6 +211,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint64_t* tfull = empty + Cfg::STAGES;   // [2]
   uint64_t* tempty = tfull + 2;            // [2]
   uint32_t* tslot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* rowmask = tslot + 4;           // [tile parity][2 groups][4 quadrants]: valid-row bits of a tile (STATS)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = p.tiles_c * p.tiles_w * p.tiles_h * p.tiles_n;
@@ -300,6 +304,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const uint32_t sw_x = (uint32_t)(r & 7);
     int local = 0;
     int nstore = 0;                              // slabs stored so far by this group
+    float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};   // STATS: channel (et & 63) of this group's slabs, row half (et >> 6)
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++local) {
       int t = tile;
       const int tc = t % p.tiles_c; t /= p.tiles_c;
@@ -312,6 +317,14 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
         const bool valid = (n < p.No) && (h < p.Ho) && (w < p.Wo);
         if (p.add_mode && valid) arow = p.add + n * p.a_sn + (h >> p.add_shift) * p.a_sh + (w >> p.add_shift) * p.a_sw;
+      }
+      if (STATS) {
+        // rows outside the image are clipped by the TMA store but a 3x3 tap can make them non-zero: mask them out of the
+        // statistics.  One 32-bit mask per TMEM quadrant; visible to the group after the post-staging barrier below
+        // (the previous tile's column pass is separated from this write by that tile's own barriers + the tfull wait).
+        const bool valid = (n0 + nl < p.No) && (h0 + hl < p.Ho) && (w0 + wl < p.Wo);
+        const uint32_t m = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) rowmask[(local & 1) * 8 + grp * 4 + q] = m;   // parity double-buffer: see hazard note in DESIGN.md
       }
       const int buf = local & 1;
       const uint32_t use = (uint32_t)(local >> 1);
@@ -365,6 +378,26 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           tma_store_5d(&tmC, slab, ch0, w0, h0, n0, 0);
           tma_store_commit();
         }
+        if (STATS) {
+          // column pass over the staged (bf16-rounded) slab: thread = (channel c, row half); rows outside the image
+          // are exact zeros (zero-filled input, no bias) and add nothing
+          const int c = et & 63, r0 = (et >> 6) * 64;
+          const uint32_t cb = (uint32_t)(c >> 3), co2 = (uint32_t)(c & 7) * 2;
+          float s_ = 0.f, q_ = 0.f;
+          const uint32_t* rm_ = rowmask + (local & 1) * 8 + grp * 4 + (r0 >> 5);
+          const uint32_t m0 = rm_[0], m1 = rm_[1];
+#pragma unroll 8
+          for (int i = 0; i < 64; ++i) {
+            const uint32_t rr = (uint32_t)(r0 + i);
+            float v_ = __bfloat162float(
+                *reinterpret_cast<const __nv_bfloat16*>(slab + rr * 128 + ((cb ^ (rr & 7)) << 4) + co2));
+            v_ = (((i < 32 ? m0 : m1) >> (i & 31)) & 1u) ? v_ : 0.f;
+            s_ += v_;
+            q_ += v_ * v_;
+          }
+          ssum[(sl - grp) >> 1] += s_;
+          ssq[(sl - grp) >> 1] += q_;
+        }
         ++nstore;
       }
       // all TMEM reads of this accumulator by this warp are complete: hand it back to the MMA warp
@@ -372,6 +405,32 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
     if (et == 0) tma_store_wait_all();
+    if (STATS) {
+      // combine the two row halves through this group's (now idle) staging buffer and publish the CTA's partial sums
+      named_bar_sync(bar_id, 128);
+      float* scr = reinterpret_cast<float*>(my_slabs);   // [j][half][64][2]
+      const int c = et & 63, hh = et >> 6;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        scr[((j * 2 + hh) * 64 + c) * 2 + 0] = ssum[j];
+        scr[((j * 2 + hh) * 64 + c) * 2 + 1] = ssq[j];
+      }
+      named_bar_sync(bar_id, 128);
+      if (hh == 0) {
+        const int cout0 = (blockIdx.x % p.tiles_c) * NT;
+        const int slot = blockIdx.x / p.tiles_c;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int sl = grp + 2 * j;
+          const int ch = cout0 + sl * 64 + c;
+          if (sl < NT / 64 && ch < p.Cout) {
+            p.stats[(size_t)ch * kNbPad + slot] = scr[((j * 2 + 0) * 64 + c) * 2 + 0] + scr[((j * 2 + 1) * 64 + c) * 2 + 0];
+            p.stats[((size_t)p.Cout + ch) * kNbPad + slot] =
+                scr[((j * 2 + 0) * 64 + c) * 2 + 1] + scr[((j * 2 + 1) * 64 + c) * 2 + 1];
+          }
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -426,13 +485,14 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
   return cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
 }
 
-template <int NT, bool EPI>
+template <int NT, bool EPI, bool STATS>
 static int launch_igemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const IgemmParams& p,
-                           cudaStream_t st) {
+                           cudaStream_t st, int* nblk_out) {
   using Cfg = Igemm2Cfg<NT>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(igemm2_kernel<NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(igemm2_kernel<NT, EPI, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) !=
+        cudaSuccess)
       return EVB_ERR_CUDA;
     attr_set = true;
   }
@@ -443,21 +503,30 @@ static int launch_igemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   const int ntiles = p.tiles_c * p.tiles_w * p.tiles_h * p.tiles_n;
-  const int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
-  igemm2_kernel<NT, EPI><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, tmC, p);
+  int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
+  if (STATS) {  // a CTA must stay on one output-channel tile: grid is a multiple of tiles_c (ntiles always is)
+    if (grid < ntiles) grid = (grid / p.tiles_c) * p.tiles_c;
+    if (grid < p.tiles_c) return EVB_ERR_ARG;
+    if (nblk_out) *nblk_out = grid / p.tiles_c;
+  }
+  igemm2_kernel<NT, EPI, STATS><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, tmC, p);
   return cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
 }
 template <int NT>
 static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const IgemmParams& p,
-                         cudaStream_t st) {
-  if (p.bias || p.add_mode) return launch_igemm2_t<NT, true>(tmA, tmB, tmC, p, st);
-  return launch_igemm2_t<NT, false>(tmA, tmB, tmC, p, st);
+                         cudaStream_t st, int* nblk_out) {
+  if (p.stats) {
+    if (p.bias || p.add_mode) return EVB_ERR_ARG;
+    return launch_igemm2_t<NT, false, true>(tmA, tmB, tmC, p, st, nblk_out);
+  }
+  if (p.bias || p.add_mode) return launch_igemm2_t<NT, true, false>(tmA, tmB, tmC, p, st, nullptr);
+  return launch_igemm2_t<NT, false, false>(tmA, tmB, tmC, p, st, nullptr);
 }
 
 // Core host entry: `a` is the tensor the A boxes are cut from, (To_n, To_h, To_w) the pixel grid the tiles
 // enumerate (output grid for fwd / stride-1 dgrad, per-phase grid for stride-2 dgrad).
 static int run_igemm(const ADesc& a, int a_stride, const void* wpk, int w_rows, int w_cin, int w_slabs,
-                     IgemmParams p, int force_nt, cudaStream_t st) {
+                     IgemmParams p, int force_nt, cudaStream_t st, int* nblk_out = nullptr) {
   if (a.C % 64 || w_cin % 64 || p.Cout % 8) return EVB_ERR_ARG;
   p.bw = pow2_le(p.Wo, 128);
   p.bh = pow2_le(p.Ho, 128 / p.bw);
@@ -488,6 +557,7 @@ static int run_igemm(const ADesc& a, int a_stride, const void* wpk, int w_rows, 
   uint32_t wb[3] = {64, (uint32_t)nt, 1};
   rc = evb_make_tmap_bf16(&tmB, wpk, 3, wd, ws, wb);
   if (rc) return rc;
+  if (p.stats && g_igemm_variant != 2) return EVB_ERR_ARG;
   if (g_igemm_variant == 2) {
     // output tensor map for the TMA-store epilogue: (channel, w, h, n, 1) with the caller's strides (covers the strided
     // per-phase outputs of the stride-2 dgrad); channels >= Cout and pixels outside the image are clipped by the TMA.
@@ -498,9 +568,9 @@ static int run_igemm(const ADesc& a, int a_stride, const void* wpk, int w_rows, 
     rc = evb_make_tmap_bf16(&tmC, p.out, 5, od, os, ob);
     if (rc) return rc;
     switch (nt) {
-      case 256: return launch_igemm2<256>(tmA, tmB, tmC, p, st);
-      case 128: return launch_igemm2<128>(tmA, tmB, tmC, p, st);
-      case 64: return launch_igemm2<64>(tmA, tmB, tmC, p, st);
+      case 256: return launch_igemm2<256>(tmA, tmB, tmC, p, st, nblk_out);
+      case 128: return launch_igemm2<128>(tmA, tmB, tmC, p, st, nblk_out);
+      case 64: return launch_igemm2<64>(tmA, tmB, tmC, p, st, nblk_out);
     }
     return EVB_ERR_ARG;
   }
@@ -526,11 +596,12 @@ extern "C" int evb_set_igemm_variant(int v) {
 // y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w) (+bias) (+add).  ksize in {1,3}, pad = ksize/2, stride in {1,2}.
 // wpk: bf16 [ksize*ksize][w_rows][Cin], w_rows >= Cout.  add_mode: 0 none, 1 same-shape bf16 tensor,
 // 2 half-resolution tensor [N,Ho/2,Wo/2,Cout] sampled nearest (FPN top-down, ever/module/fpn.py:96-105).
-extern "C" int evb_conv2d_fwd(const void* x, int N, int H, int W, int Cin, const void* wpk, int w_rows, int ksize,
-                              int stride, void* y, int Cout, const float* bias, const void* add, int add_mode,
-                              int force_nt, void* stream) {
+static int conv2d_fwd_impl(const void* x, int N, int H, int W, int Cin, const void* wpk, int w_rows, int ksize, int stride,
+                           void* y, int Cout, const float* bias, const void* add, int add_mode, int force_nt, float* stats,
+                           int* nblk_out, void* stream) {
   if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return EVB_ERR_ARG;
   IgemmParams p{};
+  p.stats = stats;
   const int Ho = H / stride, Wo = W / stride;
   p.kblocks = Cin / 64;
   p.ntaps = ksize * ksize;
@@ -558,7 +629,24 @@ extern "C" int evb_conv2d_fwd(const void* x, int N, int H, int W, int Cin, const
     p.a_sw = Cout; p.a_sh = (long long)Wa * Cout; p.a_sn = (long long)Ha * Wa * Cout;
   }
   ADesc a{x, N, H, W, Cin};
-  return run_igemm(a, stride, wpk, w_rows, Cin, ksize * ksize, p, force_nt, (cudaStream_t)stream);
+  return run_igemm(a, stride, wpk, w_rows, Cin, ksize * ksize, p, force_nt, (cudaStream_t)stream, nblk_out);
+}
+
+extern "C" int evb_conv2d_fwd(const void* x, int N, int H, int W, int Cin, const void* wpk, int w_rows, int ksize,
+                              int stride, void* y, int Cout, const float* bias, const void* add, int add_mode,
+                              int force_nt, void* stream) {
+  return conv2d_fwd_impl(x, N, H, W, Cin, wpk, w_rows, ksize, stride, y, Cout, bias, add, add_mode, force_nt, nullptr,
+                         nullptr, stream);
+}
+
+// Convolution (no bias / add) whose epilogue also emits the BatchNorm batch-statistic partial sums of its bf16 output:
+// partial = fp32 [2][Cout][320] (sum | sum of squares per channel, one column per CTA), *nblk_out columns are valid.
+// Feed them to evb_bn_finalize: replaces the separate evb_bn_stats read pass over the conv output.
+extern "C" int evb_conv2d_fwd_stats(const void* x, int N, int H, int W, int Cin, const void* wpk, int w_rows, int ksize,
+                                    int stride, void* y, int Cout, float* partial, int* nblk_out, void* stream) {
+  if (!partial || !nblk_out) return EVB_ERR_ARG;
+  return conv2d_fwd_impl(x, N, H, W, Cin, wpk, w_rows, ksize, stride, y, Cout, nullptr, nullptr, 0, 0, partial, nblk_out,
+                         stream);
 }
 
 // dx[N,H,W,Cin] (+)= conv_transpose(dy[N,Ho,Wo,Cout], w).  wpk_t: bf16 [ksize*ksize][w_rows>=Cin][Cout]

@@ -12,7 +12,7 @@
 namespace evb {
 
 constexpr int kEwThreads = 256;
-constexpr int kNbPad = 320;   // stride of the per-channel partial rows; colsum grids are capped at 296 blocks (2 per SM)
+// kNbPad (common.cuh): stride of the per-channel partial rows; colsum grids are capped at 296 blocks (2 per SM)
 
 static inline int ew_blocks(long long work, int per_block, int cap = 148 * 16) {
   long long b = (work + per_block - 1) / per_block;
@@ -717,6 +717,17 @@ extern "C" int evb_bn_stats(const void* x, long long M, int C, const float* gamm
       (const __nv_bfloat16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, M, C, (float*)ws);
   bn_finalize_kernel<<<(C + 7) / 8, 256, 0, ST>>>((const float*)ws, nb, M, C, gamma, beta, running_mean, running_var,
                                                       momentum, eps, mean, rstd, scale, shift);
+  return LAUNCH_OK();
+}
+
+// BN training statistics from per-CTA partial sums produced by the convolution epilogue (evb_conv2d_fwd_stats):
+// partial is [2][C][kNbPad] (sum, sum of squares of the bf16-rounded conv output), nblk columns are valid.
+extern "C" int evb_bn_finalize(const float* partial, int nblk, long long M, int C, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float momentum, float eps, float* mean, float* rstd,
+                               float* scale, float* shift, void* stream) {
+  if (nblk < 1 || nblk > kNbPad) return EVB_ERR_ARG;
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, ST>>>(partial, nblk, M, C, gamma, beta, running_mean, running_var, momentum, eps,
+                                                  mean, rstd, scale, shift);
   return LAUNCH_OK();
 }
 

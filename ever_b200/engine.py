@@ -26,10 +26,11 @@ def _ceil(a, b):
 
 class Act:
     """An activation tensor (NHWC bf16) plus its gradient slot."""
-    __slots__ = ('data', 'grad', 'has_grad', 'needs_grad')
+    __slots__ = ('data', 'grad', 'has_grad', 'needs_grad', 'stats')
 
     def __init__(self, data, needs_grad=True):
         self.data, self.grad, self.has_grad, self.needs_grad = data, None, False, needs_grad
+        self.stats = None   # (partial sums, nblk) of BN batch statistics emitted by the producing conv's epilogue
 
     @property
     def shape(self):
@@ -107,6 +108,7 @@ class FarSegEngine:
         self.ws = None
         self.ws_bytes = 0
         self.accumulate = False      # gradient accumulation into existing .grad (forward_times > 1)
+        self.fuse_bn_stats = True    # BN batch statistics in the producing conv's epilogue (evb_conv2d_fwd_stats)
         self._saved_for_backward = None
         self.debug = None            # dict -> named activations are recorded (tests / diagnostics)
         cfg = module.config
@@ -318,8 +320,9 @@ class FarSegEngine:
             check(L.evb_bias_grad(ptr(dy), c_ll(m_rows), c_int(cout), ptr(cp.bias.grad), None, c_int(1 if acc else 0), ptr(ws),
                                   st), 'evb_bias_grad')
 
-    def conv(self, x, cp, stride=None, bias=False, add=None, add_mode=0, train=True, dgrad=True):
-        """y = conv(x) (+bias) (+add).  bias=True uses cp.bias (padded copy when the conv is channel-padded)."""
+    def conv(self, x, cp, stride=None, bias=False, add=None, add_mode=0, train=True, dgrad=True, stats=False):
+        """y = conv(x) (+bias) (+add).  bias=True uses cp.bias (padded copy when the conv is channel-padded).
+        stats=True (training, no bias/add): the epilogue also emits the BN batch-statistic partial sums of y."""
         L = self.L
         stride = cp.stride if stride is None else stride
         n, h, w, cin = x.data.shape
@@ -327,10 +330,18 @@ class FarSegEngine:
         cout = cp.cop
         bias_t = (cp.bias_pad if cp.bias_pad is not None else cp.bias) if bias else None
         y = Act(self._new(n, ho, wo, cout))
-        check(L.evb_conv2d_fwd(ptr(x.data), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(cp.wf), c_int(cp.cop),
-                               c_int(cp.k), c_int(stride), ptr(y.data), c_int(cout), ptr(bias_t),
-                               ptr(add.data if add is not None else None), c_int(add_mode), c_int(0), stream()),
-              'evb_conv2d_fwd')
+        if stats and self.fuse_bn_stats and bias_t is None and add is None:
+            partial = self._new(2 * cout * 320, dtype=torch.float32)
+            nblk = ctypes.c_int(0)
+            check(L.evb_conv2d_fwd_stats(ptr(x.data), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(cp.wf), c_int(cp.cop),
+                                         c_int(cp.k), c_int(stride), ptr(y.data), c_int(cout), ptr(partial),
+                                         ctypes.byref(nblk), stream()), 'evb_conv2d_fwd_stats')
+            y.stats = (partial, nblk.value)
+        else:
+            check(L.evb_conv2d_fwd(ptr(x.data), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(cp.wf), c_int(cp.cop),
+                                   c_int(cp.k), c_int(stride), ptr(y.data), c_int(cout), ptr(bias_t),
+                                   ptr(add.data if add is not None else None), c_int(add_mode), c_int(0), stream()),
+                  'evb_conv2d_fwd')
         if train:
             def bwd():
                 if y.grad is None:
@@ -364,7 +375,19 @@ class FarSegEngine:
         c = bp.c
         stats = self._new(4, c, dtype=torch.float32)
         mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
-        if train and bn.training:
+        if train and bn.training and x.stats is not None:
+            m_rows = x.data.numel() // c
+            mom = 0.1 if bn.momentum is None else bn.momentum
+            partial, nblk = x.stats
+            check(L.evb_bn_finalize(ptr(partial), c_int(nblk), c_ll(m_rows), c_int(c), ptr(bp.gamma), ptr(bp.beta), ptr(bp.rm),
+                                    ptr(bp.rv), c_float(mom), c_float(bn.eps), ptr(mean), ptr(rstd), ptr(scale), ptr(shift),
+                                    stream()), 'evb_bn_finalize')
+            if bp.padded:
+                for src, dst in ((bp.rm_p, bn.running_mean), (bp.rv_p, bn.running_var)):
+                    check(L.evb_copy2d_f32(ptr(src), c_int(bp.c), ptr(dst), c_int(bp.c_real), c_int(1), c_int(bp.c_real),
+                                           c_int(0), stream()), 'evb_copy2d_f32')
+            self._bn_tracked.append(bn)
+        elif train and bn.training:
             m_rows = x.data.numel() // c
             ws = self._ws(L.evb_bn_workspace(c_ll(m_rows), c_int(c)))
             mom = 0.1 if bn.momentum is None else bn.momentum
@@ -467,17 +490,17 @@ class FarSegEngine:
     # ------------------------------------------------------------------ network
     def _block(self, x, d, train):
         if self.kind == 'bottleneck':
-            a1 = self.bn_act(self.conv(x, d['c1'], train=train), d['b1'], True, train=train)
-            a2 = self.bn_act(self.conv(a1, d['c2'], train=train), d['b2'], True, train=train)
-            o3 = self.conv(a2, d['c3'], train=train)
+            a1 = self.bn_act(self.conv(x, d['c1'], train=train, stats=train), d['b1'], True, train=train)
+            a2 = self.bn_act(self.conv(a1, d['c2'], train=train, stats=train), d['b2'], True, train=train)
+            o3 = self.conv(a2, d['c3'], train=train, stats=train)
             last_bn = d['b3']
         else:
-            a1 = self.bn_act(self.conv(x, d['c1'], train=train), d['b1'], True, train=train)
-            o3 = self.conv(a1, d['c2'], train=train)
+            a1 = self.bn_act(self.conv(x, d['c1'], train=train, stats=train), d['b1'], True, train=train)
+            o3 = self.conv(a1, d['c2'], train=train, stats=train)
             last_bn = d['b2']
         idt = x
         if 'cd' in d:
-            idt = self.bn_act(self.conv(x, d['cd'], train=train), d['bd'], False, train=train)
+            idt = self.bn_act(self.conv(x, d['cd'], train=train, stats=train), d['bd'], False, train=train)
         return self.bn_act(o3, last_bn, True, res=idt, train=train)
 
     def _encoder(self, x_nchw, train):
@@ -489,7 +512,7 @@ class FarSegEngine:
         check(L.evb_stem_im2col(ptr(x_nchw), ptr(a), c_int(n), c_int(cin), c_int(h), c_int(w), c_int(self.stem_kp),
                                 stream()), 'evb_stem_im2col')
         xa = Act(a, needs_grad=False)
-        y0 = self.conv(xa, self.stem, stride=1, train=False)   # distinct name: the closure below must keep THIS Act
+        y0 = self.conv(xa, self.stem, stride=1, train=False, stats=train)   # distinct name: the closure below keeps THIS Act
         if train:
             stem, ho, wo = self.stem, h // 2, w // 2
 
@@ -621,7 +644,7 @@ class FarSegEngine:
         for i in range(4):
             y = zs[i]
             for (cp, bp) in self.dec_blocks[i]:
-                o = self.conv(y, cp, train=train)
+                o = self.conv(y, cp, train=train, stats=train)
                 y = self.bn_relu_up(o, bp, 2, train=train) if self.dec_nup[i] else self.bn_act(o, bp, True, train=train)
             outs.append(y)
             self._dbg('dec%d' % i, y)
@@ -878,7 +901,7 @@ class ChangeStarEngine(FarSegEngine):
         u = self.conv(fb, self.cm_b, add=u, add_mode=1, train=train)
         y = self.bn_act(u, self.cm_bn0, True, train=train)
         for cp, bp in self.cm_mid:
-            y = self.bn_act(self.conv(y, cp, train=train), bp, True, train=train)
+            y = self.bn_act(self.conv(y, cp, train=train, stats=train), bp, True, train=train)
         return self._classify(y, self.cm_cls, 4, train, name=name)
 
     @staticmethod

@@ -34,6 +34,11 @@ int evb_device_sync_check(void);
  * sampled nearest (FPN top-down add, ever/module/fpn.py:96-105).  force_nt: 0 = auto tile, else 64|128|256. */
 int evb_conv2d_fwd(const void* x, int N, int H, int W, int Cin, const void* wpk, int w_rows, int ksize, int stride,
                    void* y, int Cout, const float* bias, const void* add, int add_mode, int force_nt, void* stream);
+/* Convolution (no bias / add) whose epilogue also emits BatchNorm batch-statistic partial sums of its bf16 output:
+ * partial = fp32 [2][Cout][320] (sum | sum of squares per channel, one column per CTA), *nblk_out columns valid; pass them
+ * to evb_bn_finalize (replaces the evb_bn_stats read pass; conv + BN of ever/module/_resnets.py:92-112, fpn.py:165-166). */
+int evb_conv2d_fwd_stats(const void* x, int N, int H, int W, int Cin, const void* wpk, int w_rows, int ksize, int stride,
+                         void* y, int Cout, float* partial, int* nblk_out, void* stream);
 /* kernel variant for evb_conv2d_fwd/dgrad: 2 = persistent, TMEM double-buffered, TMA-store epilogue (default);
  * 1 = one tile per CTA with direct global stores (kept for A/B measurements). */
 int evb_set_igemm_variant(int v);
@@ -69,6 +74,10 @@ long long evb_bn_workspace(long long M, int C);
 int evb_bn_stats(const void* x, long long M, int C, const float* gamma, const float* beta, float* running_mean,
                  float* running_var, float momentum, float eps, float* mean, float* rstd, float* scale, float* shift,
                  void* ws, void* stream);
+/* same outputs as evb_bn_stats, from the partial sums written by evb_conv2d_fwd_stats */
+int evb_bn_finalize(const float* partial, int nblk, long long M, int C, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps, float* mean, float* rstd,
+                    float* scale, float* shift, void* stream);
 /* eval / frozen BN: fold running statistics (ever/module/resnet.py:155-160,227-234) */
 int evb_bn_fold(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C, float* scale,
                 float* shift, float* mean, float* rstd, void* stream);

@@ -143,3 +143,41 @@ def test_conv_wgrad_atomic_staging(case):
     # the valid region of the staging buffer is zero again
     view = acc.view(k * k, cinp.value, coutp.value)[:, :cin_valid, :cout_valid]
     assert float(view.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('case', [(2, 16, 16, 64, 64, 1, 1), (1, 128, 128, 256, 256, 3, 1), (8, 16, 16, 256, 2048, 1, 1),
+                                  (3, 24, 40, 64, 192, 3, 1), (2, 32, 32, 128, 512, 1, 2), (8, 64, 64, 128, 128, 3, 1)])
+def test_conv_fwd_fused_bn_stats(case):
+    """evb_conv2d_fwd_stats + evb_bn_finalize == conv followed by BatchNorm batch statistics of its bf16 output."""
+    import ctypes
+    from ever_b200 import ops
+    from ever_b200._lib import check, lib, ptr, stream
+    n, h, w, cin, cout, k, s = case
+    L = lib()
+    c_int, c_ll, c_float = ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+    g = torch.Generator(device='cuda').manual_seed(6)
+    x = (torch.randn(n, h, w, cin, device='cuda', generator=g) + 0.3).to(torch.bfloat16)
+    wt = torch.randn(cout, cin, k, k, device='cuda', generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    wf, _ = ops.pack_conv_weight_torch(wt)
+    ho, wo = h // s, w // s
+    y = torch.empty(n, ho, wo, cout, device='cuda', dtype=torch.bfloat16)
+    partial = torch.empty(2 * cout * 320, device='cuda')
+    nblk = c_int(0)
+    check(L.evb_conv2d_fwd_stats(ptr(x), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(wf), c_int(cout), c_int(k), c_int(s),
+                                 ptr(y), c_int(cout), ptr(partial), ctypes.byref(nblk), stream()), 'fwd_stats')
+    gamma = 1 + 0.1 * torch.randn(cout, device='cuda', generator=g)
+    beta = 0.1 * torch.randn(cout, device='cuda', generator=g)
+    rm, rv = torch.zeros(cout, device='cuda'), torch.ones(cout, device='cuda')
+    st = torch.empty(4, cout, device='cuda')
+    m_rows = n * ho * wo
+    check(L.evb_bn_finalize(ptr(partial), nblk, c_ll(m_rows), c_int(cout), ptr(gamma), ptr(beta), ptr(rm), ptr(rv),
+                            c_float(0.1), c_float(1e-5), ptr(st[0]), ptr(st[1]), ptr(st[2]), ptr(st[3]), stream()), 'fin')
+    torch.cuda.synchronize()
+    _close(y, _ref_conv(x, wt, s))
+    yf = y.float().reshape(-1, cout)
+    mean, var = yf.mean(0), yf.var(0, unbiased=False)
+    assert float((st[0] - mean).abs().max()) <= 1e-4 * float(yf.abs().max())
+    rstd = (var + 1e-5).rsqrt()
+    assert float(((st[1] - rstd) / rstd).abs().max()) < 1e-3
+    torch.testing.assert_close(rm, 0.1 * mean, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(rv, 0.9 + 0.1 * yf.var(0, unbiased=True), rtol=1e-3, atol=1e-5)

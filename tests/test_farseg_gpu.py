@@ -169,6 +169,7 @@ def test_eval_masks():
                mask_agree_all=agree_all, mask_agree_bf16_oracle_vs_fp32=agree_bf, mask_agree_confident=agree_conf,
                confident_frac=float(confident.float().mean()), prob_rel=_rel(prob, logit_bf.float().softmax(dim=1)))
     print(json.dumps(rep))
+    os.makedirs('gpurun_out', exist_ok=True)
     json.dump(rep, open('gpurun_out/eval_masks.json', 'w'), indent=1)
     assert rep['logit_rel_mine_vs_bf16'] < max(2e-2, 1.5 * rep['logit_rel_bf16_vs_fp32'])
     assert agree_conf >= 0.999
@@ -267,6 +268,7 @@ def test_training_trajectory_matches_reference():
         eng.sgd_step(lr, momentum=0.9, weight_decay=1e-4, max_norm=35.0)
         my_curve.append(float(out['ce_loss']) + float(out['dice_loss']))
     torch.cuda.synchronize()
+    os.makedirs('gpurun_out', exist_ok=True)
     json.dump(dict(ref=ref_curve, mine=my_curve), open('gpurun_out/trajectory.json', 'w'), indent=1)
     print('ref', [round(v, 3) for v in ref_curve[::4]], 'mine', [round(v, 3) for v in my_curve[::4]])
     assert my_curve[-1] < 0.8 * my_curve[0] and ref_curve[-1] < 0.8 * ref_curve[0]

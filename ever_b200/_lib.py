@@ -21,14 +21,14 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.evb_last_cuda_error.restype = ctypes.c_char_p
         for fn in ('evb_conv2d_wgrad_workspace', 'evb_bn_workspace', 'evb_loss_workspace', 'evb_sgd_workspace',
-                   'evb_relation_bwd_workspace'):
+                   'evb_relation_bwd_workspace', 'evb_bilinear_up_bwd_workspace'):
             getattr(_lib, fn).restype = ctypes.c_longlong
     return _lib
 
 
 # kernels launched per C-ABI call (lower bounds; evb_conv2d_dgrad stride 2 launches up to 4)
 _KERNELS = {'evb_conv2d_wgrad': 2, 'evb_conv2d_wgrad(stem)': 2, 'evb_bn_stats': 2, 'evb_bn_bwd': 3, 'evb_bias_grad': 2,
-            'evb_loss_stats': 2, 'evb_linear_bwd': 2, 'evb_grad_norm': 2, 'evb_relation_bwd': 2}
+            'evb_loss_stats': 2, 'evb_linear_bwd': 2, 'evb_grad_norm': 2, 'evb_relation_bwd': 2, 'evb_bilinear_up_bwd_sep': 2}
 launches = [0]
 
 

@@ -501,6 +501,80 @@ bilinear_up_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __re
   }
 }
 
+// Separable form of the same transpose (fewer taps, coalesced): pass X reduces along the output row into an fp32
+// intermediate tmp[N, Ho, w, C]; pass Y reduces tmp along the output column into dx (bf16).
+__global__ void __launch_bounds__(kEwThreads)
+bilinear_bwd_x_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ tmp, int N, int h, int w, int C, int lddy,
+                      int f) {
+  const int cg = C / 8, Ho = h * f, Wo = w * f;
+  const float sx = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
+  const float inv_sx = sx > 0.f ? 1.f / sx : 0.f;
+  const unsigned total = (unsigned)N * Ho * w * cg;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    unsigned p = i / cg;
+    const int ix = (int)(p % w); p /= w;   // p = n * Ho + oy
+    int xlo = 0, xhi = Wo - 1;
+    if (sx > 0.f) { xlo = max(0, (int)floorf((ix - 1) * inv_sx) - 1); xhi = min(Wo - 1, (int)ceilf((ix + 1) * inv_sx) + 1); }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const __nv_bfloat16* row = dy + (long long)p * Wo * lddy + g * 8;
+    for (int ox = xlo; ox <= xhi; ++ox) {
+      const float fx = sx * ox;
+      const int x0 = (int)fx;
+      const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+      const float lx = fx - x0;
+      float wx = 0.f;
+      if (x0 == ix) wx += 1.f - lx;
+      if (x1 == ix) wx += lx;
+      if (wx == 0.f) continue;
+      float gv[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(row + (long long)ox * lddy), gv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += wx * gv[j];
+    }
+    float4* dst = reinterpret_cast<float4*>(tmp + (long long)i * 8);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+__global__ void __launch_bounds__(kEwThreads)
+bilinear_bwd_y_kernel(const float* __restrict__ tmp, __nv_bfloat16* __restrict__ dx, int N, int h, int w, int C, int lddx,
+                      int f) {
+  const int cg = C / 8, Ho = h * f;
+  const float sy = Ho > 1 ? (float)(h - 1) / (float)(Ho - 1) : 0.f;
+  const float inv_sy = sy > 0.f ? 1.f / sy : 0.f;
+  const unsigned total = (unsigned)N * h * w * cg;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    unsigned p = i / cg;
+    const int ix = (int)(p % w); p /= w;
+    const int iy = (int)(p % h);
+    const int n = (int)(p / h);
+    int ylo = 0, yhi = Ho - 1;
+    if (sy > 0.f) { ylo = max(0, (int)floorf((iy - 1) * inv_sy) - 1); yhi = min(Ho - 1, (int)ceilf((iy + 1) * inv_sy) + 1); }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int oy = ylo; oy <= yhi; ++oy) {
+      const float fy = sy * oy;
+      const int y0 = (int)fy;
+      const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+      const float ly = fy - y0;
+      float wy = 0.f;
+      if (y0 == iy) wy += 1.f - ly;
+      if (y1 == iy) wy += ly;
+      if (wy == 0.f) continue;
+      const float4* src = reinterpret_cast<const float4*>(tmp + ((((long long)n * Ho + oy) * w + ix) * cg + g) * 8);
+      const float4 a = src[0], b = src[1];
+      acc[0] += wy * a.x; acc[1] += wy * a.y; acc[2] += wy * a.z; acc[3] += wy * a.w;
+      acc[4] += wy * b.x; acc[5] += wy * b.y; acc[6] += wy * b.z; acc[7] += wy * b.w;
+    }
+    *reinterpret_cast<bf16x8*>(dx + (((long long)n * h + iy) * w + ix) * lddx + g * 8) = pack8(acc);
+  }
+}
+
 // dcoarse[n,h,w,:] (+)= sum of the 2x2 block of dfine  (backward of nearest x2)
 __global__ void __launch_bounds__(kEwThreads)
 sumpool2_kernel(const __nv_bfloat16* __restrict__ dfine, __nv_bfloat16* __restrict__ dcoarse, int N, int h, int w, int C,
@@ -814,6 +888,22 @@ extern "C" int evb_bilinear_up_bwd(const void* dy, void* dx, int N, int h, int w
   const long long total = (long long)N * h * w * (C / 8);
   bilinear_up_bwd_kernel<<<ew_blocks(total, kEwThreads), kEwThreads, 0, ST>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx,
                                                                            N, h, w, C, lddy, lddx, f);
+  return LAUNCH_OK();
+}
+
+extern "C" long long evb_bilinear_up_bwd_workspace(int N, int h, int w, int C, int f) {
+  return (long long)N * h * f * w * C * sizeof(float);
+}
+// separable two-pass version of evb_bilinear_up_bwd (same result up to fp32 summation order); ws: fp32 [N, f*h, w, C]
+extern "C" int evb_bilinear_up_bwd_sep(const void* dy, void* dx, int N, int h, int w, int C, int lddy, int lddx, int f,
+                                       void* ws, long long ws_bytes, void* stream) {
+  if (C % 8 || lddx % 8 || lddy % 8 || f < 1 || f > 4) return EVB_ERR_ARG;
+  if (ws_bytes < evb_bilinear_up_bwd_workspace(N, h, w, C, f)) return EVB_ERR_ARG;
+  const long long t1 = (long long)N * h * f * w * (C / 8), t2 = (long long)N * h * w * (C / 8);
+  bilinear_bwd_x_kernel<<<ew_blocks(t1, kEwThreads * 2), kEwThreads, 0, ST>>>((const __nv_bfloat16*)dy, (float*)ws, N, h, w, C,
+                                                                            lddy, f);
+  bilinear_bwd_y_kernel<<<ew_blocks(t2, kEwThreads), kEwThreads, 0, ST>>>((const float*)ws, (__nv_bfloat16*)dx, N, h, w, C, lddx,
+                                                                        f);
   return LAUNCH_OK();
 }
 

@@ -87,7 +87,7 @@ relation_fwd_kernel(const __nv_bfloat16* __restrict__ u1, const __nv_bfloat16* _
 // g1/g2 [M,C] = gradient w.r.t. the two BN outputs (ReLU masks applied); dsf_part[warp][c] = sum over the warp's pixels
 // of dlogit * cf (px_per_warp divides HW, so a warp never straddles two images; reduced deterministically afterwards).
 template <int NG, int PX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NG == 1 ? 2 : 1)
 relation_bwd_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ u1,
                     const __nv_bfloat16* __restrict__ u2, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ scale2, const float* __restrict__ shift2, const float* __restrict__ sf,

@@ -463,8 +463,10 @@ class FarSegEngine:
                 if y.grad is None:
                     return
                 low = self._new(n, h, w, c)
-                check(L.evb_bilinear_up_bwd(ptr(y.grad), ptr(low), c_int(n), c_int(h), c_int(w), c_int(c), c_int(c),
-                                            c_int(c), c_int(f), stream()), 'evb_bilinear_up_bwd')
+                ws = self._ws(L.evb_bilinear_up_bwd_workspace(c_int(n), c_int(h), c_int(w), c_int(c), c_int(f)))
+                check(L.evb_bilinear_up_bwd_sep(ptr(y.grad), ptr(low), c_int(n), c_int(h), c_int(w), c_int(c), c_int(c),
+                                                c_int(c), c_int(f), ptr(ws), c_ll(self.ws_bytes), stream()),
+                      'evb_bilinear_up_bwd_sep')
                 self._bn_backward(low, x, bp, fold, 2, None, None)
             self.tape.append(bwd)
         return y
@@ -771,8 +773,10 @@ class FarSegEngine:
                                   c_int(self.ignore_index), ptr(g['coef']), ptr(dlogits), stream()), 'evb_loss_grad')
             cls.grad = torch.zeros_like(cls.data)   # padding channels 16..63 stay zero
             cls.has_grad = True
-            check(L.evb_bilinear_up_bwd(ptr(dlogits), ptr(cls.grad), c_int(n), c_int(hh // f), c_int(ww // f), c_int(16),
-                                        c_int(16), c_int(64), c_int(f), stream()), 'evb_bilinear_up_bwd(logits)')
+            ws = self._ws(L.evb_bilinear_up_bwd_workspace(c_int(n), c_int(hh // f), c_int(ww // f), c_int(16), c_int(f)))
+            check(L.evb_bilinear_up_bwd_sep(ptr(dlogits), ptr(cls.grad), c_int(n), c_int(hh // f), c_int(ww // f), c_int(16),
+                                            c_int(16), c_int(64), c_int(f), ptr(ws), c_ll(self.ws_bytes), stream()),
+                  'evb_bilinear_up_bwd_sep')
         for fn in reversed(self.tape):
             fn()
         self.tape = []

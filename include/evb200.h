@@ -101,6 +101,10 @@ int evb_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, int N, int H
 int evb_bilinear_up(const void* x, const float* scale, const float* shift, void* y, int N, int h, int w, int C, int ldx,
                     int ldy, int f, void* stream);
 int evb_bilinear_up_bwd(const void* dy, void* dx, int N, int h, int w, int C, int lddy, int lddx, int f, void* stream);
+/* separable two-pass variant (fewer taps, coalesced); ws: fp32 [N, f*h, w, C] */
+long long evb_bilinear_up_bwd_workspace(int N, int h, int w, int C, int f);
+int evb_bilinear_up_bwd_sep(const void* dy, void* dx, int N, int h, int w, int C, int lddy, int lddx, int f, void* ws,
+                            long long ws_bytes, void* stream);
 int evb_sumpool2(const void* dfine, void* dcoarse, int N, int h, int w, int C, int accumulate, void* stream);
 int evb_merge4(const void* a, const void* b, const void* c, const void* d, void* out, long long numel, void* stream);
 int evb_scale_add(const void* x, float alpha, const void* z, void* y, long long numel, void* stream);

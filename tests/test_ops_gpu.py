@@ -122,6 +122,13 @@ def test_bilinear(f, c, ldx, ldy, bn, hw):
     yr.backward(dy[..., :c].float().permute(0, 3, 1, 2))
     assert _rel(y[..., :c].float(), nhwc(yr.detach())) < 4e-3
     assert _rel(dx[..., :c].float(), nhwc(xr.grad)) < 4e-3
+    # separable two-pass backward
+    dx2 = torch.zeros_like(dx)
+    ws = torch.empty(L.evb_bilinear_up_bwd_workspace(c_int(n), c_int(h), c_int(w), c_int(c), c_int(f)) // 4, device='cuda')
+    check(L.evb_bilinear_up_bwd_sep(ptr(dy), ptr(dx2), c_int(n), c_int(h), c_int(w), c_int(c), c_int(ldy), c_int(ldx), c_int(f),
+                                    ptr(ws), c_ll(ws.numel() * 4), stream()), 'upb_sep')
+    torch.cuda.synchronize()
+    assert _rel(dx2[..., :c].float(), nhwc(xr.grad)) < 4e-3
 
 
 def test_sumpool_merge_gap():

@@ -693,6 +693,57 @@ stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, i
   }
 }
 
+// Same lowering from a raw uint8 HWC tile [N,H,W,Cin] with the reference's normalisation fused in:
+// value = (u8 - mean[c]) / std[c]  (th_mean_std_normalize, ever/preprocess/function.py:9-32), then bf16.
+__global__ void __launch_bounds__(kEwThreads)
+stem_im2col_u8_kernel(const uint8_t* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ stdv,
+                      __nv_bfloat16* __restrict__ a, int N, int Cin, int H, int W, int KP) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int kg = KP / 8;
+  const unsigned total = (unsigned)N * Ho * Wo * kg;
+  const int K = Cin * 49;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int g = (int)(i % kg);
+    unsigned p = i / kg;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float val = 0.f;
+      if (k < K) {
+        const int c = k / 49, rs = k % 49, r = rs / 7, s_ = rs % 7;
+        const int h = 2 * ho - 3 + r, w = 2 * wo - 3 + s_;
+        if (h >= 0 && h < H && w >= 0 && w < W)
+          val = ((float)x[(((long long)n * H + h) * W + w) * Cin + c] - mean[c]) / stdv[c];
+      }
+      v[j] = val;
+    }
+    reinterpret_cast<bf16x8*>(a)[i] = pack8(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ confusion matrix
+// cm[t * K + p] += #pixels with label t and prediction p (labels outside [0,K), e.g. ignore_index, are skipped).
+// ever/metric/confusion_matrix.py:11-25 (scipy COO accumulation on the host in the reference).  Integer atomics.
+__global__ void __launch_bounds__(256)
+confusion_matrix_kernel(const uint8_t* __restrict__ pred, const long long* __restrict__ labels, long long P, int K,
+                        unsigned long long* __restrict__ cm) {
+  extern __shared__ unsigned int hist[];
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const long long t = labels[p];
+    const int q = pred[p];
+    if (t >= 0 && t < K && q < K) atomicAdd(&hist[(int)t * K + q], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x)
+    if (hist[i]) atomicAdd(&cm[i], (unsigned long long)hist[i]);
+}
+
 // ------------------------------------------------------------------------------------------------ weight packing
 // w: OIHW fp32 [Co][Ci][k][k] -> wf: bf16 [k*k][CoP][CiP]  and  wb: bf16 [k*k][CiPb][CoPb]  (zero padded)
 __global__ void pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, int kk, __nv_bfloat16* __restrict__ wf,
@@ -945,6 +996,25 @@ extern "C" int evb_stem_im2col(const float* x, void* a, int N, int Cin, int H, i
   if (KP % 8 || KP < Cin * 49 || (H & 1) || (W & 1)) return EVB_ERR_ARG;
   const long long total = (long long)N * (H / 2) * (W / 2) * (KP / 8);
   stem_im2col_kernel<<<ew_blocks(total, kEwThreads), kEwThreads, 0, ST>>>(x, (__nv_bfloat16*)a, N, Cin, H, W, KP);
+  return LAUNCH_OK();
+}
+
+extern "C" int evb_stem_im2col_u8(const void* x, const float* mean, const float* stdv, void* a, int N, int Cin, int H, int W,
+                                  int KP, void* stream) {
+  if (KP % 8 || KP < Cin * 49 || (H & 1) || (W & 1)) return EVB_ERR_ARG;
+  const long long total = (long long)N * (H / 2) * (W / 2) * (KP / 8);
+  stem_im2col_u8_kernel<<<ew_blocks(total, kEwThreads), kEwThreads, 0, ST>>>((const uint8_t*)x, mean, stdv, (__nv_bfloat16*)a, N,
+                                                                           Cin, H, W, KP);
+  return LAUNCH_OK();
+}
+
+extern "C" int evb_confusion_matrix(const void* pred, const void* labels, long long P, int K, void* cm, void* stream) {
+  if (K < 1 || K > 64) return EVB_ERR_ARG;
+  long long b = (P + 256 * 16 - 1) / (256 * 16);
+  if (b > 148 * 4) b = 148 * 4;
+  if (b < 1) b = 1;
+  confusion_matrix_kernel<<<(int)b, 256, K * K * sizeof(unsigned int), ST>>>((const uint8_t*)pred, (const long long*)labels, P, K,
+                                                                             (unsigned long long*)cm);
   return LAUNCH_OK();
 }
 

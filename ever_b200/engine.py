@@ -507,12 +507,24 @@ class FarSegEngine:
 
     def _encoder(self, x_nchw, train):
         L = self.L
-        n, cin, h, w = x_nchw.shape
+        u8 = x_nchw.dtype == torch.uint8   # raw HWC uint8 tiles [N,H,W,Cin]: normalisation fused into the im2col
+        if u8:
+            n, h, w, cin = x_nchw.shape
+        else:
+            n, cin, h, w = x_nchw.shape
         if h % 32 or w % 32:
             raise ValueError('FarSegB200 needs H, W divisible by 32 (FPN nearest-x2 adds, SURVEY.md section 5)')
         a = self._new(n, h // 2, w // 2, self.stem_kp)
-        check(L.evb_stem_im2col(ptr(x_nchw), ptr(a), c_int(n), c_int(cin), c_int(h), c_int(w), c_int(self.stem_kp),
-                                stream()), 'evb_stem_im2col')
+        if u8:
+            if getattr(self, '_in_mean', None) is None:
+                icfg = self.m.config.input
+                self._in_mean = torch.tensor(list(icfg.mean), dtype=torch.float32, device=self.dev)
+                self._in_std = torch.tensor(list(icfg.std), dtype=torch.float32, device=self.dev)
+            check(L.evb_stem_im2col_u8(ptr(x_nchw), ptr(self._in_mean), ptr(self._in_std), ptr(a), c_int(n), c_int(cin),
+                                       c_int(h), c_int(w), c_int(self.stem_kp), stream()), 'evb_stem_im2col_u8')
+        else:
+            check(L.evb_stem_im2col(ptr(x_nchw), ptr(a), c_int(n), c_int(cin), c_int(h), c_int(w), c_int(self.stem_kp),
+                                    stream()), 'evb_stem_im2col')
         xa = Act(a, needs_grad=False)
         y0 = self.conv(xa, self.stem, stride=1, train=False, stats=train)   # distinct name: the closure below keeps THIS Act
         if train:
@@ -710,7 +722,7 @@ class FarSegEngine:
         self.tape = []
         self._bn_tracked = []
         self._groups = []
-        x = x.contiguous().float()
+        x = x.contiguous() if x.dtype == torch.uint8 else x.contiguous().float()
         self.pack_weights()
         self.attach_grads()
         self._network_losses(x, labels)
@@ -790,6 +802,14 @@ class FarSegEngine:
             import torch.distributed as dist
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.AVG)
 
+    def confusion_matrix(self, mask, labels, cm):
+        """cm[K,K] (int64, device) += confusion counts of a uint8 prediction mask against int64 labels; labels outside
+        [0,K) (ignore_index) are skipped.  GPU version of ConfusionMatrix.forward (ever/metric/confusion_matrix.py:11-25)."""
+        labels = labels.contiguous().long()
+        check(self.L.evb_confusion_matrix(ptr(mask), ptr(labels), c_ll(labels.numel()), c_int(cm.shape[0]), ptr(cm),
+                                          stream()), 'evb_confusion_matrix')
+        return cm
+
     # ------------------------------------------------------------------ fused optimizer (SURVEY 8f rank 1)
     def sgd_step(self, lr, momentum=0.9, weight_decay=1e-4, max_norm=35.0):
         """clip_grad_norm_(max_norm, 2) + torch.optim.SGD step + zero_grad over the flat arenas
@@ -852,7 +872,7 @@ class FarSegEngine:
     def forward_eval(self, x, return_mask=False):
         L = self.L
         self.tape = []
-        x = x.contiguous().float()
+        x = x.contiguous() if x.dtype == torch.uint8 else x.contiguous().float()
         self.pack_weights()
         feats = self._encoder(x, False)
         merged = self._head(feats, False)

@@ -190,6 +190,8 @@ class FarSegB200(ERModule):
                                  out_feat_output_stride=4,
                                  classifier_config=dict(scale_factor=4.0, num_classes=1, kernel_size=1))),
             loss=dict(ce=dict(weight=1.0), dice=dict(weight=1.0, smooth=1.0, sync_statistics=True), ignore_index=255),
+            # uint8 HWC inputs are normalised on the fly (th_mean_std_normalize defaults, ever/preprocess/function.py:9)
+            input=dict(mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57.375)),
         ))
 
     # --------------------------------------------------------------------------------------------------

@@ -66,6 +66,13 @@ int evb_pack_weights_batched(const void* desc, const void* block_map, int nblock
 /* 7x7 stride-2 pad-3 stem lowered to a GEMM: x NCHW fp32 -> A[N*H/2*W/2][KP] bf16, k = c*49 + r*7 + s
  * (ResNet.stem_forward, ever/module/_resnets.py:205-212). */
 int evb_stem_im2col(const float* x, void* a, int N, int Cin, int H, int W, int KP, void* stream);
+/* same from a raw uint8 HWC tile [N,H,W,Cin] with (u8 - mean[c]) / std[c] fused (th_mean_std_normalize,
+ * ever/preprocess/function.py:9-32): the caller-side input pipeline, 4x fewer H2D bytes */
+int evb_stem_im2col_u8(const void* x, const float* mean, const float* stdv, void* a, int N, int Cin, int H, int W, int KP,
+                       void* stream);
+/* eval: cm[t*K + p] (int64) += pixels with label t predicted p; labels outside [0,K) skipped
+ * (ConfusionMatrix.forward, ever/metric/confusion_matrix.py:11-25) */
+int evb_confusion_matrix(const void* pred, const void* labels, long long P, int K, void* cm, void* stream);
 
 /* ---- BatchNorm2d (+ReLU, + residual add).  Replaces nn.BatchNorm2d / nn.ReLU / `out += identity`:
  * ever/module/_resnets.py:46-49,58,66-67,83-87,97,101,109-110; fpn.py:166-167; fs_relation.py:43-44,50-51. */

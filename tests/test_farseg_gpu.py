@@ -274,3 +274,28 @@ def test_training_trajectory_matches_reference():
     assert my_curve[-1] < 0.8 * my_curve[0] and ref_curve[-1] < 0.8 * ref_curve[0]
     for a, b in zip(my_curve, ref_curve):
         assert abs(a - b) <= 0.05 * abs(b) + 0.02, (my_curve, ref_curve)
+
+
+def test_uint8_input_path_and_confusion():
+    """uint8 HWC tiles through the fused normalise+im2col stem == the float path on the normalised image (bit-identical
+    losses), and the GPU confusion matrix of the eval masks."""
+    resnet, k, dec, n, h, w = 'resnet18', 5, 128, 2, 128, 128
+    _, mine = _build(resnet, k, dec)
+    mine = mine.cuda().train()
+    g = torch.Generator().manual_seed(3)
+    img = torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8).cuda()
+    y = torch.randint(0, k, (n, h, w), generator=g).cuda()
+    mean = torch.tensor([123.675, 116.28, 103.53], device='cuda').view(1, 3, 1, 1)
+    std = torch.tensor([58.395, 57.12, 57.375], device='cuda').view(1, 3, 1, 1)
+    xf = img.permute(0, 3, 1, 2).float().sub(mean).div(std)
+    state0 = {kk: v.clone() for kk, v in mine.state_dict().items()}
+    a = {kk: float(v) for kk, v in mine(img, dict(cls=y)).items()}
+    mine.load_state_dict(state0)
+    b = {kk: float(v) for kk, v in mine(xf, dict(cls=y)).items()}
+    assert a == b
+    mine.eval()
+    prob, mask = mine.engine.forward_eval(img, return_mask=True)
+    cm = torch.zeros(k, k, dtype=torch.int64, device='cuda')
+    mine.engine.confusion_matrix(mask, y, cm)
+    torch.cuda.synchronize()
+    assert torch.equal(cm, torch.bincount(y.flatten() * k + mask.flatten().long(), minlength=k * k).view(k, k))

@@ -320,3 +320,31 @@ def test_loss_binary():
     assert abs(float(losses[1]) - float(dice)) < 1e-4 * abs(float(dice))
     assert _rel(dl[..., :1].float(), nhwc(lr.grad)) < 8e-3
     assert float(dl[..., 1:].abs().max()) == 0.0
+
+
+def test_u8_input_pipeline_and_confusion_matrix():
+    L, check, ptr, stream = _L()
+    g = _gen(10)
+    n, h, w = 2, 32, 48
+    img = torch.randint(0, 256, (n, h, w, 3), device='cuda', generator=g, dtype=torch.uint8)
+    mean = torch.tensor([123.675, 116.28, 103.53], device='cuda')
+    std = torch.tensor([58.395, 57.12, 57.375], device='cuda')
+    a = torch.empty(n, h // 2, w // 2, 192, device='cuda', dtype=torch.bfloat16)
+    check(L.evb_stem_im2col_u8(ptr(img), ptr(mean), ptr(std), ptr(a), c_int(n), c_int(3), c_int(h), c_int(w), c_int(192),
+                               stream()), 'im2col_u8')
+    # reference pipeline: HWC uint8 -> CHW float -> th_mean_std_normalize -> (autocast) bf16 conv input
+    xf = img.permute(0, 3, 1, 2).float().sub(mean.view(1, 3, 1, 1)).div(std.view(1, 3, 1, 1))
+    unf = F.unfold(xf, 7, padding=3, stride=2)
+    torch.cuda.synchronize()
+    assert torch.equal(a[..., :147].reshape(n, -1, 147), unf.permute(0, 2, 1).bfloat16())
+    k = 7
+    pred = torch.randint(0, k, (n, h, w), device='cuda', generator=g, dtype=torch.uint8)
+    lab = torch.randint(0, k, (n, h, w), device='cuda', generator=g)
+    lab[torch.rand(n, h, w, device='cuda', generator=g) < 0.1] = 255
+    cm = torch.zeros(k, k, device='cuda', dtype=torch.int64)
+    for _ in range(2):
+        check(L.evb_confusion_matrix(ptr(pred), ptr(lab), c_ll(n * h * w), c_int(k), ptr(cm), stream()), 'cm')
+    torch.cuda.synchronize()
+    valid = lab != 255
+    ref = torch.bincount(lab[valid] * k + pred[valid].long(), minlength=k * k).view(k, k)
+    assert torch.equal(cm, 2 * ref)

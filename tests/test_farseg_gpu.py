@@ -299,3 +299,31 @@ def test_uint8_input_path_and_confusion():
     mine.engine.confusion_matrix(mask, y, cm)
     torch.cuda.synchronize()
     assert torch.equal(cm, torch.bincount(y.flatten() * k + mask.flatten().long(), minlength=k * k).view(k, k))
+
+
+def test_stock_optimizer_path_equals_fused_sgd():
+    """What Launcher does with a plugin model (ever/core/launcher.py:193-200, ever/interface/module.py:83-108): model(x, y) ->
+    model.backward(...) -> clip_grad_norm_ + torch.optim.SGD.step + zero_grad(set_to_none) on the model's ordinary
+    nn.Parameters.  After 3 steps the weights equal those of the engine's fused clip+SGD path."""
+    from oracle.farseg_oracle import synthetic_batch
+    resnet, k, dec, n, h, w = 'resnet18', 5, 128, 2, 128, 128
+    _, a = _build(resnet, k, dec)
+    _, b = _build(resnet, k, dec)
+    x, y = synthetic_batch(n, h, w, k)
+    x, y = x.cuda(), y.cuda()
+    a, b = a.cuda().train(), b.cuda().train()
+    opt = torch.optim.SGD(a.custom_param_groups() if hasattr(a, 'custom_param_groups') else a.parameters(), lr=0.01,
+                          momentum=0.9, weight_decay=1e-4)
+    for _ in range(3):
+        out = a(x, dict(cls=y))
+        a.backward(out, None, None)
+        torch.nn.utils.clip_grad_norm_([p for p in a.parameters() if p.requires_grad], max_norm=35, norm_type=2)
+        opt.step()
+        opt.zero_grad()          # set_to_none=True: the engine re-attaches its gradient views on the next step
+        out_b = b(x, dict(cls=y))
+        b.backward(out_b, None, None)
+        b.engine.sgd_step(0.01, momentum=0.9, weight_decay=1e-4, max_norm=35.0)
+    torch.cuda.synchronize()
+    assert abs(float(out['ce_loss']) - float(out_b['ce_loss'])) < 1e-5
+    for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert _rel(pa.data, pb.data) < 1e-5, na

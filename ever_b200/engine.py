@@ -11,6 +11,7 @@ Data layout: activations NHWC bf16; master weights / BN parameters / gradients f
 per-step bf16 weight packs [tap][Cout][Cin] (forward) and [tap][Cin][Cout] (dgrad).
 """
 import ctypes
+import os
 
 import torch
 
@@ -107,6 +108,9 @@ class FarSegEngine:
         self.tape = []
         self.ws = None
         self.ws_bytes = 0
+        self.ws2, self.ws2_bytes, self._on_side, self._side_used = None, 0, False, False
+        # weight gradients run on a second stream (parallel graph branch): they overlap the dgrad / BN chain
+        self.side = torch.cuda.Stream(device=self.dev) if os.environ.get('EVB_NO_SIDE_STREAM', '0') != '1' else None
         self.accumulate = False      # gradient accumulation into existing .grad (forward_times > 1)
         self.fuse_bn_stats = True    # BN batch statistics in the producing conv's epilogue (evb_conv2d_fwd_stats)
         self._saved_for_backward = None
@@ -263,10 +267,45 @@ class FarSegEngine:
 
     # ------------------------------------------------------------------ workspace
     def _ws(self, nbytes):
+        """scratch workspace of the stream the caller is launching on (main stream or the weight-gradient side stream)"""
+        if self._on_side:
+            if nbytes > self.ws2_bytes:
+                self.ws2_bytes = max(nbytes, 64 << 20)
+                self.ws2 = torch.empty(self.ws2_bytes // 4, dtype=torch.float32, device=self.dev)
+            return self.ws2
         if nbytes > self.ws_bytes:
             self.ws_bytes = max(nbytes, 64 << 20)
             self.ws = torch.empty(self.ws_bytes // 4, dtype=torch.float32, device=self.dev)
         return self.ws
+
+    def _ws_cap(self):
+        return self.ws2_bytes if self._on_side else self.ws_bytes
+
+    def _param_grads_async(self, tensors, fn):
+        """Run fn() (weight / bias gradient kernels: nothing downstream in backward reads their outputs) on the side
+        stream, forked from the current point of the main stream; backward() joins before the optimizer.  `tensors`
+        are kept alive for the side stream (caching-allocator stream bookkeeping)."""
+        if self.side is None:
+            fn()
+            return
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        # no record_stream needed: every tensor the side stream reads is referenced by the tape until backward() has
+        # joined the side stream (see backward(): join first, then drop the tape)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            self._on_side = True
+            try:
+                fn()
+            finally:
+                self._on_side = False
+        self._side_used = True
+
+    def _join_side(self):
+        if self.side is not None and self._side_used:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self._side_used = False
 
     def _dbg(self, name, t):
         if self.debug is not None:
@@ -298,7 +337,7 @@ class FarSegEngine:
         target = cp.weight.grad if cp.direct_grad else cp.gscr
         check(L.evb_conv2d_wgrad(ptr(x_data), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(dy), c_int(cout), c_int(cp.k),
                                  c_int(stride), ptr(target), c_int(1 if (acc and cp.direct_grad) else 0), ptr(ws),
-                                 c_ll(self.ws_bytes), c_int(0), c_int(0), st), 'evb_conv2d_wgrad')
+                                 c_ll(self._ws_cap()), c_int(0), c_int(0), st), 'evb_conv2d_wgrad')
         if not cp.direct_grad:   # copy the valid [co][ci*kk] block of the dense scratch [cop][cip*kk] into the OIHW grad
             dst = ctypes.c_void_p(cp.weight.grad.data_ptr() + 4 * cp.w_off)
             check(L.evb_copy2d_f32(ptr(cp.gscr), c_int(cp.cip * cp.kk), dst, c_int(cp.w_ld or cp.ci * cp.kk), c_int(cp.co),
@@ -348,10 +387,12 @@ class FarSegEngine:
                     return
                 dy = y.grad
                 st = stream()
-                self._wgrad(cp, x.data, dy, n, h, w, cin, cout, stride)
-                if bias:
-                    self._bias_grad(cp, dy, n * ho * wo, cout)
-                cp._gw = True
+                def param_grads():
+                    self._wgrad(cp, x.data, dy, n, h, w, cin, cout, stride)
+                    if bias:
+                        self._bias_grad(cp, dy, n * ho * wo, cout)
+                    cp._gw = True
+                self._param_grads_async((x.data, dy), param_grads)
                 if add is not None and add.needs_grad:
                     g, acc2 = self._grad_into(add)
                     if add_mode == 2:
@@ -533,8 +574,10 @@ class FarSegEngine:
             def stem_bwd():
                 if y0.grad is None:
                     return
-                self._wgrad(stem, a, y0.grad, n, ho, wo, self.stem_kp, 64, 1)
-                stem._gw = True
+                def param_grads():
+                    self._wgrad(stem, a, y0.grad, n, ho, wo, self.stem_kp, 64, 1)
+                    stem._gw = True
+                self._param_grads_async((a, y0.grad), param_grads)
             self.tape.append(stem_bwd)
         y = y0
         self._dbg('stem_conv', y)
@@ -791,6 +834,7 @@ class FarSegEngine:
                   'evb_bilinear_up_bwd_sep')
         for fn in reversed(self.tape):
             fn()
+        self._join_side()
         self.tape = []
         if allreduce:
             self.allreduce_grads()

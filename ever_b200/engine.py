@@ -108,7 +108,11 @@ class FarSegEngine:
         self.tape = []
         self.ws = None
         self.ws_bytes = 0
-        self.ws2, self.ws2_bytes, self._on_side, self._side_used = None, 0, False, False
+        self._wsmap, self._side_used = {}, False
+        self._tape_tags, self._fork_idx, self._join_idx = [], None, None
+        # pyramid levels 1..3 of the head run on their own streams (parallel graph branches; level 0 stays on main)
+        self.level_streams = ([torch.cuda.Stream(device=self.dev) for _ in range(3)]
+                              if os.environ.get('EVB_NO_LEVEL_STREAMS', '0') != '1' else None)
         # weight gradients run on a second stream (parallel graph branch): they overlap the dgrad / BN chain
         self.side = torch.cuda.Stream(device=self.dev) if os.environ.get('EVB_NO_SIDE_STREAM', '0') != '1' else None
         self.accumulate = False      # gradient accumulation into existing .grad (forward_times > 1)
@@ -267,19 +271,19 @@ class FarSegEngine:
 
     # ------------------------------------------------------------------ workspace
     def _ws(self, nbytes):
-        """scratch workspace of the stream the caller is launching on (main stream or the weight-gradient side stream)"""
-        if self._on_side:
-            if nbytes > self.ws2_bytes:
-                self.ws2_bytes = max(nbytes, 64 << 20)
-                self.ws2 = torch.empty(self.ws2_bytes // 4, dtype=torch.float32, device=self.dev)
-            return self.ws2
-        if nbytes > self.ws_bytes:
-            self.ws_bytes = max(nbytes, 64 << 20)
-            self.ws = torch.empty(self.ws_bytes // 4, dtype=torch.float32, device=self.dev)
-        return self.ws
+        """scratch workspace of the stream the caller is launching on (main, a pyramid-level branch stream or the
+        weight-gradient side stream): kernels on different streams never share scratch"""
+        key = torch.cuda.current_stream().cuda_stream
+        ent = self._wsmap.get(key)
+        if ent is None or ent[1] < nbytes:
+            nb = max(int(nbytes), 32 << 20)
+            ent = (torch.empty(nb // 4, dtype=torch.float32, device=self.dev), nb)
+            self._wsmap[key] = ent
+        return ent[0]
 
     def _ws_cap(self):
-        return self.ws2_bytes if self._on_side else self.ws_bytes
+        ent = self._wsmap.get(torch.cuda.current_stream().cuda_stream)
+        return ent[1] if ent is not None else 0
 
     def _param_grads_async(self, tensors, fn):
         """Run fn() (weight / bias gradient kernels: nothing downstream in backward reads their outputs) on the side
@@ -295,11 +299,7 @@ class FarSegEngine:
         # joined the side stream (see backward(): join first, then drop the tape)
         with torch.cuda.stream(self.side):
             self.side.wait_event(ev)
-            self._on_side = True
-            try:
-                fn()
-            finally:
-                self._on_side = False
+            fn()
         self._side_used = True
 
     def _join_side(self):
@@ -506,7 +506,7 @@ class FarSegEngine:
                 low = self._new(n, h, w, c)
                 ws = self._ws(L.evb_bilinear_up_bwd_workspace(c_int(n), c_int(h), c_int(w), c_int(c), c_int(f)))
                 check(L.evb_bilinear_up_bwd_sep(ptr(y.grad), ptr(low), c_int(n), c_int(h), c_int(w), c_int(c), c_int(c),
-                                                c_int(c), c_int(f), ptr(ws), c_ll(self.ws_bytes), stream()),
+                                                c_int(c), c_int(f), ptr(ws), c_ll(self._ws_cap()), stream()),
                       'evb_bilinear_up_bwd_sep')
                 self._bn_backward(low, x, bp, fold, 2, None, None)
             self.tape.append(bwd)
@@ -629,18 +629,54 @@ class FarSegEngine:
                 self.tape.append(bwd)
         return outs, dscene
 
+    def _level(self, i, inner_i, sf_pair, train):
+        """one pyramid level: p_i = fpn_layer(inner_i) -> FS-Relation -> decoder chain (runs on the caller's stream)"""
+        L = self.L
+        p = self.conv(inner_i, self.fpn_layer[i], train=train)
+        self._dbg('p%d' % (i + 2), p)
+        (cc, cb), (rc, rb) = self.content[i], self.reenc[i]
+        u1 = self.conv(p, cc, bias=True, train=train)
+        u2 = self.conv(p, rc, bias=True, train=train)
+        f1 = self._bn_fold(u1, cb, train)
+        f2 = self._bn_fold(u2, rb, train)
+        nn_, hh, ww, c = u1.data.shape
+        m_rows = nn_ * hh * ww
+        z = Act(self._new(nn_, hh, ww, c))
+        rel = self._new(m_rows, dtype=torch.float32)
+        sf, dsf = sf_pair
+        check(L.evb_relation_fwd(ptr(u1.data), ptr(u2.data), ptr(f1[2]), ptr(f1[3]), ptr(f2[2]), ptr(f2[3]), ptr(sf),
+                                 ptr(z.data), ptr(rel), c_ll(m_rows), c_int(hh * ww), c_int(c), stream()), 'evb_relation_fwd')
+        if train:
+            def bwd():
+                if z.grad is None:
+                    return
+                g1 = self._new(*u1.data.shape)
+                g2 = self._new(*u2.data.shape)
+                ws = self._ws(L.evb_relation_bwd_workspace(c_ll(m_rows), c_int(hh * ww), c_int(c)))
+                check(L.evb_relation_bwd(ptr(z.grad), ptr(u1.data), ptr(u2.data), ptr(f1[2]), ptr(f1[3]), ptr(f2[2]),
+                                         ptr(f2[3]), ptr(sf), ptr(rel), ptr(g1), ptr(g2), ptr(dsf), c_ll(m_rows),
+                                         c_int(hh * ww), c_int(c), ptr(ws), stream()), 'evb_relation_bwd')
+                self._bn_backward(g1, u1, cb, f1, 0, None, None)
+                self._bn_backward(g2, u2, rb, f2, 0, None, None)
+            # runs BEFORE the conv backward closures of u1/u2 (registered earlier => run later)
+            self.tape.append(bwd)
+        self._dbg('z%d' % i, z)
+        self._dbg('rel%d' % i, rel)
+        self._dbg('sf%d' % i, sf)
+        y = z
+        for (cp, bp) in self.dec_blocks[i]:
+            o = self.conv(y, cp, train=train, stats=train)
+            y = self.bn_relu_up(o, bp, 2, train=train) if self.dec_nup[i] else self.bn_act(o, bp, True, train=train)
+        self._dbg('dec%d' % i, y)
+        return y
+
     def _head(self, feats, train):
         L = self.L
         # ---- FPN (top-down, nearest x2 fused into the lateral 1x1 epilogue)
         inner = [None] * 4
         inner[3] = self.conv(feats[3], self.fpn_inner[3], train=train)
-        ps = [None] * 4
-        ps[3] = self.conv(inner[3], self.fpn_layer[3], train=train)
         for i in (2, 1, 0):
             inner[i] = self.conv(feats[i], self.fpn_inner[i], add=inner[i + 1], add_mode=2, train=train)
-            ps[i] = self.conv(inner[i], self.fpn_layer[i], train=train)
-        for i in range(4):
-            self._dbg('p%d' % (i + 2), ps[i])
         # ---- scene embedding
         c5 = feats[3]
         n, h5, w5, cc5 = c5.data.shape
@@ -660,51 +696,32 @@ class FarSegEngine:
         sfs, dscene = self._scene_mlp(scene, n, train)
         if train:
             holder['dscene'] = dscene
-        # ---- FS-Relation per level
-        zs = []
+        # ---- per pyramid level: FPN output conv -> FS-Relation -> decoder chain.  The four chains are independent:
+        #      levels 1..3 (small maps, latency-bound kernels) run on their own streams = parallel graph branches
+        outs = [None] * 4
+        main = torch.cuda.current_stream()
+        if train:
+            self._fork_idx = len(self.tape)
+        ev_fork = None
+        if self.level_streams is not None:
+            ev_fork = torch.cuda.Event()
+            ev_fork.record(main)
         for i in range(4):
-            p = ps[i]
-            (cc, cb), (rc, rb) = self.content[i], self.reenc[i]
-            u1 = self.conv(p, cc, bias=True, train=train)
-            u2 = self.conv(p, rc, bias=True, train=train)
-            f1 = self._bn_fold(u1, cb, train)
-            f2 = self._bn_fold(u2, rb, train)
-            nn_, hh, ww, c = u1.data.shape
-            m_rows = nn_ * hh * ww
-            z = Act(self._new(nn_, hh, ww, c))
-            rel = self._new(m_rows, dtype=torch.float32)
-            sf, dsf = sfs[i]
-            check(L.evb_relation_fwd(ptr(u1.data), ptr(u2.data), ptr(f1[2]), ptr(f1[3]), ptr(f2[2]), ptr(f2[3]), ptr(sf),
-                                     ptr(z.data), ptr(rel), c_ll(m_rows), c_int(hh * ww), c_int(c), stream()),
-                  'evb_relation_fwd')
-            if train:
-                def bwd(z=z, u1=u1, u2=u2, f1=f1, f2=f2, sf=sf, dsf=dsf, rel=rel, cb=cb, rb=rb, m_rows=m_rows, hh=hh,
-                        ww=ww, c=c):
-                    if z.grad is None:
-                        return
-                    g1 = self._new(*u1.data.shape)
-                    g2 = self._new(*u2.data.shape)
-                    ws = self._ws(L.evb_relation_bwd_workspace(c_ll(m_rows), c_int(hh * ww), c_int(c)))
-                    check(L.evb_relation_bwd(ptr(z.grad), ptr(u1.data), ptr(u2.data), ptr(f1[2]), ptr(f1[3]), ptr(f2[2]),
-                                             ptr(f2[3]), ptr(sf), ptr(rel), ptr(g1), ptr(g2), ptr(dsf), c_ll(m_rows),
-                                             c_int(hh * ww), c_int(c), ptr(ws), stream()), 'evb_relation_bwd')
-                    self._bn_backward(g1, u1, cb, f1, 0, None, None)
-                    self._bn_backward(g2, u2, rb, f2, 0, None, None)
-                # must run BEFORE the conv backward closures of u1/u2 (registered earlier => run later): ok
-                self.tape.append(bwd)
-            zs.append(z)
-            self._dbg('z%d' % i, z)
-            self._dbg('rel%d' % i, rel)
-            self._dbg('sf%d' % i, sf)
-        # ---- asymmetric decoder
-        outs = []
-        for i in range(4):
-            y = zs[i]
-            for (cp, bp) in self.dec_blocks[i]:
-                o = self.conv(y, cp, train=train, stats=train)
-                y = self.bn_relu_up(o, bp, 2, train=train) if self.dec_nup[i] else self.bn_act(o, bp, True, train=train)
-            outs.append(y)
-            self._dbg('dec%d' % i, y)
+            st_i = self.level_streams[i - 1] if (self.level_streams is not None and i > 0) else None
+            t0 = len(self.tape)
+            if st_i is not None:
+                st_i.wait_event(ev_fork)
+                with torch.cuda.stream(st_i):
+                    outs[i] = self._level(i, inner[i], sfs[i], train)
+                if train:
+                    self._tape_tags.append((t0, len(self.tape), st_i))
+            else:
+                outs[i] = self._level(i, inner[i], sfs[i], train)
+        if self.level_streams is not None:
+            for st_i in self.level_streams:
+                main.wait_stream(st_i)
+        if train:
+            self._join_idx = len(self.tape)
         merged = Act(self._new(*outs[0].data.shape))
         check(L.evb_merge4(ptr(outs[0].data), ptr(outs[1].data), ptr(outs[2].data), ptr(outs[3].data), ptr(merged.data),
                            c_ll(merged.data.numel()), stream()), 'evb_merge4')
@@ -763,6 +780,7 @@ class FarSegEngine:
     def _forward_part1(self, x, labels):
         """pack weights, encoder, head, loss statistics (everything before the Dice all-reduce)."""
         self.tape = []
+        self._tape_tags, self._fork_idx, self._join_idx = [], None, None
         self._bn_tracked = []
         self._groups = []
         x = x.contiguous() if x.dtype == torch.uint8 else x.contiguous().float()
@@ -830,14 +848,41 @@ class FarSegEngine:
             cls.has_grad = True
             ws = self._ws(L.evb_bilinear_up_bwd_workspace(c_int(n), c_int(hh // f), c_int(ww // f), c_int(16), c_int(f)))
             check(L.evb_bilinear_up_bwd_sep(ptr(dlogits), ptr(cls.grad), c_int(n), c_int(hh // f), c_int(ww // f), c_int(16),
-                                            c_int(16), c_int(64), c_int(f), ptr(ws), c_ll(self.ws_bytes), stream()),
+                                            c_int(16), c_int(64), c_int(f), ptr(ws), c_ll(self._ws_cap()), stream()),
                   'evb_bilinear_up_bwd_sep')
-        for fn in reversed(self.tape):
-            fn()
+        self._run_tape()
         self._join_side()
         self.tape = []
         if allreduce:
             self.allreduce_grads()
+
+    def _run_tape(self):
+        """Run the backward closures in reverse order.  Closures of a pyramid-level branch run on that branch's stream:
+        entering the branch region the branch streams wait for the main stream (dq is ready), leaving it the main stream
+        waits for all of them (dsf_i and inner_i.grad are complete) -- the mirror image of the forward fork/join."""
+        tags = {}
+        for a, b, st_ in self._tape_tags:
+            for j in range(a, b):
+                tags[j] = st_
+        main = torch.cuda.current_stream()
+        fork_idx, join_idx = self._fork_idx, self._join_idx
+        use = self.level_streams is not None and fork_idx is not None
+        for idx in range(len(self.tape) - 1, -1, -1):
+            if use and idx == join_idx - 1:      # about to enter the branch region (from the loss side)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                for st_ in self.level_streams:
+                    st_.wait_event(ev)
+            st_ = tags.get(idx)
+            if st_ is not None:
+                with torch.cuda.stream(st_):
+                    self.tape[idx]()
+            else:
+                self.tape[idx]()
+            if use and idx == fork_idx:          # all branch closures are enqueued: join
+                for st_ in self.level_streams:
+                    main.wait_stream(st_)
+        self._tape_tags, self._fork_idx, self._join_idx = [], None, None
 
     def allreduce_grads(self):
         """The one gradient exchange of the step: NCCL all-reduce (mean) of the flat fp32 gradient arena

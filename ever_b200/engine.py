@@ -118,6 +118,7 @@ class FarSegEngine:
         self.accumulate = False      # gradient accumulation into existing .grad (forward_times > 1)
         self.fuse_bn_stats = True    # BN batch statistics in the producing conv's epilogue (evb_conv2d_fwd_stats)
         self._saved_for_backward = None
+        self._graphs = {}
         self.debug = None            # dict -> named activations are recorded (tests / diagnostics)
         cfg = module.config
         self.ignore_index = int(cfg.loss.ignore_index)
@@ -838,6 +839,10 @@ class FarSegEngine:
             raise RuntimeError('backward() without a preceding training forward')
         groups = self._saved_for_backward
         self._saved_for_backward = None
+        if isinstance(groups, str):   # graph_forward already replayed the backward
+            if allreduce:
+                self.allreduce_grads()
+            return
         for g in groups:
             logits, cls, k, f = g['logits'], g['cls'], g['k'], g['f']
             n, hh, ww, _ = logits.shape
@@ -956,6 +961,32 @@ class FarSegEngine:
             self._dice_allreduce()
             g2.replay()
         return replay, out
+
+    def graph_forward(self, x, labels):
+        """Training step through cached CUDA graphs, for callers with static shapes (the plugin's forward when
+        config.cuda_graph is on): inputs are copied into static device buffers, the captured forward + loss + backward
+        is replayed, the static loss tensors are returned and the gradients are already in the arena (backward() then
+        only runs the gradient all-reduce).  One capture per (shape, dtype) signature."""
+        lab = labels if isinstance(labels, dict) else dict(cls=labels)
+        key = (tuple(x.shape), x.dtype) + tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(lab.items()))
+        ent = self._graphs.get(key)
+        if ent is None:
+            sx = torch.empty_like(x, device=self.dev)
+            sl = {k: torch.empty_like(v, device=self.dev) for k, v in lab.items()}
+            sx.copy_(x)
+            for k, v in lab.items():
+                sl[k].copy_(v)
+            replay, out = self.capture_step(sx, sl if isinstance(labels, dict) else sl['cls'])
+            ent = (sx, sl, replay, out)
+            self._graphs[key] = ent
+        sx, sl, replay, out = ent
+        sx.copy_(x, non_blocking=True)
+        for k, v in lab.items():
+            sl[k].copy_(v, non_blocking=True)
+        self.attach_grads()
+        replay()
+        self._saved_for_backward = 'graph'
+        return out
 
     @torch.no_grad()
     def forward_eval(self, x, return_mask=False):

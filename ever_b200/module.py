@@ -192,6 +192,9 @@ class FarSegB200(ERModule):
             loss=dict(ce=dict(weight=1.0), dice=dict(weight=1.0, smooth=1.0, sync_statistics=True), ignore_index=255),
             # uint8 HWC inputs are normalised on the fly (th_mean_std_normalize defaults, ever/preprocess/function.py:9)
             input=dict(mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57.375)),
+            # static-shape training: forward() replays a cached CUDA graph of forward + loss + backward (one capture per
+            # input signature); backward() then only all-reduces.  Off by default (eager launches, any shape).
+            cuda_graph=False,
         ))
 
     # --------------------------------------------------------------------------------------------------
@@ -211,6 +214,8 @@ class FarSegB200(ERModule):
             if y is None:
                 raise ValueError('training forward needs y (dict with key "cls" or a label tensor)')
             labels = y['cls'] if isinstance(y, dict) else y
+            if bool(self.config.cuda_graph):
+                return eng.graph_forward(x, labels)
             return eng.forward_train(x, labels)
         return eng.forward_eval(x)
 
@@ -276,6 +281,8 @@ class ChangeStarB200(FarSegB200):
         if self.training:
             if not isinstance(y, dict) or 'cls' not in y or 'change' not in y:
                 raise ValueError("training forward needs y = {'cls': ..., 'change': ...}")
+            if bool(self.config.cuda_graph):
+                return eng.graph_forward(x, y)
             return eng.forward_train(x, y)
         return eng.forward_eval(x)
 

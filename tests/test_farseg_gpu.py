@@ -327,3 +327,28 @@ def test_stock_optimizer_path_equals_fused_sgd():
     assert abs(float(out['ce_loss']) - float(out_b['ce_loss'])) < 1e-5
     for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
         assert _rel(pa.data, pb.data) < 1e-5, na
+
+
+def test_plugin_cuda_graph_mode():
+    """config.cuda_graph=True: model(x, y) replays a cached graph of forward + loss + backward (static shapes);
+    losses and gradients are bit-identical to the eager plugin path, for changing batch contents."""
+    from oracle.farseg_oracle import synthetic_batch
+    resnet, k, dec, n, h, w = 'resnet18', 5, 128, 2, 128, 128
+    _, a = _build(resnet, k, dec)
+    _, b = _build(resnet, k, dec)
+    a, b = a.cuda().train(), b.cuda().train()
+    b.config.cuda_graph = True
+    for it in range(3):
+        x, y = synthetic_batch(n, h, w, k, seed_offset=it)
+        x, y = x.cuda(), y.cuda()
+        oa = a(x, dict(cls=y))
+        a.backward(oa, None, None)
+        ob = b(x, dict(cls=y))
+        b.backward(ob, None, None)
+        torch.cuda.synchronize()
+        assert {kk: float(v) for kk, v in oa.items()} == {kk: float(v) for kk, v in ob.items()}
+        assert torch.equal(a.engine.flat_g, b.engine.flat_g)
+        a.engine.sgd_step(0.01)
+        b.engine.sgd_step(0.01)
+    assert torch.equal(a.engine.flat_w, b.engine.flat_w)
+    assert len(b.engine._graphs) == 1

@@ -36,6 +36,18 @@ int evb_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint6
   return r == CUDA_SUCCESS ? EVB_OK : EVB_ERR_DRIVER;
 }
 
+#include <cstdlib>
+int g_evb_pdl = [] {
+  const char* e = getenv("EVB_PDL");
+  return (e && e[0] == '0') ? 0 : 1;
+}();
+
+// programmatic dependent launch of the tensor-core kernels (prologue overlaps the predecessor's tail): 1 on, 0 off
+extern "C" int evb_set_pdl(int on) {
+  g_evb_pdl = on ? 1 : 0;
+  return EVB_OK;
+}
+
 extern "C" int evb_version() { return 100; }
 
 // Last CUDA error string for diagnostics (does not clear sticky errors).

@@ -237,6 +237,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t taddr = *tslot;
+  pdl_wait();   // everything above overlapped the predecessor's tail; global memory is touched only below
 
   if (warp == 0) {
     if (lane == 0) {
@@ -509,7 +510,9 @@ static int launch_igemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     if (grid < p.tiles_c) return EVB_ERR_ARG;
     if (nblk_out) *nblk_out = grid / p.tiles_c;
   }
-  igemm2_kernel<NT, EPI, STATS><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, tmC, p);
+  if (evb_launch_pdl(igemm2_kernel<NT, EPI, STATS>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, st, tmA, tmB, tmC, p) !=
+      cudaSuccess)
+    return EVB_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
 }
 template <int NT>

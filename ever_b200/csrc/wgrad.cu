@@ -82,6 +82,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t taddr = *tslot;
+  pdl_wait();   // prologue above overlaps the predecessor's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -363,7 +364,7 @@ static int launch_wgrad(const CUtensorMap& a, const CUtensorMap& b, const WgradP
     attr_set = true;
   }
   const int grid = p.nsplit * p.ntaps * p.tiles_ci * p.tiles_co;
-  wgrad_kernel<NT, MT><<<grid, 192, Cfg::SMEM, st>>>(a, b, p);
+  if (evb_launch_pdl(wgrad_kernel<NT, MT>, dim3(grid), dim3(192), Cfg::SMEM, st, a, b, p) != cudaSuccess) return EVB_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
 }
 

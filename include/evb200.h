@@ -25,6 +25,9 @@ extern "C" {
 int evb_version(void);
 const char* evb_last_cuda_error(void);
 int evb_device_sync_check(void);
+/* programmatic dependent launch of the tensor-core kernels (their prologue overlaps the predecessor's tail); default on,
+ * EVB_PDL=0 in the environment or evb_set_pdl(0) turns it off */
+int evb_set_pdl(int on);
 
 /* ---- convolution (tcgen05 implicit GEMM).  Replaces nn.Conv2d forward/backward:
  * ever/module/_resnets.py:21-29,139-150 (ResNet 3x3/1x1/stem), ever/module/ops.py:53-55 (ConvBlock),

@@ -181,3 +181,32 @@ def test_two_rank_loss_rule_matches_ddp_reference():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) < 1e-5
+
+
+def test_step_loop_lr_timing_matches_reference_launcher():
+    """The reference sets the LR for the NEXT iteration from the not-yet-incremented global step
+    (ever/core/launcher.py:224-237): iteration 1 at base_lr, iteration k >= 2 at schedule(k - 2).  SURVEY.md a15 records the
+    Launcher log for poly(base 0.007, power 0.9, max_iters 3): lr after steps 1, 2, 3 = 0.007, 0.00486, 0.002604."""
+    from ever_b200.trainer import StepLoop, poly_lr
+
+    class _Eng:
+        def set_distributed(self, *a):
+            pass
+
+    class _Cfg:
+        cuda_graph = False
+
+    class _Model:
+        config = _Cfg()
+
+        def _engine(self):
+            return _Eng()
+    loop = StepLoop(_Model(), poly_lr(0.007, 0.9, 3), base_lr=0.007)
+    logged, used = [], []
+    for _ in range(3):
+        used.append(loop.lr)
+        loop._update_lr()
+        loop.global_step += 1
+        logged.append(loop.lr)
+    assert [round(v, 6) for v in logged] == [0.007, 0.00486, 0.002604]
+    assert [round(v, 6) for v in used] == [0.007, 0.007, 0.00486]

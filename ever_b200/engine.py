@@ -196,7 +196,10 @@ class FarSegEngine:
         self.fpn_inner = [C(getattr(h.fpn, 'fpn_inner%d' % i)[0]) for i in range(1, 5)]
         self.fpn_layer = [C(getattr(h.fpn, 'fpn_layer%d' % i)[0]) for i in range(1, 5)]
         fs = h.fs_relation
-        self.scene = [(s[0], s[2]) for s in fs.scene_encoder]  # (conv 2048->256, conv 256->256) as linears
+        # scene MLPs (conv 2048->256, conv 256->256) as linears: one per level, or one shared (scale_aware_proj=False)
+        self.scene_shared = not getattr(fs, 'scale_aware_proj', True)
+        self.scene = ([(fs.scene_encoder[0], fs.scene_encoder[2])] if self.scene_shared
+                      else [(s[0], s[2]) for s in fs.scene_encoder])
         self.content = [(C(s[0]), BNP_(s[1])) for s in fs.content_encoders]
         self.reenc = [(C(s[0]), BNP_(s[1])) for s in fs.feature_reencoders]
         dec = h.fpn_decoder
@@ -616,9 +619,17 @@ class FarSegEngine:
                                    c_int(0), stream()), 'evb_linear_fwd')
             dsf = self._new(n, co, dtype=torch.float32) if train else None
             outs.append((sf, dsf))
+            if self.scene_shared:
+                # scale_aware_proj=False (fs_relation.py:29-35,63-66): every level reads the same scene vector; each
+                # level's relation backward writes its own d(sf) buffer, summed in level order (fixed -> deterministic)
+                # before the shared MLP's backward
+                outs += [(sf, self._new(n, co, dtype=torch.float32) if train else None) for _ in range(3)]
             if train:
-                def bwd(l1=l1, l2=l2, hid=hid, sf=sf, dsf=dsf, co=co):
+                def bwd(l1=l1, l2=l2, hid=hid, sf=sf, dsf=dsf, co=co, extra=[d for _, d in outs[1:]] if self.scene_shared else []):
                     acc = 1 if self.accumulate else 0
+                    for d in extra:
+                        check(L.evb_copy2d_f32(ptr(d), c_int(co), ptr(dsf), c_int(co), c_int(n), c_int(co), c_int(1),
+                                               stream()), 'evb_copy2d_f32')
                     dhid = self._new(n, co, dtype=torch.float32)
                     check(L.evb_linear_bwd(ptr(dsf), ptr(sf), ptr(hid), ptr(l2.weight), ptr(l2.weight.grad),
                                            ptr(l2.bias.grad), ptr(dhid), c_int(n), c_int(co), c_int(co), c_int(0),

@@ -91,11 +91,14 @@ class _FPN(nn.Module):
 class _FSRelation(nn.Module):
     def __init__(self, scene_embedding_channels, in_channels_list, out_channels, scale_aware_proj=True):
         super().__init__()
-        if not scale_aware_proj:
-            raise NotImplementedError('FarSegB200 implements the default scale_aware_proj=True (fs_relation.py:193)')
-        self.scene_encoder = nn.ModuleList([
-            nn.Sequential(nn.Conv2d(scene_embedding_channels, out_channels, 1), nn.ReLU(True),
-                          nn.Conv2d(out_channels, out_channels, 1)) for _ in in_channels_list])
+        self.scale_aware_proj = bool(scale_aware_proj)
+        if self.scale_aware_proj:   # one scene MLP per pyramid level (fs_relation.py:22-28)
+            self.scene_encoder = nn.ModuleList([
+                nn.Sequential(nn.Conv2d(scene_embedding_channels, out_channels, 1), nn.ReLU(True),
+                              nn.Conv2d(out_channels, out_channels, 1)) for _ in in_channels_list])
+        else:                       # a single MLP shared by all levels (fs_relation.py:29-35)
+            self.scene_encoder = nn.Sequential(nn.Conv2d(scene_embedding_channels, out_channels, 1), nn.ReLU(True),
+                                               nn.Conv2d(out_channels, out_channels, 1))
         self.content_encoders = nn.ModuleList(
             [nn.Sequential(nn.Conv2d(c, out_channels, 1), nn.BatchNorm2d(out_channels), nn.ReLU(True)) for c in in_channels_list])
         self.feature_reencoders = nn.ModuleList(
@@ -180,8 +183,10 @@ class FarSegB200(ERModule):
 
     def set_default_config(self):
         self.config.update(dict(
+            # with_cp (activation checkpointing flags per stage, resnet.py:189-208) is accepted and has no effect: it
+            # never changes results, and the engine keeps every activation of the step resident in HBM by design
             encoder=dict(resnet_type='resnet50', in_channels=3, pretrained=False, batchnorm_trainable=True, freeze_at=0,
-                         output_stride=32, include_conv5=True),
+                         output_stride=32, include_conv5=True, with_cp=(False, False, False, False)),
             head=dict(
                 fpn=dict(in_channels_list=(256, 512, 1024, 2048), out_channels=256),
                 fs_relation=dict(scene_embedding_channels=2048, in_channels_list=(256, 256, 256, 256), out_channels=256,

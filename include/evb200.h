@@ -153,6 +153,26 @@ int evb_grad_norm(const float* g, long long n, float max_norm, float* norm_out, 
 int evb_sgd_step(float* w, float* g, float* mom, long long n, const float* lr, float momentum, float wd,
                  const float* clip, int first_step, int zero_grad, void* stream);
 
+/* ---- index-map kernels either side of the path.
+ * Map rows are int32[12] in device memory: {a00, a01, b0, a10, a11, b1, s, y0, y1, x0, x1, cb}.
+ * evb_pixel_gather: dst[n,i,j,:] = src[s][a00*i+a01*j+b0][a10*i+a11*j+b1][:] when that source pixel lies in
+ * [y0,y1) x [x0,x1), else `fill` (per element of elem_bytes).  One launch does any composition of torch.rot90 / torch.flip /
+ * transpose / crop / constant pad on a batch of pixel-interleaved images or label maps: THRandomRotate90k,
+ * THRandomHorizontalFlip, THRandomVerticalFlip, THRandomCrop (ever/preprocess/thsegm.py:7-147), th_divisible_pad /
+ * th_pad_to_size (ever/preprocess/function.py:35-83), the TTA transforms (ever/magic/transform/segm.py:9-72). */
+int evb_pixel_gather(const void* src, int Ns, int Hs, int Ws, int pix_bytes, int elem_bytes, long long fill,
+                     const void* maps, void* dst, int N, int Ho, int Wo, void* stream);
+/* canvas[B,K,Hc,Wc] fp32 += prob[*,K,h,w] tiles (a map row sends pixel (y,x) inside [y0,y1)x[x0,x1) of canvas `cb` (12th
+ * int of the row) to tile s pixel (a00*y+a01*x+b0, a10*y+a11*x+b1)); rows are summed in table order (deterministic, no
+ * atomics); count[B,Hc,Wc] += coverage.
+ * The accumulation a caller of sliding_window() (ever/magic/bigimage/sliding_window.py:8-33) does on the host, and
+ * `sum(outs)` of tta() (ever/magic/transform/tta.py:11-23) with the inverse transforms folded into the maps. */
+int evb_canvas_accumulate(const float* prob, int N, int K, int h, int w, const void* maps, float* canvas, float* count,
+                          int B, int Hc, int Wc, int ylo, int yhi, int xlo, int xhi, void* stream);
+/* prob[B,K,P] = canvas / count[B,P] (count NULL: / uniform_count, tta.py:21), mask[B,P] uint8 = argmax (K == 1: > 0.5) */
+int evb_canvas_finalize(const float* canvas, const float* count, float uniform_count, int B, int K, long long P,
+                        float* prob, void* mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

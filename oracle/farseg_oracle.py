@@ -216,14 +216,19 @@ class FPNOracle(nn.Module):
 
 
 class FSRelationOracle(nn.Module):
-    """FSRelation (scale_aware_proj=True), reference ever/module/fs_relation.py:14-73."""
+    """FSRelation, reference ever/module/fs_relation.py:14-73: one scene MLP per pyramid level when
+    scale_aware_proj (:22-28, the FarSegHead default :193), else a single shared MLP (:29-35)."""
 
     def __init__(self, scene_embedding_channels, in_channels_list, out_channels, scale_aware_proj=True):
         super().__init__()
-        assert scale_aware_proj, 'oracle restates the default scale_aware_proj=True path'
-        self.scene_encoder = nn.ModuleList([
-            nn.Sequential(nn.Conv2d(scene_embedding_channels, out_channels, 1), nn.ReLU(True),
-                          nn.Conv2d(out_channels, out_channels, 1)) for _ in in_channels_list])
+        self.scale_aware_proj = scale_aware_proj
+        if scale_aware_proj:
+            self.scene_encoder = nn.ModuleList([
+                nn.Sequential(nn.Conv2d(scene_embedding_channels, out_channels, 1), nn.ReLU(True),
+                              nn.Conv2d(out_channels, out_channels, 1)) for _ in in_channels_list])
+        else:
+            self.scene_encoder = nn.Sequential(nn.Conv2d(scene_embedding_channels, out_channels, 1), nn.ReLU(True),
+                                               nn.Conv2d(out_channels, out_channels, 1))
         self.content_encoders = nn.ModuleList()
         self.feature_reencoders = nn.ModuleList()
         for c in in_channels_list:
@@ -232,8 +237,12 @@ class FSRelationOracle(nn.Module):
 
     def forward(self, scene, feats):
         cfs = [enc(p) for enc, p in zip(self.content_encoders, feats)]
-        sfs = [enc(scene) for enc in self.scene_encoder]
-        rel = [torch.sigmoid((sf * cf).sum(dim=1, keepdim=True)) for sf, cf in zip(sfs, cfs)]
+        if self.scale_aware_proj:
+            sfs = [enc(scene) for enc in self.scene_encoder]
+            rel = [torch.sigmoid((sf * cf).sum(dim=1, keepdim=True)) for sf, cf in zip(sfs, cfs)]
+        else:
+            sf = self.scene_encoder(scene)
+            rel = [torch.sigmoid((sf * cf).sum(dim=1, keepdim=True)) for cf in cfs]
         pfs = [enc(p) for enc, p in zip(self.feature_reencoders, feats)]
         return [r * p for r, p in zip(rel, pfs)]
 
@@ -269,10 +278,11 @@ class DecoderOracle(nn.Module):
 class FarSegHeadOracle(nn.Module):
     """FarSegHead.forward, reference ever/module/fs_relation.py:166-206."""
 
-    def __init__(self, in_channels_list=(256, 512, 1024, 2048), fpn_channels=256, decoder_channels=256, num_classes=1):
+    def __init__(self, in_channels_list=(256, 512, 1024, 2048), fpn_channels=256, decoder_channels=256, num_classes=1,
+                 scale_aware_proj=True):
         super().__init__()
         self.fpn = FPNOracle(in_channels_list, fpn_channels)
-        self.fs_relation = FSRelationOracle(in_channels_list[-1], (fpn_channels,) * 4, fpn_channels, True)
+        self.fs_relation = FSRelationOracle(in_channels_list[-1], (fpn_channels,) * 4, fpn_channels, scale_aware_proj)
         self.fpn_decoder = DecoderOracle(fpn_channels, decoder_channels, num_classes=num_classes)
 
     def forward(self, feats):
@@ -320,10 +330,10 @@ class FarSegOracle(nn.Module):
     in training, softmax probabilities in eval."""
 
     def __init__(self, resnet_type='resnet50', num_classes=15, decoder_channels=256, in_channels=3, freeze_at=0,
-                 batchnorm_trainable=True):
+                 batchnorm_trainable=True, scale_aware_proj=True):
         super().__init__()
         self.en = ResNetEncoderOracle(resnet_type, in_channels, freeze_at, batchnorm_trainable)
-        self.head = FarSegHeadOracle(self.en.out_channels, 256, decoder_channels, num_classes)
+        self.head = FarSegHeadOracle(self.en.out_channels, 256, decoder_channels, num_classes, scale_aware_proj)
         self.dice_all_reduce = None
 
     def logits(self, x):

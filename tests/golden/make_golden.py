@@ -27,6 +27,8 @@ CASES = {
     'r18_k5_2x64': ('resnet18', 5, 2, 64, 64, 128),
     'r50_k15_1x64': ('resnet50', 15, 1, 64, 64, 256),
     'r18_k1_2x64': ('resnet18', 1, 2, 64, 64, 128),
+    # ResNetEncoder(in_channels=8) (resnet.py:100-117: fresh 7x7 conv) + FSRelation(scale_aware_proj=False) (fs_relation.py:29-35)
+    'r18_k5_c8_shared_2x64': ('resnet18', 5, 2, 64, 64, 128, dict(in_channels=8, scale_aware_proj=False)),
 }
 
 
@@ -47,19 +49,20 @@ class RefFarSeg(er.ERModule):
         self.config.update(dict(encoder=dict(), head=dict()))
 
 
-def ref_config(resnet, k, dec):
+def ref_config(resnet, k, dec, in_channels=3, scale_aware_proj=True):
     chans = (64, 128, 256, 512) if resnet in ('resnet18', 'resnet34') else (256, 512, 1024, 2048)
-    return dict(encoder=dict(resnet_type=resnet),
+    return dict(encoder=dict(resnet_type=resnet, in_channels=in_channels),
                 head=dict(fpn=dict(in_channels_list=chans, out_channels=256),
-                          fs_relation=dict(scene_embedding_channels=chans[-1]),
+                          fs_relation=dict(scene_embedding_channels=chans[-1], scale_aware_proj=scale_aware_proj),
                           fpn_decoder=dict(out_channels=dec, classifier_config=dict(num_classes=k, scale_factor=4.0, kernel_size=1))))
 
 
 def run_case(name):
-    resnet, k, n, h, w, dec = CASES[name]
-    m = RefFarSeg(ref_config(resnet, k, dec))
+    resnet, k, n, h, w, dec = CASES[name][:6]
+    opts = CASES[name][6] if len(CASES[name]) > 6 else {}
+    m = RefFarSeg(ref_config(resnet, k, dec, **opts))
     deterministic_fill(m, seed=0)
-    x, y = synthetic_batch(n, h, w, max(k, 2))
+    x, y = synthetic_batch(n, h, w, max(k, 2), in_channels=opts.get('in_channels', 3))
     if k == 1:
         # binary case exercises the sigmoid branch of dice (loss.py:66-68); CE is replaced by masked BCE
         from ever.module.loss import binary_cross_entropy_with_logits
@@ -88,5 +91,5 @@ def run_case(name):
 
 if __name__ == '__main__':
     torch.set_num_threads(8)
-    for c in CASES:
+    for c in (sys.argv[1:] or CASES):
         run_case(c)

@@ -19,12 +19,15 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-12))
 
 
-def _build(resnet, k, dec, freeze_at=0, bn_trainable=True):
+def _build(resnet, k, dec, freeze_at=0, bn_trainable=True, in_channels=3, scale_aware_proj=True):
     from ever_b200.module import FarSegB200
     from oracle.farseg_oracle import FarSegOracle, deterministic_fill
-    ora = deterministic_fill(FarSegOracle(resnet, k, dec, freeze_at=freeze_at, batchnorm_trainable=bn_trainable), 0)
-    mine = FarSegB200(dict(encoder=dict(resnet_type=resnet, freeze_at=freeze_at, batchnorm_trainable=bn_trainable),
-                           head=dict(fpn_decoder=dict(out_channels=dec, classifier_config=dict(num_classes=k)))))
+    ora = deterministic_fill(FarSegOracle(resnet, k, dec, freeze_at=freeze_at, batchnorm_trainable=bn_trainable,
+                                          in_channels=in_channels, scale_aware_proj=scale_aware_proj), 0)
+    mine = FarSegB200(dict(encoder=dict(resnet_type=resnet, freeze_at=freeze_at, batchnorm_trainable=bn_trainable,
+                                        in_channels=in_channels),
+                           head=dict(fs_relation=dict(scale_aware_proj=scale_aware_proj),
+                                     fpn_decoder=dict(out_channels=dec, classifier_config=dict(num_classes=k)))))
     mine.load_state_dict(ora.state_dict(), strict=True)
     return ora, mine
 
@@ -55,7 +58,12 @@ def _oracle_step(ora, x, y, autocast):
 
 
 CASES = [('resnet18', 5, 128, 2, 128, 128), ('resnet50', 15, 256, 2, 128, 128), ('resnet18', 5, 128, 3, 96, 160),
-         ('resnet18', 1, 128, 2, 128, 128), ('resnet50', 5, 128, 2, 128, 128, dict(freeze_at=2, bn_trainable=False))]
+         ('resnet18', 1, 128, 2, 128, 128), ('resnet50', 5, 128, 2, 128, 128, dict(freeze_at=2, bn_trainable=False)),
+         # ResNetEncoder(in_channels=8) (resnet.py:100-117) + FSRelation(scale_aware_proj=False) (fs_relation.py:29-35);
+         # same options as the real-reference fixture tests/golden/r18_k5_c8_shared_2x64.pt
+         ('resnet18', 5, 128, 2, 128, 128, dict(in_channels=8, scale_aware_proj=False)),
+         # hyperspectral-style high-channel stem (BASELINE configs[4] shape class): 200 input channels, ragged tile
+         ('resnet18', 5, 128, 1, 96, 160, dict(in_channels=200))]
 
 
 @pytest.mark.parametrize('case', CASES)
@@ -64,7 +72,7 @@ def test_train_step_parity(case):
     resnet, k, dec, n, h, w = case[:6]
     opts = case[6] if len(case) > 6 else {}
     ora, mine = _build(resnet, k, dec, **opts)
-    x, y = synthetic_batch(n, h, w, max(k, 2))
+    x, y = synthetic_batch(n, h, w, max(k, 2), in_channels=opts.get('in_channels', 3))
     x, y = x.cuda(), y.cuda()
     if opts.get('bn_trainable') is False:
         # frozen BN runs on running statistics: calibrate them to the batch statistics first so the random-weight
@@ -120,7 +128,7 @@ def test_train_step_parity(case):
     worst = sorted(grads.items(), key=lambda kv: -kv[1])[:8]
     rep['worst'] = worst
     os.makedirs('gpurun_out', exist_ok=True)
-    json.dump(rep, open('gpurun_out/parity_%s_%dx%dx%d.json' % (resnet, n, h, w), 'w'), indent=1)
+    json.dump(rep, open('gpurun_out/parity_%s_k%d_%dx%dx%d_c%d.json' % (resnet, k, n, h, w, x.shape[1]), 'w'), indent=1)
     print(json.dumps(dict(losses=rep['loss_mine'], bf16=loss_bf, fp32=loss_32, worst=worst)))
     for kk in loss_bf:
         assert abs(rep['loss_mine'][kk] - loss_bf[kk]) <= 1e-2 * abs(loss_bf[kk]), (kk, rep['loss_mine'], loss_bf)

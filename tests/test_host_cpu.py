@@ -44,13 +44,15 @@ def test_sass_has_tcgen05_and_tma():
     assert 'LDTM' in sass
 
 
-@pytest.mark.parametrize('resnet,k,dec', [('resnet18', 5, 128), ('resnet50', 15, 256), ('resnet101', 7, 256)])
-def test_state_dict_contract(resnet, k, dec):
+@pytest.mark.parametrize('resnet,k,dec,opts', [('resnet18', 5, 128, {}), ('resnet50', 15, 256, {}), ('resnet101', 7, 256, {}),
+                                               ('resnet18', 5, 128, dict(in_channels=8, scale_aware_proj=False))])
+def test_state_dict_contract(resnet, k, dec, opts):
     from ever_b200.module import FarSegB200
     from oracle.farseg_oracle import FarSegOracle
-    m = FarSegB200(dict(encoder=dict(resnet_type=resnet),
-                        head=dict(fpn_decoder=dict(out_channels=dec, classifier_config=dict(num_classes=k)))))
-    o = FarSegOracle(resnet, k, dec)
+    m = FarSegB200(dict(encoder=dict(resnet_type=resnet, in_channels=opts.get('in_channels', 3), with_cp=(True, True, False, False)),
+                        head=dict(fs_relation=dict(scale_aware_proj=opts.get('scale_aware_proj', True)),
+                                  fpn_decoder=dict(out_channels=dec, classifier_config=dict(num_classes=k)))))
+    o = FarSegOracle(resnet, k, dec, **opts)
     a = [(n, tuple(v.shape), v.dtype) for n, v in m.state_dict().items()]
     b = [(n, tuple(v.shape), v.dtype) for n, v in o.state_dict().items()]
     assert a == b

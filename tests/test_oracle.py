@@ -12,13 +12,14 @@ import torch.nn.functional as F
 from oracle.farseg_oracle import (FarSegOracle, bce_loss_oracle, deterministic_fill, dice_loss_oracle,
                                   synthetic_batch)
 
-CASES = ['r18_k5_2x64', 'r50_k15_1x64', 'r18_k1_2x64']
+CASES = ['r18_k5_2x64', 'r50_k15_1x64', 'r18_k1_2x64', 'r18_k5_c8_shared_2x64']
 
 
 def _run_oracle(case):
-    resnet, k, n, h, w, dec = case
-    m = deterministic_fill(FarSegOracle(resnet, k, dec), 0)
-    x, y = synthetic_batch(n, h, w, max(k, 2))
+    resnet, k, n, h, w, dec = case[:6]
+    opts = case[6] if len(case) > 6 else {}
+    m = deterministic_fill(FarSegOracle(resnet, k, dec, **opts), 0)
+    x, y = synthetic_batch(n, h, w, max(k, 2), in_channels=opts.get('in_channels', 3))
     m.train()
     if k == 1:
         logit = m.logits(x)
@@ -54,17 +55,18 @@ def test_oracle_matches_golden(name, golden_dir):
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/ever'), reason='reference tree only exists in the build container')
-def test_oracle_bit_exact_vs_reference(golden_dir):
-    sys.path.insert(0, '/root/reference')
-    sys.path.insert(0, os.path.join(golden_dir, '_stubs'))
-    sys.path.insert(0, golden_dir)
+@pytest.mark.parametrize('name', ['r18_k5_2x64', 'r18_k5_c8_shared_2x64'])
+def test_oracle_bit_exact_vs_reference(name, golden_dir):
+    for p_ in ('/root/reference', os.path.join(golden_dir, '_stubs'), golden_dir):
+        if p_ not in sys.path:
+            sys.path.insert(0, p_)
     import make_golden as mg
-    name = 'r18_k5_2x64'
-    resnet, k, n, h, w, dec = mg.CASES[name]
-    ref = deterministic_fill(mg.RefFarSeg(mg.ref_config(resnet, k, dec)), 0)
-    ora = deterministic_fill(FarSegOracle(resnet, k, dec), 0)
+    resnet, k, n, h, w, dec = mg.CASES[name][:6]
+    opts = mg.CASES[name][6] if len(mg.CASES[name]) > 6 else {}
+    ref = deterministic_fill(mg.RefFarSeg(mg.ref_config(resnet, k, dec, **opts)), 0)
+    ora = deterministic_fill(FarSegOracle(resnet, k, dec, **opts), 0)
     assert list(ref.state_dict().keys()) == list(ora.state_dict().keys())
-    x, y = synthetic_batch(n, h, w, k)
+    x, y = synthetic_batch(n, h, w, k, in_channels=opts.get('in_channels', 3))
     ref.train(), ora.train()
     torch.set_num_threads(8)
     lr, _ = ref(x, dict(cls=y))

@@ -137,7 +137,7 @@ def tta(model, image, tta_config, return_mask=False):
             raise NotImplementedError('tta() handles single-output models')
         if canvas is None:
             canvas = torch.zeros((n, prob.shape[1], h, w), dtype=torch.float32, device=image.device)
-        inv = m.inverse()
+        inv = m.inverse().shifted(0, 0)   # canvas rows clip in canvas coordinates: the whole image
         _canvas_accumulate(prob.contiguous(), [inv.row(i, i) for i in range(n)], canvas, None, (0, h, 0, w))
     return _finalize_out(_canvas_finalize(canvas, None, float(len(tta_config)), return_mask), return_mask)
 

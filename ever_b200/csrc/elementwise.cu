@@ -120,14 +120,15 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 // one warp per channel: lanes stride over the partial blocks, fixed-order tree -> deterministic
+template <int LDP = kNbPad>
 __device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s,
                                                 double& ss) {
   const int lane = threadIdx.x & 31;
   double a = 0.0, b = 0.0;
-  const float* pa = partial + (size_t)c * kNbPad;
-  const float* pb = partial + ((size_t)C + c) * kNbPad;
+  const float* pa = partial + (size_t)c * LDP;
+  const float* pb = partial + ((size_t)C + c) * LDP;
 #pragma unroll
-  for (int j = 0; j < kNbPad / 32; ++j) {
+  for (int j = 0; j < LDP / 32; ++j) {
     const int k = lane + 32 * j;
     if (k < nblk) { a += pa[k]; b += pb[k]; }
   }
@@ -305,6 +306,415 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Narrow-vector variants of the BatchNorm streaming kernels.  A thread owns V (4 or 8) consecutive channels, so its
+// per-channel constants live in 3-4 * V registers; with V = 4 the kernels need ~half the registers of the V = 8 versions,
+// twice as many CTAs fit per SM and twice the bytes are in flight per SM (measured on B200: the V = 8 backward kernels
+// ran at 46 % of the copy bandwidth, in-flight-limited).  MASK is a template parameter so unused constants are pruned.
+// ------------------------------------------------------------------------------------------------
+template <int V> struct bvec;
+template <> struct alignas(8) bvec<4> { uint32_t u[2]; };
+template <> struct alignas(16) bvec<8> { uint32_t u[4]; };
+template <int V>
+__device__ __forceinline__ void unpackv(const bvec<V>& v, float (&f)[V]) {
+#pragma unroll
+  for (int i = 0; i < V / 2; ++i) {
+    float2 t = unpack_bf16x2(v.u[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+template <int V>
+__device__ __forceinline__ bvec<V> packv(const float (&f)[V]) {
+  bvec<V> v;
+#pragma unroll
+  for (int i = 0; i < V / 2; ++i) v.u[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+// BN backward reduction: per-channel sums of g = dy * mask and g * (x - mean) over M rows (rstd is applied by the finalize
+// kernel).  MASK 0: none; 1: ymask > 0; 2: recomputed bf16(x*scale+shift) > 0.  partial[which][C][kNbPadBwd], column = block.
+constexpr int kNbPadBwd = 640;   // up to 4 reduce blocks per SM
+template <int V, int MASK, int UN>
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                     const __nv_bfloat16* __restrict__ ymask, const float* __restrict__ mean,
+                     const float* __restrict__ scale, const float* __restrict__ shift, long long M, int C,
+                     float* __restrict__ partial) {
+  extern __shared__ float sm[];  // [thread][2 * V]
+  const int cg = C / V;
+  const int rows_par = blockDim.x / cg;
+  const int t = threadIdx.x;
+  const int g = t % cg, rsub = t / cg;
+  const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  float s0[V], s1[V], mu[V], sc[V], sh[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    s0[j] = s1[j] = 0.f;
+    mu[j] = mean[g * V + j];
+    if (MASK == 2) { sc[j] = scale[g * V + j]; sh[j] = shift[g * V + j]; }
+  }
+  const size_t col = (size_t)g * V;
+  for (long long rb = r0 + rsub; rb < r1; rb += (long long)rows_par * UN) {
+    bvec<V> xq[UN], gq[UN], yq[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long r = rb + (long long)u * rows_par;
+      if (r < r1) {
+        xq[u] = *reinterpret_cast<const bvec<V>*>(x + r * C + col);
+        gq[u] = *reinterpret_cast<const bvec<V>*>(dy + r * C + col);
+        if (MASK == 1) yq[u] = *reinterpret_cast<const bvec<V>*>(ymask + r * C + col);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long r = rb + (long long)u * rows_par;
+      if (r >= r1) continue;
+      float xv[V], gv[V];
+      unpackv<V>(xq[u], xv);
+      unpackv<V>(gq[u], gv);
+      if (MASK == 1) {
+        float yv[V];
+        unpackv<V>(yq[u], yv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
+      } else if (MASK == 2) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) gv[j] = bf16_round(xv[j] * sc[j] + sh[j]) > 0.f ? gv[j] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) { s0[j] += gv[j]; s1[j] += gv[j] * (xv[j] - mu[j]); }
+    }
+  }
+  float* my = sm + (size_t)t * 2 * V;
+#pragma unroll
+  for (int j = 0; j < V; ++j) { my[j] = s0[j]; my[V + j] = s1[j]; }
+  __syncthreads();
+  for (int o = t; o < 2 * C; o += blockDim.x) {
+    const int which = o / C, c = o % C;
+    const int gg = c / V, j = c % V;
+    float acc = 0.f;
+    for (int rs_ = 0; rs_ < rows_par; ++rs_) acc += sm[((size_t)rs_ * cg + gg) * 2 * V + which * V + j];
+    partial[((size_t)which * C + c) * kNbPadBwd + blockIdx.x] = acc;
+  }
+}
+
+// finalize of bn_bwd_reduce_kernel: dbeta = sum g, dgamma = rstd * sum g (x - mean); fixed-order fp64 reduction
+__global__ void bn_bwd_finalize2_kernel(const float* __restrict__ partial, int nblk, int C, const float* __restrict__ rstd,
+                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
+                                        float* __restrict__ fresh) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= C) return;
+  double s, ss;
+  reduce_partials<kNbPadBwd>(partial, nblk, C, c, s, ss);
+  if ((threadIdx.x & 31) != 0) return;
+  const float dg = (float)(ss * (double)rstd[c]);
+  fresh[c] = (float)s;
+  fresh[C + c] = dg;
+  if (dgamma) { if (accumulate) dgamma[c] += dg; else dgamma[c] = dg; }
+  if (dbeta) { if (accumulate) dbeta[c] += (float)s; else dbeta[c] = (float)s; }
+}
+
+// dx = a*g + k0 - c2*x (see bn_bwd_apply_kernel), V channels per thread, UN vectors in flight
+template <int V, int MASK, int UN>
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_apply2_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                     const __nv_bfloat16* __restrict__ ymask, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ dgamma, const float* __restrict__ dbeta, int frozen,
+                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres, int dres_acc, unsigned nvec, int C,
+                     float inv_m) {
+  const int cg = C / V;
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned stride = gridDim.x * blockDim.x;
+  const int c0 = (int)(tid % (unsigned)cg) * V;
+  float a[V], k0[V], c2[V], sh[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int c = c0 + j;
+    a[j] = scale[c];
+    if (MASK == 2) sh[j] = shift[c];
+    if (frozen) { c2[j] = 0.f; k0[j] = 0.f; }
+    else {
+      c2[j] = a[j] * rstd[c] * dgamma[c] * inv_m;
+      k0[j] = c2[j] * mean[c] - a[j] * dbeta[c] * inv_m;
+    }
+  }
+  typedef bvec<V> VT;
+  for (unsigned i0 = tid; i0 < nvec; i0 += stride * UN) {
+    VT gv[UN], xv[UN], yv[UN], dv[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const unsigned i = i0 + u * stride;
+      if (i < nvec) {
+        gv[u] = reinterpret_cast<const VT*>(dy)[i];
+        xv[u] = reinterpret_cast<const VT*>(x)[i];
+        if (MASK == 1) yv[u] = reinterpret_cast<const VT*>(ymask)[i];
+        if (dres && dres_acc) dv[u] = reinterpret_cast<const VT*>(dres)[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const unsigned i = i0 + u * stride;
+      if (i < nvec) {
+        float g[V], xf[V];
+        unpackv<V>(gv[u], g);
+        unpackv<V>(xv[u], xf);
+        if (MASK == 1) {
+          float yf[V];
+          unpackv<V>(yv[u], yf);
+#pragma unroll
+          for (int j = 0; j < V; ++j) g[j] = yf[j] > 0.f ? g[j] : 0.f;
+        } else if (MASK == 2) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) g[j] = bf16_round(xf[j] * a[j] + sh[j]) > 0.f ? g[j] : 0.f;
+        }
+        if (dres) {
+          float d[V];
+          if (dres_acc) {
+            unpackv<V>(dv[u], d);
+#pragma unroll
+            for (int j = 0; j < V; ++j) d[j] += g[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) d[j] = g[j];
+          }
+          reinterpret_cast<VT*>(dres)[i] = packv<V>(d);
+        }
+        float o[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) o[j] = a[j] * g[j] + k0[j] - c2[j] * xf[j];
+        reinterpret_cast<VT*>(dx)[i] = packv<V>(o);
+      }
+    }
+  }
+}
+
+// y = act(bf16(x*scale+shift) [+ res]), V channels per thread
+template <int V, int UN>
+__global__ void __launch_bounds__(kEwThreads)
+bn_apply2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                 const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, unsigned nvec, int C, int relu) {
+  const int cg = C / V;
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned stride = gridDim.x * blockDim.x;
+  const int c0 = (int)(tid % (unsigned)cg) * V;
+  float a[V], b[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { a[j] = scale[c0 + j]; b[j] = shift[c0 + j]; }
+  typedef bvec<V> VT;
+  for (unsigned i0 = tid; i0 < nvec; i0 += stride * UN) {
+    VT xv[UN], rv[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const unsigned i = i0 + u * stride;
+      if (i < nvec) {
+        xv[u] = reinterpret_cast<const VT*>(x)[i];
+        if (res) rv[u] = reinterpret_cast<const VT*>(res)[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const unsigned i = i0 + u * stride;
+      if (i < nvec) {
+        float v[V];
+        unpackv<V>(xv[u], v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = v[j] * a[j] + b[j];
+        if (res) {
+          float r[V];
+          unpackv<V>(rv[u], r);
+#pragma unroll
+          for (int j = 0; j < V; ++j) v[j] = bf16_round(v[j]) + r[j];
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        reinterpret_cast<VT*>(y)[i] = packv<V>(v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cp.async-staged BatchNorm backward.  The register-staged kernels above keep at most UN 16-byte loads per tensor in
+// flight per thread and stall between "issue" and "consume" phases (measured 2.7-3.7 TB/s of the 6.5 TB/s copy peak on
+// the 67 MB layers).  Here every thread streams its own vectors through a private ring of S shared-memory slots filled
+// by cp.async (LDGSTS, L1-bypassing): S-1 loads per tensor stay in flight per thread without holding registers, no block
+// barrier is needed (a thread only reads slots it filled itself), and 3 CTAs x 256 threads fit per SM.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kCaStages = 8;
+
+// per-channel sums of g = dy*mask and g*(x-mean); same partial layout / finalize as bn_bwd_reduce_kernel
+template <int MASK>
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_reduce_ca_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                        const __nv_bfloat16* __restrict__ ymask, const float* __restrict__ mean,
+                        const float* __restrict__ scale, const float* __restrict__ shift, long long M, int C,
+                        float* __restrict__ partial) {
+  constexpr int NT = MASK == 1 ? 3 : 2;   // tensors streamed
+  constexpr int S = kCaStages;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  bf16x8* ring = reinterpret_cast<bf16x8*>(smraw);   // [S][NT][blockDim]
+  const int nthr = blockDim.x;
+  const int cg = C / 8;
+  const int rows_par = nthr / cg;
+  const int t = threadIdx.x;
+  const int g = t % cg, rsub = t / cg;
+  const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  float s0[8], s1[8], mu[8], sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s0[j] = s1[j] = 0.f;
+    mu[j] = mean[g * 8 + j];
+    if (MASK == 2) { sc[j] = scale[g * 8 + j]; sh[j] = shift[g * 8 + j]; }
+  }
+  const size_t col = (size_t)g * 8;
+  const long long first = r0 + rsub;
+  const int niter = first < r1 ? (int)((r1 - first + rows_par - 1) / rows_par) : 0;
+  auto issue = [&](int it) {
+    if (it < niter) {
+      const size_t off = (size_t)(first + (long long)it * rows_par) * C + col;
+      bf16x8* slot = ring + (size_t)(it % S) * NT * nthr + t;
+      cp_async16(slot, x + off);
+      cp_async16(slot + nthr, dy + off);
+      if (MASK == 1) cp_async16(slot + 2 * nthr, ymask + off);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int it = 0; it < S - 1; ++it) issue(it);
+  for (int it = 0; it < niter; ++it) {
+    issue(it + S - 1);
+    cp_async_wait<S - 1>();
+    const bf16x8* slot = ring + (size_t)(it % S) * NT * nthr + t;
+    float xv[8], gv[8];
+    unpack8(slot[0], xv);
+    unpack8(slot[nthr], gv);
+    if (MASK == 1) {
+      float yv[8];
+      unpack8(slot[2 * nthr], yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
+    } else if (MASK == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] = bf16_round(xv[j] * sc[j] + sh[j]) > 0.f ? gv[j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s0[j] += gv[j]; s1[j] += gv[j] * (xv[j] - mu[j]); }
+  }
+  cp_async_wait<0>();
+  __syncthreads();   // everyone is done with the ring: reuse it for the cross-row reduction
+  float* sm = reinterpret_cast<float*>(smraw);
+  float* my = sm + (size_t)t * 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { my[j] = s0[j]; my[8 + j] = s1[j]; }
+  __syncthreads();
+  for (int o = t; o < 2 * C; o += nthr) {
+    const int which = o / C, c = o % C;
+    const int gg = c / 8, j = c % 8;
+    float acc = 0.f;
+    for (int rs_ = 0; rs_ < rows_par; ++rs_) acc += sm[((size_t)rs_ * cg + gg) * 16 + which * 8 + j];
+    partial[((size_t)which * C + c) * kNbPadBwd + blockIdx.x] = acc;
+  }
+}
+
+// dx = a*g + k0 - c2*x ; optional dres (+)= g   (the dres accumulate input is a plain load: it is rare and L2-resident)
+template <int MASK>
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_apply_ca_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                       const __nv_bfloat16* __restrict__ ymask, const float* __restrict__ mean,
+                       const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
+                       const float* __restrict__ dgamma, const float* __restrict__ dbeta, int frozen,
+                       __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres, int dres_acc, unsigned nvec, int C,
+                       float inv_m) {
+  constexpr int NT = MASK == 1 ? 3 : 2;
+  constexpr int S = kCaStages;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  bf16x8* ring = reinterpret_cast<bf16x8*>(smraw);   // [S][NT][blockDim]
+  const int nthr = blockDim.x;
+  const int t = threadIdx.x;
+  const int cg = C / 8;
+  const unsigned tid = blockIdx.x * nthr + t;
+  const unsigned stride = gridDim.x * nthr;
+  const int c0 = (int)(tid % (unsigned)cg) * 8;
+  float a[8], k0[8], c2[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    a[j] = scale[c];
+    if (MASK == 2) sh[j] = shift[c];
+    if (frozen) { c2[j] = 0.f; k0[j] = 0.f; }
+    else {
+      c2[j] = a[j] * rstd[c] * dgamma[c] * inv_m;
+      k0[j] = c2[j] * mean[c] - a[j] * dbeta[c] * inv_m;
+    }
+  }
+  const int niter = tid < nvec ? (int)((nvec - tid + stride - 1) / stride) : 0;
+  const bf16x8* gx = reinterpret_cast<const bf16x8*>(x);
+  const bf16x8* gg = reinterpret_cast<const bf16x8*>(dy);
+  const bf16x8* gy = reinterpret_cast<const bf16x8*>(ymask);
+  auto issue = [&](int it) {
+    if (it < niter) {
+      const size_t i = (size_t)tid + (size_t)it * stride;
+      bf16x8* slot = ring + (size_t)(it % S) * NT * nthr + t;
+      cp_async16(slot, gx + i);
+      cp_async16(slot + nthr, gg + i);
+      if (MASK == 1) cp_async16(slot + 2 * nthr, gy + i);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int it = 0; it < S - 1; ++it) issue(it);
+  for (int it = 0; it < niter; ++it) {
+    issue(it + S - 1);
+    cp_async_wait<S - 1>();
+    const size_t i = (size_t)tid + (size_t)it * stride;
+    const bf16x8* slot = ring + (size_t)(it % S) * NT * nthr + t;
+    float xf[8], g[8];
+    unpack8(slot[0], xf);
+    unpack8(slot[nthr], g);
+    if (MASK == 1) {
+      float yf[8];
+      unpack8(slot[2 * nthr], yf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = yf[j] > 0.f ? g[j] : 0.f;
+    } else if (MASK == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = bf16_round(xf[j] * a[j] + sh[j]) > 0.f ? g[j] : 0.f;
+    }
+    if (dres) {
+      float d[8];
+      if (dres_acc) {
+        unpack8(reinterpret_cast<const bf16x8*>(dres)[i], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] += g[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = g[j];
+      }
+      reinterpret_cast<bf16x8*>(dres)[i] = pack8(d);
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = a[j] * g[j] + k0[j] - c2[j] * xf[j];
+    reinterpret_cast<bf16x8*>(dx)[i] = pack8(o);
+  }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------ max pool 3x3 s2 p1
@@ -830,7 +1240,7 @@ static int colsum_blocks(long long M, int C) {
   return (int)b;
 }
 
-extern "C" long long evb_bn_workspace(long long M, int C) { (void)M; return ((long long)kNbPad + 1) * 2 * C * sizeof(float); }
+extern "C" long long evb_bn_workspace(long long M, int C) { (void)M; return ((long long)kNbPadBwd + 1) * 2 * C * sizeof(float); }
 
 // Training BN statistics of x[M,C] + folded scale/shift + running-stat update.
 extern "C" int evb_bn_stats(const void* x, long long M, int C, const float* gamma, const float* beta, float* running_mean,
@@ -863,37 +1273,132 @@ extern "C" int evb_bn_fold(const float* gamma, const float* beta, const float* r
 }
 
 // y = act(bf16(x*scale+shift) [+res])
+static int g_bn_blocks_per_sm = 4;   // reduce-kernel grid cap (blocks per SM), <= kNbPadBwd / 148
+extern "C" int evb_set_bn_reduce_blocks(int per_sm) {
+  if (per_sm < 1 || per_sm * 148 > kNbPadBwd) return EVB_ERR_ARG;
+  g_bn_blocks_per_sm = per_sm;
+  return EVB_OK;
+}
+static int g_bn_variant = 2;   // BN backward kernels: 2 = cp.async-staged (default), 1 = register-staged
+extern "C" int evb_set_bn_variant(int v) {
+  if (v != 1 && v != 2) return EVB_ERR_ARG;
+  g_bn_variant = v;
+  return EVB_OK;
+}
+static int g_bn_vec = 0;   // 0 = auto (4 channels per thread when C <= 1024), 4 / 8 forced (A/B measurements)
+extern "C" int evb_set_bn_vec(int v) {
+  if (v != 0 && v != 4 && v != 8) return EVB_ERR_ARG;
+  g_bn_vec = v;
+  return EVB_OK;
+}
+static inline int bn_vec_for(int C) {
+  int v = g_bn_vec ? g_bn_vec : 4;
+  if (v == 4 && (C % 4 || C / 4 > kEwThreads)) v = 8;
+  return v;
+}
+
 extern "C" int evb_bn_apply(const void* x, const float* scale, const float* shift, const void* res, void* y, long long M,
                             int C, int relu, void* stream) {
   if (C % 8) return EVB_ERR_ARG;
-  const long long nvec = M * C / 8;
-  const int cg_ = C / 8;
-  if (cg_ > kEwThreads) return EVB_ERR_ARG;
+  if (C / 8 > kEwThreads) return EVB_ERR_ARG;
+  int V = bn_vec_for(C);
+  if (M * C / 4 >= (1LL << 31) - (1LL << 24)) V = 8;   // the narrow kernels index vectors with 32 bits
+  const long long nvec = M * C / V;
+  const int cg_ = C / V;
   const int bt = (kEwThreads / cg_) * cg_;
-  bn_apply_kernel<<<ew_blocks(nvec, bt * 4), bt, 0, ST>>>((const __nv_bfloat16*)x, scale, shift,
-                                                                       (const __nv_bfloat16*)res, (__nv_bfloat16*)y, nvec,
-                                                                       C, relu);
+  if (V == 4)
+    bn_apply2_kernel<4, 8><<<ew_blocks(nvec, bt * 8), bt, 0, ST>>>((const __nv_bfloat16*)x, scale, shift,
+                                                                  (const __nv_bfloat16*)res, (__nv_bfloat16*)y,
+                                                                  (unsigned)nvec, C, relu);
+  else
+    bn_apply_kernel<<<ew_blocks(nvec, bt * 4), bt, 0, ST>>>((const __nv_bfloat16*)x, scale, shift,
+                                                           (const __nv_bfloat16*)res, (__nv_bfloat16*)y, nvec, C, relu);
   return LAUNCH_OK();
 }
 
 // BN (+ReLU mask) backward.  mask_mode: 0 none, 1 from ymask>0, 2 recomputed from x*scale+shift>0.
 // frozen!=0: statistics were constants (eval / frozen BN): dx = g*scale, dgamma/dbeta still produced.
+template <int MASK>
+static int launch_bn_bwd_ca(const void* dy, const void* x, const void* ymask, const float* mean, const float* rstd,
+                            const float* scale, const float* shift, int frozen, void* dx, void* dres, int dres_acc,
+                            float* dgamma, float* dbeta, int param_acc, long long M, int C, void* ws, cudaStream_t st) {
+  constexpr int NT = MASK == 1 ? 3 : 2;
+  const int cg = C / 8;
+  const int bt = (kEwThreads / cg) * cg;
+  const int rows_par = bt / cg;
+  const size_t smem = (size_t)kCaStages * NT * bt * 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(bn_bwd_reduce_ca_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 256 * 16) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(bn_bwd_apply_ca_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 256 * 16) !=
+            cudaSuccess)
+      return EVB_ERR_CUDA;
+    attr_set = true;
+  }
+  long long nb = (M + (long long)rows_par * 16 - 1) / ((long long)rows_par * 16);   // >= 16 iterations per thread
+  int per_sm = g_bn_blocks_per_sm;
+  if (per_sm > (NT == 3 ? 2 : 3)) per_sm = NT == 3 ? 2 : 3;   // resident CTAs per SM with the 64 / 96 KB rings
+  const int cap = per_sm * 148;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  bn_bwd_reduce_ca_kernel<MASK><<<(int)nb, bt, smem, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
+                                                         (const __nv_bfloat16*)ymask, mean, scale, shift, M, C, (float*)ws);
+  float* fresh = (float*)ws + (size_t)kNbPadBwd * 2 * C;
+  bn_bwd_finalize2_kernel<<<(C + 7) / 8, 256, 0, st>>>((const float*)ws, (int)nb, C, rstd, dgamma, dbeta, param_acc, fresh);
+  const long long nvec = M * C / 8;
+  bn_bwd_apply_ca_kernel<MASK><<<ew_blocks(nvec, bt * 8, 148 * (NT == 3 ? 2 : 3)), bt, smem, st>>>(
+      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ymask, mean, rstd, scale, shift, fresh + C,
+      fresh, frozen, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, dres_acc, (unsigned)nvec, C, 1.0f / (float)M);
+  return EVB_OK;
+}
+
+template <int V, int MASK>
+static void launch_bn_bwd(const void* dy, const void* x, const void* ymask, const float* mean, const float* rstd,
+                          const float* scale, const float* shift, int frozen, void* dx, void* dres, int dres_acc,
+                          float* dgamma, float* dbeta, int param_acc, long long M, int C, void* ws, cudaStream_t st) {
+  constexpr int UNR = V == 4 ? 4 : 2, UNA = V == 4 ? 4 : 2;
+  const int cg = C / V;
+  const int bt = (kEwThreads / cg) * cg;
+  const int rows_par = bt / cg;
+  long long nb = (M + (long long)rows_par * UNR * 2 - 1) / ((long long)rows_par * UNR * 2);
+  const int cap = g_bn_blocks_per_sm * 148;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  bn_bwd_reduce_kernel<V, MASK, UNR><<<(int)nb, bt, bt * 2 * V * sizeof(float), st>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)ymask, mean, scale, shift, M, C, (float*)ws);
+  float* fresh = (float*)ws + (size_t)kNbPadBwd * 2 * C;
+  bn_bwd_finalize2_kernel<<<(C + 7) / 8, 256, 0, st>>>((const float*)ws, (int)nb, C, rstd, dgamma, dbeta, param_acc, fresh);
+  const long long nvec = M * C / V;
+  bn_bwd_apply2_kernel<V, MASK, UNA><<<ew_blocks(nvec, bt * UNA), bt, 0, st>>>(
+      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ymask, mean, rstd, scale, shift, fresh + C,
+      fresh, frozen, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, dres_acc, (unsigned)nvec, C, 1.0f / (float)M);
+}
+
 extern "C" int evb_bn_bwd(const void* dy, const void* x, const void* ymask, const float* mean, const float* rstd,
                           const float* scale, const float* shift, int mask_mode, int frozen, void* dx, void* dres,
                           int dres_acc, float* dgamma, float* dbeta, int param_acc, long long M, int C, void* ws,
                           void* stream) {
-  if (C % 8 || C > 2048) return EVB_ERR_ARG;
-  const int nb = colsum_blocks(M, C);
-  colsum_kernel<1><<<nb, kEwThreads, kEwThreads * 16 * sizeof(float), ST>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)ymask, mean, rstd, scale, shift, mask_mode,
-      M, C, (float*)ws);
-  float* fresh = (float*)ws + (size_t)kNbPad * 2 * C;
-  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, ST>>>((const float*)ws, nb, C, dgamma, dbeta, param_acc, fresh);
-  const long long nvec = M * C / 8;
-  const int bt = (kEwThreads / (C / 8)) * (C / 8);
-  bn_bwd_apply_kernel<<<ew_blocks(nvec, bt * 2), bt, 0, ST>>>(
-      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ymask, mean, rstd, scale, shift, fresh + C,
-      fresh, mask_mode, frozen, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, dres_acc, nvec, C, 1.0f / (float)M);
+  if (C % 8 || C > 2048 || mask_mode < 0 || mask_mode > 2) return EVB_ERR_ARG;
+  if (M * C / 8 >= (1LL << 31) - (1LL << 24)) return EVB_ERR_ARG;
+  int V = bn_vec_for(C);
+  if (M * C / 4 >= (1LL << 31) - (1LL << 24)) V = 8;
+  if (g_bn_variant == 2) {
+    int rc;
+    if (mask_mode == 0) rc = launch_bn_bwd_ca<0>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
+    else if (mask_mode == 1) rc = launch_bn_bwd_ca<1>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
+    else rc = launch_bn_bwd_ca<2>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
+    if (rc) return rc;
+    return LAUNCH_OK();
+  }
+#define EVB_BN_BWD(V_, MK_) launch_bn_bwd<V_, MK_>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, \
+                                                   dbeta, param_acc, M, C, ws, ST)
+  if (V == 4) {
+    if (mask_mode == 0) EVB_BN_BWD(4, 0); else if (mask_mode == 1) EVB_BN_BWD(4, 1); else EVB_BN_BWD(4, 2);
+  } else {
+    if (mask_mode == 0) EVB_BN_BWD(8, 0); else if (mask_mode == 1) EVB_BN_BWD(8, 1); else EVB_BN_BWD(8, 2);
+  }
+#undef EVB_BN_BWD
   return LAUNCH_OK();
 }
 

@@ -95,6 +95,12 @@ int evb_bn_fold(const float* gamma, const float* beta, const float* rm, const fl
 int evb_bn_apply(const void* x, const float* scale, const float* shift, const void* res, void* y, long long M, int C,
                  int relu, void* stream);
 /* backward of the above.  mask_mode 0 none | 1 (ymask>0) | 2 recomputed from x.  dres (+)= masked dy. */
+/* channels per thread of the BN streaming kernels: 0 auto (4 when C <= 1024), 4 or 8 forced (A/B measurements) */
+int evb_set_bn_vec(int v);
+/* BN backward kernels: 2 = cp.async-staged shared-memory rings (default), 1 = register-staged loads */
+int evb_set_bn_variant(int v);
+/* grid cap of the BN backward reduction, blocks per SM (1..4, default 4) */
+int evb_set_bn_reduce_blocks(int per_sm);
 int evb_bn_bwd(const void* dy, const void* x, const void* ymask, const float* mean, const float* rstd, const float* scale,
                const float* shift, int mask_mode, int frozen, void* dx, void* dres, int dres_acc, float* dgamma,
                float* dbeta, int param_acc, long long M, int C, void* ws, void* stream);

@@ -11,7 +11,7 @@ sys.path.insert(0, '.')
 from ever_b200._lib import check, lib, ptr, stream  # noqa: E402
 
 c_int, c_ll, c_float = ctypes.c_int, ctypes.c_longlong, ctypes.c_float
-SHAPES = [(131072, 256), (131072, 64), (32768, 512), (32768, 128), (8192, 1024), (8192, 256), (2048, 2048), (2048, 512)]
+SHAPES = [(131072, 256), (131072, 64), (32768, 512), (32768, 128), (8192, 1024), (2048, 2048)]
 
 
 def timeit(fn, nset, iters=40, warm=5):
@@ -65,12 +65,21 @@ def main():
 
         def copy(i):
             y[i].copy_(x[i])
-        for name, fn, units in (('copy', copy, 2), ('apply', apply, 2), ('apply_res', apply_res, 3), ('stats', stats, 1),
-                                ('bwd_mask2', bwd2, 5), ('bwd_mask1_dres', bwd1, 8)):
-            us = timeit(fn, nset)
-            r[name + '_us'] = round(us, 2)
-            r[name + '_gbs'] = round(units * one / us / 1e3, 1)
-            r[name + '_frac'] = round(units * one / us / 1e3 / peak, 3)
+        for vec, bps in ((8, 2), (4, 2), (0, 3), (0, 2)):
+            L.evb_set_bn_variant(c_int(2 if vec == 0 else 1))
+            L.evb_set_bn_vec(c_int(vec))
+            L.evb_set_bn_reduce_blocks(c_int(bps))
+            for name, fn, units in (('copy', copy, 2), ('apply', apply, 2), ('apply_res', apply_res, 3), ('stats', stats, 1),
+                                    ('bwd_mask2', bwd2, 5), ('bwd_mask1_dres', bwd1, 8)):
+                if (vec, bps) != (8, 2) and not name.startswith('bwd'):
+                    continue
+                us = timeit(fn, nset)
+                name = name + ('_v%db%d' % (vec, bps) if name.startswith('bwd') else '')
+                r[name + '_us'] = round(us, 2)
+                r[name + '_gbs'] = round(units * one / us / 1e3, 1)
+        L.evb_set_bn_vec(c_int(0))
+        L.evb_set_bn_variant(c_int(2))
+        L.evb_set_bn_reduce_blocks(c_int(4))
         rows.append(r)
         print(json.dumps(r))
         del x, dy, y, dx, res

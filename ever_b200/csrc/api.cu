@@ -48,7 +48,17 @@ extern "C" int evb_set_pdl(int on) {
   return EVB_OK;
 }
 
-extern "C" int evb_version() { return 100; }
+int g_evb_pdl_small = [] {
+  const char* e = getenv("EVB_PDL_SMALL");
+  return (e && e[0] == '0') ? 0 : 1;
+}();
+// programmatic dependent launch of the BatchNorm finalize / apply kernels (their launch overlaps the producer's tail)
+extern "C" int evb_set_pdl_small(int on) {
+  g_evb_pdl_small = on ? 1 : 0;
+  return EVB_OK;
+}
+
+extern "C" int evb_version() { return 101; }
 
 // Last CUDA error string for diagnostics (does not clear sticky errors).
 extern "C" const char* evb_last_cuda_error() { return cudaGetErrorString(cudaPeekAtLastError()); }

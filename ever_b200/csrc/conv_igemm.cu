@@ -519,7 +519,9 @@ template <int NT>
 static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const IgemmParams& p,
                          cudaStream_t st, int* nblk_out) {
   if (p.stats) {
-    if (p.bias || p.add_mode) return EVB_ERR_ARG;
+    if (p.add_mode) return EVB_ERR_ARG;
+    // with a bias the statistics are those of bf16(conv + bias): rows outside the image are masked out of the sums
+    if (p.bias) return launch_igemm2_t<NT, true, true>(tmA, tmB, tmC, p, st, nblk_out);
     return launch_igemm2_t<NT, false, true>(tmA, tmB, tmC, p, st, nblk_out);
   }
   if (p.bias || p.add_mode) return launch_igemm2_t<NT, true, false>(tmA, tmB, tmC, p, st, nullptr);
@@ -649,6 +651,15 @@ extern "C" int evb_conv2d_fwd_stats(const void* x, int N, int H, int W, int Cin,
                                     int stride, void* y, int Cout, float* partial, int* nblk_out, void* stream) {
   if (!partial || !nblk_out) return EVB_ERR_ARG;
   return conv2d_fwd_impl(x, N, H, W, Cin, wpk, w_rows, ksize, stride, y, Cout, nullptr, nullptr, 0, 0, partial, nblk_out,
+                         stream);
+}
+// same with a per-channel fp32 bias added before the bf16 rounding (conv + bias -> BN of the FS-Relation encoders,
+// ever/module/fs_relation.py:41-52): the statistics are those of the biased, rounded output
+extern "C" int evb_conv2d_fwd_bias_stats(const void* x, int N, int H, int W, int Cin, const void* wpk, int w_rows, int ksize,
+                                         int stride, void* y, int Cout, const float* bias, float* partial, int* nblk_out,
+                                         void* stream) {
+  if (!partial || !nblk_out || !bias) return EVB_ERR_ARG;
+  return conv2d_fwd_impl(x, N, H, W, Cin, wpk, w_rows, ksize, stride, y, Cout, bias, nullptr, 0, 0, partial, nblk_out,
                          stream);
 }
 

@@ -141,6 +141,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, 
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, float* __restrict__ mean, float* __restrict__ rstd,
                                    float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_wait();   // may be launched programmatically behind the conv whose epilogue wrote `partial`
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
   double s, ss;
@@ -407,6 +408,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
 __global__ void bn_bwd_finalize2_kernel(const float* __restrict__ partial, int nblk, int C, const float* __restrict__ rstd,
                                         float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
                                         float* __restrict__ fresh) {
+  pdl_wait();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
   double s, ss;
@@ -652,6 +654,7 @@ bn_bwd_apply_ca_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
   const unsigned tid = blockIdx.x * nthr + t;
   const unsigned stride = gridDim.x * nthr;
   const int c0 = (int)(tid % (unsigned)cg) * 8;
+  pdl_wait();
   float a[8], k0[8], c2[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -713,6 +716,62 @@ bn_bwd_apply_ca_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = a[j] * g[j] + k0[j] - c2[j] * xf[j];
     reinterpret_cast<bf16x8*>(dx)[i] = pack8(o);
+  }
+  cp_async_wait<0>();
+}
+
+// y = act(bf16(x*scale+shift) [+ res]) with the cp.async rings (RES: the residual tensor is streamed too)
+template <int RES>
+__global__ void __launch_bounds__(kEwThreads)
+bn_apply_ca_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                   const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, unsigned nvec, int C, int relu) {
+  constexpr int NT = RES ? 2 : 1;
+  constexpr int S = kCaStages;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  bf16x8* ring = reinterpret_cast<bf16x8*>(smraw);   // [S][NT][blockDim]
+  const int nthr = blockDim.x, t = threadIdx.x;
+  const int cg = C / 8;
+  const unsigned tid = blockIdx.x * nthr + t;
+  const unsigned stride = gridDim.x * nthr;
+  const int c0 = (int)(tid % (unsigned)cg) * 8;
+  pdl_wait();
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a[j] = scale[c0 + j]; b[j] = shift[c0 + j]; }
+  const int niter = tid < nvec ? (int)((nvec - tid + stride - 1) / stride) : 0;
+  const bf16x8* gx = reinterpret_cast<const bf16x8*>(x);
+  const bf16x8* gr = reinterpret_cast<const bf16x8*>(res);
+  auto issue = [&](int it) {
+    if (it < niter) {
+      const size_t i = (size_t)tid + (size_t)it * stride;
+      bf16x8* slot = ring + (size_t)(it % S) * NT * nthr + t;
+      cp_async16(slot, gx + i);
+      if (RES) cp_async16(slot + nthr, gr + i);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int it = 0; it < S - 1; ++it) issue(it);
+  for (int it = 0; it < niter; ++it) {
+    issue(it + S - 1);
+    cp_async_wait<S - 1>();
+    const size_t i = (size_t)tid + (size_t)it * stride;
+    const bf16x8* slot = ring + (size_t)(it % S) * NT * nthr + t;
+    float v[8];
+    unpack8(slot[0], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = v[j] * a[j] + b[j];
+    if (RES) {
+      float r[8];
+      unpack8(slot[nthr], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = bf16_round(v[j]) + r[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    reinterpret_cast<bf16x8*>(y)[i] = pack8(v);
   }
   cp_async_wait<0>();
 }
@@ -1183,15 +1242,16 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, 
 // (wf[tap][co][ci]: ci contiguous; wb[tap][ci][co]: co contiguous) are coalesced.  Padding rows/columns of the packs are
 // never written (the pack arena is zero-initialised once).
 __global__ void __launch_bounds__(256)
-pack_weights_batched_kernel(const long long* __restrict__ desc, const int* __restrict__ block_map) {
+pack_weights_batched_kernel(const long long* __restrict__ desc, const int* __restrict__ block_map, int block0) {
   __shared__ float tile[9][32][33];  // [tap][co][ci]
-  const long long* d = desc + (long long)block_map[blockIdx.x] * 12;
+  const int bid = blockIdx.x + block0;
+  const long long* d = desc + (long long)block_map[bid] * 12;
   const float* w = reinterpret_cast<const float*>(d[0]);
   __nv_bfloat16* wf = reinterpret_cast<__nv_bfloat16*>(d[1]);
   __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(d[2]);
   const int Co = (int)d[3], Ci = (int)d[4], kk = (int)d[5], CoP = (int)d[6], CiP = (int)d[7], CiPb = (int)d[8],
             CoPb = (int)d[9];
-  const int t = blockIdx.x - (int)d[10];
+  const int t = bid - (int)d[10];
   const long long w_ld = d[11] ? d[11] : (long long)Ci * kk;
   const int tiles_ci = (Ci + 31) / 32;
   const int co0 = (t / tiles_ci) * 32, ci0 = (t % tiles_ci) * 32;
@@ -1261,8 +1321,9 @@ extern "C" int evb_bn_finalize(const float* partial, int nblk, long long M, int 
                                float* running_mean, float* running_var, float momentum, float eps, float* mean, float* rstd,
                                float* scale, float* shift, void* stream) {
   if (nblk < 1 || nblk > kNbPad) return EVB_ERR_ARG;
-  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, ST>>>(partial, nblk, M, C, gamma, beta, running_mean, running_var, momentum, eps,
-                                                  mean, rstd, scale, shift);
+  if (evb_launch_pdl_small(bn_finalize_kernel, dim3((C + 7) / 8), dim3(256), 0, ST, partial, nblk, M, C, gamma, beta,
+                           running_mean, running_var, momentum, eps, mean, rstd, scale, shift) != cudaSuccess)
+    return EVB_ERR_CUDA;
   return LAUNCH_OK();
 }
 
@@ -1301,7 +1362,31 @@ extern "C" int evb_bn_apply(const void* x, const float* scale, const float* shif
                             int C, int relu, void* stream) {
   if (C % 8) return EVB_ERR_ARG;
   if (C / 8 > kEwThreads) return EVB_ERR_ARG;
-  int V = bn_vec_for(C);
+  if (g_bn_variant == 2 && M * C / 8 < (1LL << 31) - (1LL << 24)) {   // cp.async rings, 16-byte vectors
+    const long long nvec = M * C / 8;
+    const int cg_ = C / 8;
+    const int bt = (kEwThreads / cg_) * cg_;
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(bn_apply_ca_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 256 * 16) != cudaSuccess ||
+          cudaFuncSetAttribute(bn_apply_ca_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 256 * 16) != cudaSuccess)
+        return EVB_ERR_CUDA;
+      attr_set = true;
+    }
+    cudaError_t e;
+    if (res)
+      e = evb_launch_pdl_small(bn_apply_ca_kernel<1>, dim3(ew_blocks(nvec, bt * 8, 148 * 3)), dim3(bt),
+                               (size_t)kCaStages * 2 * bt * 16, ST, (const __nv_bfloat16*)x, scale, shift,
+                               (const __nv_bfloat16*)res, (__nv_bfloat16*)y, (unsigned)nvec, C, relu);
+    else
+      e = evb_launch_pdl_small(bn_apply_ca_kernel<0>, dim3(ew_blocks(nvec, bt * 8, 148 * 4)), dim3(bt),
+                               (size_t)kCaStages * bt * 16, ST, (const __nv_bfloat16*)x, scale, shift,
+                               (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)y, (unsigned)nvec, C, relu);
+    if (e != cudaSuccess) return EVB_ERR_CUDA;
+    return LAUNCH_OK();
+  }
+  int V = g_bn_vec == 4 ? 4 : 8;   // register-staged: 8 channels per thread unless forced (V = 4 measured no faster here)
+  if (V == 4 && (C % 4 || C / 4 > kEwThreads)) V = 8;
   if (M * C / 4 >= (1LL << 31) - (1LL << 24)) V = 8;   // the narrow kernels index vectors with 32 bits
   const long long nvec = M * C / V;
   const int cg_ = C / V;
@@ -1316,8 +1401,6 @@ extern "C" int evb_bn_apply(const void* x, const float* scale, const float* shif
   return LAUNCH_OK();
 }
 
-// BN (+ReLU mask) backward.  mask_mode: 0 none, 1 from ymask>0, 2 recomputed from x*scale+shift>0.
-// frozen!=0: statistics were constants (eval / frozen BN): dx = g*scale, dgamma/dbeta still produced.
 template <int MASK>
 static int launch_bn_bwd_ca(const void* dy, const void* x, const void* ymask, const float* mean, const float* rstd,
                             const float* scale, const float* shift, int frozen, void* dx, void* dres, int dres_acc,
@@ -1345,11 +1428,15 @@ static int launch_bn_bwd_ca(const void* dy, const void* x, const void* ymask, co
   bn_bwd_reduce_ca_kernel<MASK><<<(int)nb, bt, smem, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
                                                          (const __nv_bfloat16*)ymask, mean, scale, shift, M, C, (float*)ws);
   float* fresh = (float*)ws + (size_t)kNbPadBwd * 2 * C;
-  bn_bwd_finalize2_kernel<<<(C + 7) / 8, 256, 0, st>>>((const float*)ws, (int)nb, C, rstd, dgamma, dbeta, param_acc, fresh);
+  if (evb_launch_pdl_small(bn_bwd_finalize2_kernel, dim3((C + 7) / 8), dim3(256), 0, st, (const float*)ws, (int)nb, C, rstd,
+                           dgamma, dbeta, param_acc, fresh) != cudaSuccess)
+    return EVB_ERR_CUDA;
   const long long nvec = M * C / 8;
-  bn_bwd_apply_ca_kernel<MASK><<<ew_blocks(nvec, bt * 8, 148 * (NT == 3 ? 2 : 3)), bt, smem, st>>>(
-      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ymask, mean, rstd, scale, shift, fresh + C,
-      fresh, frozen, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, dres_acc, (unsigned)nvec, C, 1.0f / (float)M);
+  if (evb_launch_pdl_small(bn_bwd_apply_ca_kernel<MASK>, dim3(ew_blocks(nvec, bt * 8, 148 * (NT == 3 ? 2 : 3))), dim3(bt), smem,
+                           st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ymask, mean, rstd,
+                           scale, shift, (const float*)(fresh + C), (const float*)fresh, frozen, (__nv_bfloat16*)dx,
+                           (__nv_bfloat16*)dres, dres_acc, (unsigned)nvec, C, 1.0f / (float)M) != cudaSuccess)
+    return EVB_ERR_CUDA;
   return EVB_OK;
 }
 
@@ -1532,7 +1619,14 @@ extern "C" int evb_pack_weight(const float* w, int Co, int Ci, int kk, void* wf,
 }
 
 extern "C" int evb_pack_weights_batched(const void* desc, const void* block_map, int nblocks, void* stream) {
-  pack_weights_batched_kernel<<<nblocks, 256, 0, ST>>>((const long long*)desc, (const int*)block_map);
+  pack_weights_batched_kernel<<<nblocks, 256, 0, ST>>>((const long long*)desc, (const int*)block_map, 0);
+  return LAUNCH_OK();
+}
+// blocks [block0, block0 + nblocks) of the same table: lets the caller pack the first layers' weights on the main stream
+// and the rest on a second stream that overlaps the start of the forward pass
+extern "C" int evb_pack_weights_range(const void* desc, const void* block_map, int block0, int nblocks, void* stream) {
+  if (nblocks <= 0) return EVB_OK;
+  pack_weights_batched_kernel<<<nblocks, 256, 0, ST>>>((const long long*)desc, (const int*)block_map, block0);
   return LAUNCH_OK();
 }
 

@@ -288,10 +288,14 @@ loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restric
     float mx = z[0];
 #pragma unroll
     for (int c = 1; c < K; ++c) mx = fmaxf(mx, z[c]);
+    // one exponential per class: e_c = exp(z_c - max) (arguments <= 0: the ex2.approx intrinsic is within ~1e-6 relative),
+    // softmax p_c = e_c / sum e; the kernel is instruction-bound, a second exp(z_c - lse) per class cost 40 % of it
+    float e[KA];
     float se = 0.f;
 #pragma unroll
-    for (int c = 0; c < K; ++c) se += expf(z[c] - mx);
+    for (int c = 0; c < K; ++c) { e[c] = __expf(z[c] - mx); se += e[c]; }
     const float lse = mx + logf(se);
+    const float inv_se = 1.f / se;
     if (PASS == 0) {
       if (valid) {
         float zt = 0.f;
@@ -301,7 +305,7 @@ loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restric
         acc[1] += 1.f;
 #pragma unroll
         for (int c = 0; c < K; ++c) {
-          const float pc = expf(z[c] - lse);
+          const float pc = e[c] * inv_se;
           acc[2 + K + c] += pc;
           if (c == (int)t) { acc[2 + c] += pc; acc[2 + 2 * K + c] += 1.f; }
         }
@@ -313,7 +317,7 @@ loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restric
         float pc[KA], dot = 0.f;
 #pragma unroll
         for (int c = 0; c < K; ++c) {
-          pc[c] = expf(z[c] - lse);
+          pc[c] = e[c] * inv_se;
           const float gc = coef[1 + K + c] - (c == (int)t ? coef[1 + c] : 0.f);  // B_c - y_c * A_c
           dot += pc[c] * gc;
         }
@@ -409,12 +413,16 @@ loss_binary_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __
 }
 
 // stats[i] = sum_blocks partial (double accumulation, fixed order)
+// one warp per statistic: lanes stride over the block partials, fp64, fixed shuffle tree -> deterministic
 __global__ void loss_reduce_kernel(const float* __restrict__ partial, int nblk, int n, float* __restrict__ stats) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= n) return;
+  const int lane = threadIdx.x & 31;
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += partial[(long long)b * n + i];
-  stats[i] = (float)s;
+  for (int b = lane; b < nblk; b += 32) s += partial[(long long)b * n + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) stats[i] = (float)s;
 }
 
 // From (possibly all-reduced) statistics: losses[0]=ce, losses[1]=dice; coef = {ce_scale/n_valid, A_c, B_c}.
@@ -455,11 +463,19 @@ __global__ void __launch_bounds__(256) sqsum_kernel(const float* __restrict__ g,
     partial[blockIdx.x] = t;
   }
 }
+// 256 threads: strided fp64 partial sums, fixed shared-memory tree -> deterministic
 __global__ void norm_finalize_kernel(const float* partial, int nblk, float* out /*[0]=norm,[1]=clip coef*/, float max_norm) {
-  if (threadIdx.x || blockIdx.x) return;
+  __shared__ double red[256];
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += partial[b];
-  const float norm = (float)sqrt(s);
+  for (int b = threadIdx.x; b < nblk; b += 256) s += partial[b];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x) return;
+  const float norm = (float)sqrt(red[0]);
   out[0] = norm;
   float coef = max_norm > 0.f ? max_norm / (norm + 1e-6f) : 1.f;
   out[1] = coef < 1.f ? coef : 1.f;
@@ -555,7 +571,7 @@ extern "C" int evb_loss_stats(const void* logits, const void* labels, long long 
   if (K == 1) {
     loss_binary_kernel<0><<<nb, 256, 0, ST>>>((const __nv_bfloat16*)logits, (const long long*)labels, P, LD, ignore_index,
                                               (float*)ws, nullptr, nullptr);
-    loss_reduce_kernel<<<1, 128, 0, ST>>>((const float*)ws, nb, n, stats);
+    loss_reduce_kernel<<<(n * 32 + 127) / 128, 128, 0, ST>>>((const float*)ws, nb, n, stats);
     return LAUNCH_OK();
   }
 #define EVB_LOSS_LAUNCH(PASS_, GRID_, ...)                                                        \
@@ -568,7 +584,7 @@ extern "C" int evb_loss_stats(const void* logits, const void* labels, long long 
   }
   EVB_LOSS_LAUNCH(0, nb, (const __nv_bfloat16*)logits, (const long long*)labels, P, K, LD, ignore_index, (float*)ws,
                   nullptr, nullptr)
-  loss_reduce_kernel<<<(n + 127) / 128, 128, 0, ST>>>((const float*)ws, nb, n, stats);
+  loss_reduce_kernel<<<(n * 32 + 127) / 128, 128, 0, ST>>>((const float*)ws, nb, n, stats);
   return LAUNCH_OK();
 }
 // Between A and B the caller may all-reduce stats[2 : 2+3K] (Dice statistics) across ranks into dice_stats.
@@ -604,7 +620,7 @@ extern "C" int evb_grad_norm(const float* g, long long n, float max_norm, float*
   if (b > 148 * 8) b = 148 * 8;
   if (b < 1) b = 1;
   sqsum_kernel<<<(int)b, 256, 0, ST>>>(g, n, (float*)ws);
-  norm_finalize_kernel<<<1, 32, 0, ST>>>((const float*)ws, (int)b, norm_out, max_norm);
+  norm_finalize_kernel<<<1, 256, 0, ST>>>((const float*)ws, (int)b, norm_out, max_norm);
   return LAUNCH_OK();
 }
 // torch.optim.SGD step over a flat arena (ever/opt/optimizer.py:7-9), lr read from device memory.

@@ -250,6 +250,12 @@ class FarSegEngine:
         self._pack_desc = torch.tensor(rows, dtype=torch.int64, device=self.dev)
         self._pack_map = torch.tensor(bmap, dtype=torch.int32, device=self.dev)
         self._pack_nblk = nblk
+        # blocks of the convolutions the forward pass needs first (stem, layer1, layer2): packed on the main stream; the
+        # rest (layer3, layer4, head: ~95 % of the parameters) is packed on the side stream while those layers run
+        first_late = self.stages[2][0]['c1'] if len(self.stages) > 2 else None
+        self._pack_split = nblk
+        if first_late is not None and self.side is not None and os.environ.get('EVB_NO_PACK_OVERLAP', '0') != '1':
+            self._pack_split = rows[self.convs.index(first_late)][10]
         self._pack_ptrs = [cp.weight.data_ptr() for cp in self.convs]
 
     def pack_weights(self):
@@ -257,8 +263,20 @@ class FarSegEngine:
         st = stream()
         if getattr(self, '_pack_desc', None) is None or self._pack_ptrs != [cp.weight.data_ptr() for cp in self.convs]:
             self._build_pack_table()
-        check(self.L.evb_pack_weights_batched(ptr(self._pack_desc), ptr(self._pack_map), c_int(self._pack_nblk), st),
-              'evb_pack_weights_batched')
+        self._pack_ev = None
+        if self._pack_split < self._pack_nblk:
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(ev)
+                check(self.L.evb_pack_weights_range(ptr(self._pack_desc), ptr(self._pack_map), c_int(self._pack_split),
+                                                    c_int(self._pack_nblk - self._pack_split), stream()),
+                      'evb_pack_weights_range')
+                self._pack_ev = torch.cuda.Event()
+                self._pack_ev.record(self.side)
+        check(self.L.evb_pack_weights_range(ptr(self._pack_desc), ptr(self._pack_map), c_int(0), c_int(self._pack_split), st),
+              'evb_pack_weights_range')
         for cp in self.convs:
             cp._gw = False
             if cp.bias_pad is not None:
@@ -305,6 +323,11 @@ class FarSegEngine:
             self.side.wait_event(ev)
             fn()
         self._side_used = True
+
+    def _join_pack(self):
+        if getattr(self, '_pack_ev', None) is not None:
+            torch.cuda.current_stream().wait_event(self._pack_ev)
+            self._pack_ev = None
 
     def _join_side(self):
         if self.side is not None and self._side_used:
@@ -363,9 +386,14 @@ class FarSegEngine:
             check(L.evb_bias_grad(ptr(dy), c_ll(m_rows), c_int(cout), ptr(cp.bias.grad), None, c_int(1 if acc else 0), ptr(ws),
                                   st), 'evb_bias_grad')
 
-    def conv(self, x, cp, stride=None, bias=False, add=None, add_mode=0, train=True, dgrad=True, stats=False):
+    def conv(self, x, cp, stride=None, bias=False, add=None, add_mode=0, train=True, dgrad=True, stats=False,
+             bias_grad_zero=False):
         """y = conv(x) (+bias) (+add).  bias=True uses cp.bias (padded copy when the conv is channel-padded).
-        stats=True (training, no bias/add): the epilogue also emits the BN batch-statistic partial sums of y."""
+        stats=True (training, no add): the epilogue also emits the BN batch-statistic partial sums of y.
+        bias_grad_zero: the conv feeds a training-mode BatchNorm directly, so d(loss)/d(bias) = sum_rows dx_BN is
+        identically zero (dx = a*g + k0 - c2*x sums to a*sum(g) + M*k0 - c2*M*mean = 0 by the definition of k0): the
+        gradient is written as exact zeros instead of summing rounding noise over the rows (the reference's value there is
+        ~1e-8 of the other gradients)."""
         L = self.L
         stride = cp.stride if stride is None else stride
         n, h, w, cin = x.data.shape
@@ -373,12 +401,18 @@ class FarSegEngine:
         cout = cp.cop
         bias_t = (cp.bias_pad if cp.bias_pad is not None else cp.bias) if bias else None
         y = Act(self._new(n, ho, wo, cout))
-        if stats and self.fuse_bn_stats and bias_t is None and add is None:
+        if stats and self.fuse_bn_stats and add is None:
             partial = self._new(2 * cout * 320, dtype=torch.float32)
             nblk = ctypes.c_int(0)
-            check(L.evb_conv2d_fwd_stats(ptr(x.data), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(cp.wf), c_int(cp.cop),
-                                         c_int(cp.k), c_int(stride), ptr(y.data), c_int(cout), ptr(partial),
-                                         ctypes.byref(nblk), stream()), 'evb_conv2d_fwd_stats')
+            if bias_t is None:
+                check(L.evb_conv2d_fwd_stats(ptr(x.data), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(cp.wf),
+                                             c_int(cp.cop), c_int(cp.k), c_int(stride), ptr(y.data), c_int(cout),
+                                             ptr(partial), ctypes.byref(nblk), stream()), 'evb_conv2d_fwd_stats')
+            else:
+                check(L.evb_conv2d_fwd_bias_stats(ptr(x.data), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(cp.wf),
+                                                  c_int(cp.cop), c_int(cp.k), c_int(stride), ptr(y.data), c_int(cout),
+                                                  ptr(bias_t), ptr(partial), ctypes.byref(nblk), stream()),
+                      'evb_conv2d_fwd_bias_stats')
             y.stats = (partial, nblk.value)
         else:
             check(L.evb_conv2d_fwd(ptr(x.data), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(cp.wf), c_int(cp.cop),
@@ -393,7 +427,10 @@ class FarSegEngine:
                 st = stream()
                 def param_grads():
                     self._wgrad(cp, x.data, dy, n, h, w, cin, cout, stride)
-                    if bias:
+                    if bias and bias_grad_zero and cp.bias.grad is not None:
+                        if not (self.accumulate or cp._gw):
+                            cp.bias.grad.zero_()
+                    elif bias:
                         self._bias_grad(cp, dy, n * ho * wo, cout)
                     cp._gw = True
                 self._param_grads_async((x.data, dy), param_grads)
@@ -592,6 +629,8 @@ class FarSegEngine:
         feats = []
         freeze_at = int(self.m.config.encoder.freeze_at)
         for si, blocks in enumerate(self.stages):
+            if si == 2:
+                self._join_pack()      # layer3 onwards reads the packs written on the side stream
             if train and freeze_at >= si + 1:
                 y.needs_grad = False   # everything that produced y is frozen: no gradient flows further down
             for d in blocks:
@@ -600,6 +639,7 @@ class FarSegEngine:
                 y.needs_grad = False   # this stage and everything below it are frozen
             feats.append(y)
             self._dbg('c%d' % (si + 2), y)
+        self._join_pack()
         return feats
 
     def _scene_mlp(self, scene, n, train):
@@ -647,8 +687,9 @@ class FarSegEngine:
         p = self.conv(inner_i, self.fpn_layer[i], train=train)
         self._dbg('p%d' % (i + 2), p)
         (cc, cb), (rc, rb) = self.content[i], self.reenc[i]
-        u1 = self.conv(p, cc, bias=True, train=train)
-        u2 = self.conv(p, rc, bias=True, train=train)
+        # conv + bias -> training-mode BN: statistics from the conv epilogue, bias gradient identically zero
+        u1 = self.conv(p, cc, bias=True, train=train, stats=train, bias_grad_zero=train and cb.bn.training)
+        u2 = self.conv(p, rc, bias=True, train=train, stats=train, bias_grad_zero=train and rb.bn.training)
         f1 = self._bn_fold(u1, cb, train)
         f2 = self._bn_fold(u2, rb, train)
         nn_, hh, ww, c = u1.data.shape

@@ -28,6 +28,8 @@ int evb_device_sync_check(void);
 /* programmatic dependent launch of the tensor-core kernels (their prologue overlaps the predecessor's tail); default on,
  * EVB_PDL=0 in the environment or evb_set_pdl(0) turns it off */
 int evb_set_pdl(int on);
+/* same for the BatchNorm finalize / apply kernels behind them; default on, EVB_PDL_SMALL=0 or evb_set_pdl_small(0) = off */
+int evb_set_pdl_small(int on);
 
 /* ---- convolution (tcgen05 implicit GEMM).  Replaces nn.Conv2d forward/backward:
  * ever/module/_resnets.py:21-29,139-150 (ResNet 3x3/1x1/stem), ever/module/ops.py:53-55 (ConvBlock),
@@ -42,6 +44,9 @@ int evb_conv2d_fwd(const void* x, int N, int H, int W, int Cin, const void* wpk,
  * to evb_bn_finalize (replaces the evb_bn_stats read pass; conv + BN of ever/module/_resnets.py:92-112, fpn.py:165-166). */
 int evb_conv2d_fwd_stats(const void* x, int N, int H, int W, int Cin, const void* wpk, int w_rows, int ksize, int stride,
                          void* y, int Cout, float* partial, int* nblk_out, void* stream);
+/* same, with a per-channel fp32 bias added before the bf16 rounding (conv+bias -> BN, ever/module/fs_relation.py:41-52) */
+int evb_conv2d_fwd_bias_stats(const void* x, int N, int H, int W, int Cin, const void* wpk, int w_rows, int ksize, int stride,
+                              void* y, int Cout, const float* bias, float* partial, int* nblk_out, void* stream);
 /* kernel variant for evb_conv2d_fwd/dgrad: 2 = persistent, TMEM double-buffered, TMA-store epilogue (default);
  * 1 = one tile per CTA with direct global stores (kept for A/B measurements). */
 int evb_set_igemm_variant(int v);
@@ -66,6 +71,8 @@ int evb_pack_weight(const float* w, int Co, int Ci, int kk, void* wf, int CoP, i
                     void* stream);
 /* every convolution of a model in one launch; desc: int64[n][12], block_map: int32[nblocks] (see elementwise.cu) */
 int evb_pack_weights_batched(const void* desc, const void* block_map, int nblocks, void* stream);
+/* blocks [block0, block0 + nblocks) of the same table (first layers on the main stream, the rest on a second stream) */
+int evb_pack_weights_range(const void* desc, const void* block_map, int block0, int nblocks, void* stream);
 /* 7x7 stride-2 pad-3 stem lowered to a GEMM: x NCHW fp32 -> A[N*H/2*W/2][KP] bf16, k = c*49 + r*7 + s
  * (ResNet.stem_forward, ever/module/_resnets.py:205-212). */
 int evb_stem_im2col(const float* x, void* a, int N, int Cin, int H, int W, int KP, void* stream);

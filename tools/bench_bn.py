@@ -71,10 +71,12 @@ def main():
             L.evb_set_bn_reduce_blocks(c_int(bps))
             for name, fn, units in (('copy', copy, 2), ('apply', apply, 2), ('apply_res', apply_res, 3), ('stats', stats, 1),
                                     ('bwd_mask2', bwd2, 5), ('bwd_mask1_dres', bwd1, 8)):
-                if (vec, bps) != (8, 2) and not name.startswith('bwd'):
+                if name in ('copy', 'stats') and (vec, bps) != (8, 2):
+                    continue
+                if bps == 2 and vec == 0:
                     continue
                 us = timeit(fn, nset)
-                name = name + ('_v%db%d' % (vec, bps) if name.startswith('bwd') else '')
+                name = name + ('_v%db%d' % (vec, bps) if name not in ('copy', 'stats') else '')
                 r[name + '_us'] = round(us, 2)
                 r[name + '_gbs'] = round(units * one / us / 1e3, 1)
         L.evb_set_bn_vec(c_int(0))

@@ -1133,13 +1133,16 @@ __global__ void gap_bwd_kernel(const float* __restrict__ dscene, __nv_bfloat16* 
 }
 
 // ------------------------------------------------------------------------------------------------ stem im2col
-// x: NCHW fp32 [N,Cin,H,W] -> A: [N*Ho*Wo][KP] bf16, k = c*49 + r*7 + s (7x7, stride 2, pad 3), zero padded to KP.
+// x: NCHW fp32 [N,Cin,H,W] -> A: [N*Ho*Wo][KP] bf16, k = c*ks*ks + r*ks + s (ks x ks window, given stride / pad), zero
+// padded to KP.  (7,2,3) = the 7x7 stem; (3,2,1) = the first conv of the deep (v1c) stem.
 __global__ void __launch_bounds__(kEwThreads)
-stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int N, int Cin, int H, int W, int KP) {
-  const int Ho = H / 2, Wo = W / 2;
+stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int N, int Cin, int H, int W, int KP, int ks,
+                   int stride, int pad) {
+  const int Ho = H / stride, Wo = W / stride;
   const int kg = KP / 8;
   const unsigned total = (unsigned) (long long)N * Ho * Wo * kg;
-  const int K = Cin * 49;
+  const int kk = ks * ks;
+  const int K = Cin * kk;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int g = (int)(i % kg);
     unsigned p = i / kg;
@@ -1152,8 +1155,8 @@ stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, i
       const int k = g * 8 + j;
       float val = 0.f;
       if (k < K) {
-        const int c = k / 49, rs = k % 49, r = rs / 7, s = rs % 7;
-        const int h = 2 * ho - 3 + r, w = 2 * wo - 3 + s;
+        const int c = k / kk, rs = k % kk, r = rs / ks, s = rs % ks;
+        const int h = stride * ho - pad + r, w = stride * wo - pad + s;
         if (h >= 0 && h < H && w >= 0 && w < W) val = x[(((long long)n * Cin + c) * H + h) * W + w];
       }
       v[j] = val;
@@ -1166,11 +1169,12 @@ stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, i
 // value = (u8 - mean[c]) / std[c]  (th_mean_std_normalize, ever/preprocess/function.py:9-32), then bf16.
 __global__ void __launch_bounds__(kEwThreads)
 stem_im2col_u8_kernel(const uint8_t* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ stdv,
-                      __nv_bfloat16* __restrict__ a, int N, int Cin, int H, int W, int KP) {
-  const int Ho = H / 2, Wo = W / 2;
+                      __nv_bfloat16* __restrict__ a, int N, int Cin, int H, int W, int KP, int ks, int stride, int pad) {
+  const int Ho = H / stride, Wo = W / stride;
   const int kg = KP / 8;
   const unsigned total = (unsigned)N * Ho * Wo * kg;
-  const int K = Cin * 49;
+  const int kk = ks * ks;
+  const int K = Cin * kk;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int g = (int)(i % kg);
     unsigned p = i / kg;
@@ -1183,8 +1187,8 @@ stem_im2col_u8_kernel(const uint8_t* __restrict__ x, const float* __restrict__ m
       const int k = g * 8 + j;
       float val = 0.f;
       if (k < K) {
-        const int c = k / 49, rs = k % 49, r = rs / 7, s_ = rs % 7;
-        const int h = 2 * ho - 3 + r, w = 2 * wo - 3 + s_;
+        const int c = k / kk, rs = k % kk, r = rs / ks, s_ = rs % ks;
+        const int h = stride * ho - pad + r, w = stride * wo - pad + s_;
         if (h >= 0 && h < H && w >= 0 && w < W)
           val = ((float)x[(((long long)n * H + h) * W + w) * Cin + c] - mean[c]) / stdv[c];
       }
@@ -1584,22 +1588,37 @@ extern "C" int evb_gap_bwd(const float* dscene, void* dx, int N, int HW, int C, 
   return LAUNCH_OK();
 }
 
-extern "C" int evb_stem_im2col(const float* x, void* a, int N, int Cin, int H, int W, int KP, void* stream) {
-  if (KP % 8 || KP < Cin * 49 || (H & 1) || (W & 1)) return EVB_ERR_ARG;
-  const long long total = (long long)N * (H / 2) * (W / 2) * (KP / 8);
-  stem_im2col_kernel<<<ew_blocks(total, kEwThreads), kEwThreads, 0, ST>>>(x, (__nv_bfloat16*)a, N, Cin, H, W, KP);
+static int im2col_check(int N, int Cin, int H, int W, int KP, int ks, int stride, int pad) {
+  if (KP % 8 || ks < 1 || ks > 7 || stride < 1 || stride > 2 || pad < 0 || pad > 3 || KP < Cin * ks * ks) return EVB_ERR_ARG;
+  if (H % stride || W % stride) return EVB_ERR_ARG;
+  if ((long long)N * (H / stride) * (W / stride) * (KP / 8) >= (1LL << 32)) return EVB_ERR_ARG;
+  return EVB_OK;
+}
+// general window: A[N*(H/stride)*(W/stride)][KP] from NCHW fp32 (ks x ks, stride 1|2, pad)
+extern "C" int evb_im2col_nchw(const float* x, void* a, int N, int Cin, int H, int W, int KP, int ks, int stride, int pad,
+                               void* stream) {
+  if (im2col_check(N, Cin, H, W, KP, ks, stride, pad)) return EVB_ERR_ARG;
+  const long long total = (long long)N * (H / stride) * (W / stride) * (KP / 8);
+  stem_im2col_kernel<<<ew_blocks(total, kEwThreads), kEwThreads, 0, ST>>>(x, (__nv_bfloat16*)a, N, Cin, H, W, KP, ks, stride,
+                                                                       pad);
   return LAUNCH_OK();
 }
-
+extern "C" int evb_im2col_u8(const void* x, const float* mean, const float* stdv, void* a, int N, int Cin, int H, int W,
+                             int KP, int ks, int stride, int pad, void* stream) {
+  if (im2col_check(N, Cin, H, W, KP, ks, stride, pad)) return EVB_ERR_ARG;
+  const long long total = (long long)N * (H / stride) * (W / stride) * (KP / 8);
+  stem_im2col_u8_kernel<<<ew_blocks(total, kEwThreads), kEwThreads, 0, ST>>>((const uint8_t*)x, mean, stdv, (__nv_bfloat16*)a,
+                                                                          N, Cin, H, W, KP, ks, stride, pad);
+  return LAUNCH_OK();
+}
+// the 7x7 stride-2 pad-3 stem (ever/module/_resnets.py:149-150)
+extern "C" int evb_stem_im2col(const float* x, void* a, int N, int Cin, int H, int W, int KP, void* stream) {
+  return evb_im2col_nchw(x, a, N, Cin, H, W, KP, 7, 2, 3, stream);
+}
 extern "C" int evb_stem_im2col_u8(const void* x, const float* mean, const float* stdv, void* a, int N, int Cin, int H, int W,
                                   int KP, void* stream) {
-  if (KP % 8 || KP < Cin * 49 || (H & 1) || (W & 1)) return EVB_ERR_ARG;
-  const long long total = (long long)N * (H / 2) * (W / 2) * (KP / 8);
-  stem_im2col_u8_kernel<<<ew_blocks(total, kEwThreads), kEwThreads, 0, ST>>>((const uint8_t*)x, mean, stdv, (__nv_bfloat16*)a, N,
-                                                                           Cin, H, W, KP);
-  return LAUNCH_OK();
+  return evb_im2col_u8(x, mean, stdv, a, N, Cin, H, W, KP, 7, 2, 3, stream);
 }
-
 extern "C" int evb_confusion_matrix(const void* pred, const void* labels, long long P, int K, void* cm, void* stream) {
   if (K < 1 || K > 64) return EVB_ERR_ARG;
   long long b = (P + 256 * 16 - 1) / (256 * 16);

@@ -177,10 +177,26 @@ class FarSegEngine:
             cp = ConvP.from_conv(conv, **kw)
             self.convs.append(cp)
             return cp
-        self.stem_kp = _ceil(r.conv1.in_channels * 49, 64)
-        self.stem = C(r.conv1, as_matrix=True)   # [64][Cin*49] GEMM; Cin*49 padded to stem_kp
+        self.deep_stem = bool(getattr(r, 'deep_stem', False))
+        if self.deep_stem:
+            # v1c stem (_resnets.py:137-147): 3x3 s2 (Cin->32) as a GEMM over im2col rows, then 3x3 32->32 and 3x3 32->64
+            # on the tensor-core kernel with the 32-channel tensors zero-padded to its 64-channel granularity
+            st = r.stem
+            self.stem_window = (3, 2, 1)
+            self.stem_kp = _ceil(st[0].in_channels * 9, 64)
+            self.stem = C(st[0], as_matrix=True, cout_pad=64)
+            self.stem_bn = BNP_(st[1], cpad=64)
+            c2 = ConvP(st[3].weight, None, 1, cout_pad=64, cin_pad=64)
+            c3 = ConvP(st[6].weight, None, 1, cin_pad=64)
+            self.convs += [c2, c3]
+            self.stem_tail = [(c2, BNP_(st[4], cpad=64)), (c3, BNP_(st[7]))]
+        else:
+            self.stem_window = (7, 2, 3)
+            self.stem_kp = _ceil(r.conv1.in_channels * 49, 64)
+            self.stem = C(r.conv1, as_matrix=True)   # [64][Cin*49] GEMM; Cin*49 padded to stem_kp
+            self.stem_bn = BNP_(r.bn1)
+            self.stem_tail = []
         self.stem.need_dgrad = False
-        self.stem_bn = BNP_(r.bn1)
         self.stages = []
         for li in range(1, 5):
             blocks = []
@@ -597,16 +613,18 @@ class FarSegEngine:
         if h % 32 or w % 32:
             raise ValueError('FarSegB200 needs H, W divisible by 32 (FPN nearest-x2 adds, SURVEY.md section 5)')
         a = self._new(n, h // 2, w // 2, self.stem_kp)
+        ks, sstride, spad = self.stem_window
         if u8:
             if getattr(self, '_in_mean', None) is None:
                 icfg = self.m.config.input
                 self._in_mean = torch.tensor(list(icfg.mean), dtype=torch.float32, device=self.dev)
                 self._in_std = torch.tensor(list(icfg.std), dtype=torch.float32, device=self.dev)
-            check(L.evb_stem_im2col_u8(ptr(x_nchw), ptr(self._in_mean), ptr(self._in_std), ptr(a), c_int(n), c_int(cin),
-                                       c_int(h), c_int(w), c_int(self.stem_kp), stream()), 'evb_stem_im2col_u8')
+            check(L.evb_im2col_u8(ptr(x_nchw), ptr(self._in_mean), ptr(self._in_std), ptr(a), c_int(n), c_int(cin),
+                                  c_int(h), c_int(w), c_int(self.stem_kp), c_int(ks), c_int(sstride), c_int(spad), stream()),
+                  'evb_im2col_u8')
         else:
-            check(L.evb_stem_im2col(ptr(x_nchw), ptr(a), c_int(n), c_int(cin), c_int(h), c_int(w), c_int(self.stem_kp),
-                                    stream()), 'evb_stem_im2col')
+            check(L.evb_im2col_nchw(ptr(x_nchw), ptr(a), c_int(n), c_int(cin), c_int(h), c_int(w), c_int(self.stem_kp),
+                                    c_int(ks), c_int(sstride), c_int(spad), stream()), 'evb_im2col_nchw')
         xa = Act(a, needs_grad=False)
         y0 = self.conv(xa, self.stem, stride=1, train=False, stats=train)   # distinct name: the closure below keeps THIS Act
         if train:
@@ -623,6 +641,8 @@ class FarSegEngine:
         y = y0
         self._dbg('stem_conv', y)
         y = self.bn_act(y, self.stem_bn, True, train=train)
+        for cp_, bp_ in self.stem_tail:   # deep stem: two more 3x3 conv + BN + ReLU
+            y = self.bn_act(self.conv(y, cp_, train=train, stats=train), bp_, True, train=train)
         self._dbg('stem_act', y)
         y = self.maxpool(y, train=train)
         self._dbg('pool', y)
@@ -957,17 +977,22 @@ class FarSegEngine:
         return cm
 
     # ------------------------------------------------------------------ fused optimizer
+    def ensure_optimizer_state(self):
+        """momentum arena (same slots as flat_w / flat_g), device-side lr / norm scalars, norm workspace"""
+        if not hasattr(self, '_mom'):
+            n = self.flat_w.numel()
+            self._mom = torch.zeros_like(self.flat_w)
+            self._lr = torch.zeros(1, dtype=torch.float32, device=self.dev)
+            self._norm = torch.zeros(2, dtype=torch.float32, device=self.dev)
+            self._sgd_ws = torch.empty(self.L.evb_sgd_workspace(c_ll(n)) // 4 + 4, dtype=torch.float32, device=self.dev)
+            self._sgd_first = True
+
     def sgd_step(self, lr, momentum=0.9, weight_decay=1e-4, max_norm=35.0):
         """clip_grad_norm_(max_norm, 2) + torch.optim.SGD step + zero_grad over the flat arenas
         (ever/interface/module.py:83-108, ever/opt/optimizer.py:7-9) as two kernels; lr lives on the device."""
         L = self.L
         n = self.flat_w.numel()
-        if not hasattr(self, '_mom'):
-            self._mom = torch.zeros_like(self.flat_w)
-            self._lr = torch.zeros(1, dtype=torch.float32, device=self.dev)
-            self._norm = torch.zeros(2, dtype=torch.float32, device=self.dev)
-            self._sgd_ws = torch.empty(L.evb_sgd_workspace(c_ll(n)) // 4 + 4, dtype=torch.float32, device=self.dev)
-            self._sgd_first = True
+        self.ensure_optimizer_state()
         self._lr.fill_(float(lr))
         check(L.evb_grad_norm(ptr(self.flat_g), c_ll(n), c_float(max_norm if max_norm else 0.0), ptr(self._norm),
                               ptr(self._sgd_ws), stream()), 'evb_grad_norm')

@@ -19,6 +19,9 @@ RESNETS = {  # block kind, blocks per stage  (ever/module/_resnets.py:241-278)
     'resnet34': ('basic', (3, 4, 6, 3)),
     'resnet50': ('bottleneck', (3, 4, 6, 3)),
     'resnet101': ('bottleneck', (3, 4, 23, 3)),
+    # deep-stem variants: three 3x3 convs instead of the 7x7 (_resnets.py:137-147, 327-345)
+    'resnet50_v1c': ('bottleneck', (3, 4, 6, 3)),
+    'resnet101_v1c': ('bottleneck', (3, 4, 23, 3)),
 }
 
 
@@ -49,8 +52,14 @@ class _ResNetParams(nn.Module):
         kind, counts = RESNETS[resnet_type]
         exp = 1 if kind == 'basic' else 4
         self.kind = kind
-        self.conv1 = nn.Conv2d(in_channels, 64, 7, 2, 3, bias=False)
-        self.bn1 = nn.BatchNorm2d(64)
+        self.deep_stem = resnet_type.endswith('_v1c')
+        if self.deep_stem:   # keys stem.0 / .1 / .3 / .4 / .6 / .7 (the ReLUs hold no parameters)
+            self.stem = nn.Sequential(nn.Conv2d(in_channels, 32, 3, 2, 1, bias=False), nn.BatchNorm2d(32), nn.ReLU(True),
+                                      nn.Conv2d(32, 32, 3, 1, 1, bias=False), nn.BatchNorm2d(32), nn.ReLU(True),
+                                      nn.Conv2d(32, 64, 3, 1, 1, bias=False), nn.BatchNorm2d(64), nn.ReLU(True))
+        else:
+            self.conv1 = nn.Conv2d(in_channels, 64, 7, 2, 3, bias=False)
+            self.bn1 = nn.BatchNorm2d(64)
         cin = 64
         for li, (planes, n) in enumerate(zip((64, 128, 256, 512), counts), 1):
             blocks = []
@@ -169,7 +178,11 @@ class FarSegB200(ERModule):
                     for p in m.parameters():
                         p.requires_grad = False
                     m.eval()
-        groups = [[r.conv1, r.bn1], [r.layer1], [r.layer2], [r.layer3], [r.layer4]]
+        if int(enc.freeze_at) >= 1 and r.deep_stem:
+            # the reference's _freeze_at touches resnet.conv1 / bn1, which a deep-stem ResNet does not have (resnet.py:162-165)
+            raise AttributeError("ResNetEncoder(freeze_at >= 1) with a deep-stem (v1c) ResNet: 'ResNet' object has no "
+                                 "attribute 'conv1' (same failure as the reference, ever/module/resnet.py:164)")
+        groups = [[] if r.deep_stem else [r.conv1, r.bn1], [r.layer1], [r.layer2], [r.layer3], [r.layer4]]
         for i, g in enumerate(groups, 1):
             if int(enc.freeze_at) >= i:
                 for m in g:

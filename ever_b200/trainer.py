@@ -17,6 +17,8 @@ import time
 
 import torch
 
+from . import checkpoint as ckpt
+
 
 class _LRHolder:
     """optimizer stand-in for reference LearningRate objects (they only touch param_groups[*]['lr'])"""
@@ -76,3 +78,34 @@ class StepLoop:
                     self.log_fn(self.global_step, last, self.lr, time.time() - t0)
         self.lr_used = lr_used
         return last
+
+    # ------------------------------------------------------------------ checkpoints in the reference's format
+    def save_checkpoint(self, model_dir, filename=None):
+        """CheckPoint.save (ever/core/checkpoint.py:51-73): model state_dict, global step and the optimizer state in
+        torch.optim.SGD's own layout (the flat momentum arena is split back into per-parameter momentum buffers), so the
+        reference Launcher can resume from it."""
+        if self.rank != 0:
+            return None
+        eng = self.model._engine()
+        params = list(self.model.parameters())
+        mom = getattr(eng, '_mom', None)
+        opt_state = ckpt.sgd_state_from_flat(params, mom, self.lr, self.momentum, self.weight_decay,
+                                             has_momentum=mom is not None and not getattr(eng, '_sgd_first', True))
+        state = {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()}
+        return ckpt.write_checkpoint(model_dir, state, opt_state, self.global_step, filename)
+
+    def try_resume(self, model_dir):
+        """CheckPoint.try_resume (checkpoint.py:79-107): load the checkpoint named under 'last' in checkpoint_info.json --
+        written by this class or by the reference Launcher with torch.optim.SGD -- into the model, the momentum arena and
+        the step counter.  Returns True if a checkpoint was loaded."""
+        c = ckpt.read_last_checkpoint(model_dir)
+        if c is None:
+            return False
+        self.model.load_state_dict(c[ckpt.MODEL])
+        eng = self.model._engine()
+        eng.ensure_optimizer_state()
+        has, group = ckpt.flat_from_sgd_state(list(self.model.parameters()), c[ckpt.OPTIMIZER], eng._mom)
+        eng._sgd_first = not has
+        self.global_step = int(c[ckpt.GLOBALSTEP])
+        self._holder.param_groups[0]['lr'] = float(group['lr'])
+        return True

@@ -80,6 +80,11 @@ int evb_stem_im2col(const float* x, void* a, int N, int Cin, int H, int W, int K
  * ever/preprocess/function.py:9-32): the caller-side input pipeline, 4x fewer H2D bytes */
 int evb_stem_im2col_u8(const void* x, const float* mean, const float* stdv, void* a, int N, int Cin, int H, int W, int KP,
                        void* stream);
+/* general ks x ks window (stride 1|2, pad): the first 3x3 stride-2 conv of the deep "v1c" stem (ever/module/_resnets.py:137-147)
+ * uses (3, 2, 1); evb_stem_im2col[_u8] = (7, 2, 3) */
+int evb_im2col_nchw(const float* x, void* a, int N, int Cin, int H, int W, int KP, int ks, int stride, int pad, void* stream);
+int evb_im2col_u8(const void* x, const float* mean, const float* stdv, void* a, int N, int Cin, int H, int W, int KP, int ks,
+                  int stride, int pad, void* stream);
 /* eval: cm[t*K + p] (int64) += pixels with label t predicted p; labels outside [0,K) skipped
  * (ConfusionMatrix.forward, ever/metric/confusion_matrix.py:11-25) */
 int evb_confusion_matrix(const void* pred, const void* labels, long long P, int K, void* cm, void* stream);

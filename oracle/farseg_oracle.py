@@ -81,6 +81,8 @@ RESNET_SPECS = {
     'resnet34': (_Basic, (3, 4, 6, 3)),
     'resnet50': (_Bottle, (3, 4, 6, 3)),
     'resnet101': (_Bottle, (3, 4, 23, 3)),
+    'resnet50_v1c': (_Bottle, (3, 4, 6, 3)),    # deep stem, reference ever/module/_resnets.py:327-345
+    'resnet101_v1c': (_Bottle, (3, 4, 23, 3)),
 }
 
 
@@ -91,9 +93,16 @@ class _ResNetTrunk(nn.Module):
     def __init__(self, kind, in_channels=3):
         super().__init__()
         block, counts = RESNET_SPECS[kind]
-        self.conv1 = nn.Conv2d(in_channels, 64, 7, 2, 3, bias=False)
-        self.bn1 = nn.BatchNorm2d(64)
-        self.relu = nn.ReLU(inplace=True)
+        self.deep_stem = kind.endswith('_v1c')
+        if self.deep_stem:   # three 3x3 convs, reference ever/module/_resnets.py:137-147
+            self.stem = nn.Sequential(
+                nn.Conv2d(in_channels, 32, 3, 2, 1, bias=False), nn.BatchNorm2d(32), nn.ReLU(inplace=True),
+                nn.Conv2d(32, 32, 3, 1, 1, bias=False), nn.BatchNorm2d(32), nn.ReLU(inplace=True),
+                nn.Conv2d(32, 64, 3, 1, 1, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True))
+        else:
+            self.conv1 = nn.Conv2d(in_channels, 64, 7, 2, 3, bias=False)
+            self.bn1 = nn.BatchNorm2d(64)
+            self.relu = nn.ReLU(inplace=True)
         self.maxpool = nn.MaxPool2d(3, 2, 1)
         cin = 64
         for li, (planes, n) in enumerate(zip((64, 128, 256, 512), counts), 1):
@@ -138,7 +147,7 @@ class ResNetEncoderOracle(nn.Module):
                     for p in m.parameters():
                         p.requires_grad = False
                     m.eval()
-        groups = [[r.conv1, r.bn1], [r.layer1], [r.layer2], [r.layer3], [r.layer4]]
+        groups = [[] if r.deep_stem else [r.conv1, r.bn1], [r.layer1], [r.layer2], [r.layer3], [r.layer4]]
         for i, g in enumerate(groups, 1):
             if self.freeze_at >= i:
                 for m in g:
@@ -152,7 +161,8 @@ class ResNetEncoderOracle(nn.Module):
 
     def forward(self, x):
         r = self.resnet
-        x = r.maxpool(r.relu(r.bn1(r.conv1(x))))
+        x = r.stem(x) if r.deep_stem else r.relu(r.bn1(r.conv1(x)))   # stem_forward, _resnets.py:205-212
+        x = r.maxpool(x)
         c2 = r.layer1(x)
         c3 = r.layer2(c2)
         c4 = r.layer3(c3)

@@ -28,6 +28,8 @@ CASES = {
     'r50_k15_1x64': ('resnet50', 15, 1, 64, 64, 256),
     'r18_k1_2x64': ('resnet18', 1, 2, 64, 64, 128),
     # ResNetEncoder(in_channels=8) (resnet.py:100-117: fresh 7x7 conv) + FSRelation(scale_aware_proj=False) (fs_relation.py:29-35)
+    # deep-stem ResNet (three 3x3 convs, _resnets.py:137-147)
+    'r50v1c_k5_1x64': ('resnet50_v1c', 5, 1, 64, 64, 128),
     'r18_k5_c8_shared_2x64': ('resnet18', 5, 2, 64, 64, 128, dict(in_channels=8, scale_aware_proj=False)),
 }
 
@@ -76,7 +78,8 @@ def run_case(name):
     sum(losses.values()).backward()
     gsum = {kk: float(p.grad.double().sum()) for kk, p in m.named_parameters()}
     gnorm = {kk: float(p.grad.double().norm()) for kk, p in m.named_parameters()}
-    bn_after = {kk: v.clone() for kk, v in m.state_dict().items() if 'running' in kk and ('bn1.' in kk and 'layer' not in kk)}
+    bn_after = {kk: v.clone() for kk, v in m.state_dict().items()
+                if 'running' in kk and (('bn1.' in kk or 'stem.' in kk) and 'layer' not in kk)}
     m.eval()
     with torch.no_grad():
         prob = m(x)

@@ -37,7 +37,7 @@ def _oracle_step(ora, x, y, autocast):
     feats = {}
     hooks = []
     r_, hd = ora.en.resnet, ora.head
-    points = [('stem_conv', r_.conv1), ('pool', r_.maxpool), ('c2', r_.layer1), ('c3', r_.layer2), ('c4', r_.layer3),
+    points = [('stem_conv', r_.stem[0] if r_.deep_stem else r_.conv1), ('pool', r_.maxpool), ('c2', r_.layer1), ('c3', r_.layer2), ('c4', r_.layer3),
               ('c5', r_.layer4), ('p2', hd.fpn.fpn_layer1), ('p3', hd.fpn.fpn_layer2), ('p4', hd.fpn.fpn_layer3),
               ('p5', hd.fpn.fpn_layer4), ('merged', hd.fpn_decoder.dropout), ('cls', hd.fpn_decoder.classifier[0])]
     points += [('dec%d' % i, hd.fpn_decoder.blocks[i]) for i in range(4)]
@@ -63,7 +63,9 @@ CASES = [('resnet18', 5, 128, 2, 128, 128), ('resnet50', 15, 256, 2, 128, 128), 
          # same options as the real-reference fixture tests/golden/r18_k5_c8_shared_2x64.pt
          ('resnet18', 5, 128, 2, 128, 128, dict(in_channels=8, scale_aware_proj=False)),
          # hyperspectral-style high-channel stem (BASELINE configs[4] shape class): 200 input channels, ragged tile
-         ('resnet18', 5, 128, 1, 96, 160, dict(in_channels=200))]
+         ('resnet18', 5, 128, 1, 96, 160, dict(in_channels=200)),
+         # deep-stem ResNet-50 v1c (three 3x3 convs, _resnets.py:137-147); real-reference fixture r50v1c_k5_1x64.pt
+         ('resnet50_v1c', 5, 128, 2, 128, 128)]
 
 
 @pytest.mark.parametrize('case', CASES)
@@ -388,3 +390,42 @@ def test_step_loop_trains():
     assert abs(loop.lr_used[0] - 0.02) < 1e-12 and abs(loop.lr_used[1] - 0.02) < 1e-12
     assert abs(loop.lr_used[2] - 0.02 * (1 - 1 / 20) ** 0.9) < 1e-12
     assert 'grad_norm' in last and last['grad_norm'] > 0
+
+
+def test_step_loop_checkpoint_resume_is_bit_identical(tmp_path):
+    """StepLoop.save_checkpoint / try_resume in the reference's checkpoint format (ever/core/checkpoint.py:51-117): 4 steps,
+    save, fresh model + loop resumed from the file, 3 more steps == 7 uninterrupted steps, bit for bit (parameters, BN
+    buffers and momentum); the saved optimizer state loads into a stock torch.optim.SGD."""
+    from ever_b200.trainer import StepLoop, poly_lr
+    from oracle.farseg_oracle import synthetic_batch
+    resnet, k, dec, n, h, w = 'resnet18', 5, 128, 2, 128, 128
+    x, y = synthetic_batch(n, h, w, k)
+    xs, yd = x.pin_memory(), dict(cls=y.pin_memory())
+
+    def batches():
+        while True:
+            yield xs, yd
+
+    def fresh():
+        _, m = _build(resnet, k, dec)
+        return m.cuda(), None
+    a, _ = fresh()
+    la = StepLoop(a, poly_lr(0.02, 0.9, 20), base_lr=0.02)
+    la.train_iters(batches(), 7)
+    b, _ = fresh()
+    lb = StepLoop(b, poly_lr(0.02, 0.9, 20), base_lr=0.02)
+    lb.train_iters(batches(), 4)
+    path = lb.save_checkpoint(str(tmp_path))
+    assert os.path.basename(path) == 'checkpoint-4.pth'
+    c, _ = fresh()
+    lc = StepLoop(c, poly_lr(0.02, 0.9, 20), base_lr=0.02)
+    assert lc.try_resume(str(tmp_path)) and lc.global_step == 4 and lc.lr == lb.lr
+    lc.train_iters(batches(), 7)
+    torch.cuda.synchronize()
+    sa, sc = a.state_dict(), c.state_dict()
+    assert all(torch.equal(sa[kk], sc[kk]) for kk in sa)
+    assert torch.equal(a.engine._mom, c.engine._mom)
+    ck = torch.load(path, weights_only=False)
+    opt = torch.optim.SGD(b.parameters(), lr=0.5, momentum=0.9, weight_decay=1e-4)
+    opt.load_state_dict(ck['opt'])
+    assert abs(opt.param_groups[0]['lr'] - lb.lr) < 1e-15 and len(opt.state) == len(list(b.parameters()))

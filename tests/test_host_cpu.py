@@ -45,7 +45,8 @@ def test_sass_has_tcgen05_and_tma():
 
 
 @pytest.mark.parametrize('resnet,k,dec,opts', [('resnet18', 5, 128, {}), ('resnet50', 15, 256, {}), ('resnet101', 7, 256, {}),
-                                               ('resnet18', 5, 128, dict(in_channels=8, scale_aware_proj=False))])
+                                               ('resnet18', 5, 128, dict(in_channels=8, scale_aware_proj=False)),
+                                               ('resnet50_v1c', 5, 128, {})])
 def test_state_dict_contract(resnet, k, dec, opts):
     from ever_b200.module import FarSegB200
     from oracle.farseg_oracle import FarSegOracle

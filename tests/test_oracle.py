@@ -12,7 +12,7 @@ import torch.nn.functional as F
 from oracle.farseg_oracle import (FarSegOracle, bce_loss_oracle, deterministic_fill, dice_loss_oracle,
                                   synthetic_batch)
 
-CASES = ['r18_k5_2x64', 'r50_k15_1x64', 'r18_k1_2x64', 'r18_k5_c8_shared_2x64']
+CASES = ['r18_k5_2x64', 'r50_k15_1x64', 'r18_k1_2x64', 'r18_k5_c8_shared_2x64', 'r50v1c_k5_1x64']
 
 
 def _run_oracle(case):
@@ -55,7 +55,7 @@ def test_oracle_matches_golden(name, golden_dir):
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/ever'), reason='reference tree only exists in the build container')
-@pytest.mark.parametrize('name', ['r18_k5_2x64', 'r18_k5_c8_shared_2x64'])
+@pytest.mark.parametrize('name', ['r18_k5_2x64', 'r18_k5_c8_shared_2x64', 'r50v1c_k5_1x64'])
 def test_oracle_bit_exact_vs_reference(name, golden_dir):
     for p_ in ('/root/reference', os.path.join(golden_dir, '_stubs'), golden_dir):
         if p_ not in sys.path:
@@ -71,9 +71,20 @@ def test_oracle_bit_exact_vs_reference(name, golden_dir):
     torch.set_num_threads(8)
     lr, _ = ref(x, dict(cls=y))
     lo = ora(x, dict(cls=y))
+    # ResNet-18 cases are bit-reproducible on the CPU; the ResNet-50 case is not even reference-vs-reference (a fresh copy
+    # of the real reference differs from itself by ~3e-6 in 165 gradients: threaded MKL-DNN reductions), so it is compared
+    # at 5e-5 of each tensor's max instead
+    exact = 'r18' in name
     for kk in lr:
-        assert torch.equal(lr[kk], lo[kk]), kk
+        if exact:
+            assert torch.equal(lr[kk], lo[kk]), kk
+        else:
+            assert abs(float(lr[kk]) - float(lo[kk])) <= 1e-6 * max(1.0, abs(float(lr[kk]))), kk
     sum(lr.values()).backward()
     sum(lo.values()).backward()
     for (ka, pa), (kb, pb) in zip(ref.named_parameters(), ora.named_parameters()):
-        assert ka == kb and torch.equal(pa.grad, pb.grad), ka
+        assert ka == kb
+        if exact:
+            assert torch.equal(pa.grad, pb.grad), ka
+        else:
+            assert float((pa.grad - pb.grad).abs().max()) <= 5e-5 * float(pa.grad.abs().max()) + 1e-12, ka

@@ -1010,10 +1010,16 @@ class FarSegEngine:
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
+        # the warm-up runs real training forwards: keep the BatchNorm buffers (running statistics, num_batches_tracked) as
+        # they were, so that capturing a graph never counts as extra training steps
+        bufs = [b for b in self.m.buffers()]
+        saved = [b.detach().clone() for b in bufs]
         with torch.cuda.stream(side):
             for _ in range(2):  # warm-up: sets kernel attributes, sizes the workspace
                 self.forward_train(x, labels)
                 self.backward(allreduce=False)
+            for b, s_ in zip(bufs, saved):
+                b.copy_(s_)
         cur.wait_stream(side)
         torch.cuda.synchronize()
         split = self.world > 1 and self.sync_dice

@@ -1588,6 +1588,72 @@ extern "C" int evb_gap_bwd(const float* dscene, void* dx, int N, int HW, int C, 
   return LAUNCH_OK();
 }
 
+namespace evb {
+// Fast im2col for small windows (KP / 8 <= 256): blockDim is a multiple of KP/8, so a thread owns one 8-element slot of the
+// K axis for every pixel it visits: the (channel, row, column) of its 8 taps, their offsets from the window origin and
+// their validity tests are computed once; interior pixels (whole window inside the image) take a path without bounds
+// tests.  The generic kernel spent ~25 integer instructions per element on div/mod and was instruction-bound (214 us for
+// the 201 MB stem matrix; the write alone takes ~35 us).
+template <bool U8>
+__global__ void __launch_bounds__(kEwThreads)
+stem_im2col_fast_kernel(const void* __restrict__ xin, const float* __restrict__ mean, const float* __restrict__ stdv,
+                        __nv_bfloat16* __restrict__ a, int N, int Cin, int H, int W, int KP, int ks, int stride, int pad) {
+  const int Ho = H / stride, Wo = W / stride;
+  const int kg = KP / 8;
+  const int kk = ks * ks, K = Cin * kk;
+  const int g = threadIdx.x % kg;
+  const int psub = threadIdx.x / kg, ppb = blockDim.x / kg;   // pixel lane within the block, pixels per block iteration
+  int off[8], rr[8], ss[8];
+  float mu[8], is[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = g * 8 + j;
+    if (k < K) {
+      const int c = k / kk, rs = k % kk;
+      rr[j] = rs / ks - pad;
+      ss[j] = rs % ks - pad;
+      off[j] = U8 ? (rr[j] * W + ss[j]) * Cin + c : c * H * W + rr[j] * W + ss[j];
+      if (U8) { mu[j] = mean[c]; is[j] = stdv[c]; }
+    } else {
+      rr[j] = 1 << 20;   // never valid
+      ss[j] = 0;
+      off[j] = 0;
+      if (U8) { mu[j] = 0.f; is[j] = 1.f; }
+    }
+  }
+  const int lo = pad, hi_h = H - (ks - 1 - pad), hi_w = W - (ks - 1 - pad);   // window fully inside: lo <= h0 < hi
+  const long long npix = (long long)N * Ho * Wo;
+  const bool tail = g * 8 + 8 > K;   // slot touches the zero padding of the K axis
+  for (long long p = (long long)blockIdx.x * ppb + psub; p < npix; p += (long long)gridDim.x * ppb) {
+    const int wo = (int)(p % Wo);
+    const long long t = p / Wo;
+    const int ho = (int)(t % Ho), n = (int)(t / Ho);
+    const int h0 = ho * stride, w0 = wo * stride;
+    const long long base = U8 ? (((long long)n * H + h0) * W + w0) * Cin : ((long long)n * Cin * H + h0) * W + w0;
+    float v[8];
+    if (!tail && h0 >= lo && h0 < hi_h && w0 >= lo && w0 < hi_w) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (U8) v[j] = ((float)__ldg(reinterpret_cast<const uint8_t*>(xin) + base + off[j]) - mu[j]) / is[j];
+        else v[j] = __ldg(reinterpret_cast<const float*>(xin) + base + off[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int h = h0 + rr[j], w = w0 + ss[j];
+        float val = 0.f;
+        if (h >= 0 && h < H && w >= 0 && w < W) {
+          if (U8) val = ((float)__ldg(reinterpret_cast<const uint8_t*>(xin) + base + off[j]) - mu[j]) / is[j];
+          else val = __ldg(reinterpret_cast<const float*>(xin) + base + off[j]);
+        }
+        v[j] = val;
+      }
+    }
+    reinterpret_cast<bf16x8*>(a)[p * kg + g] = pack8(v);
+  }
+}
+}  // namespace evb
+
 static int im2col_check(int N, int Cin, int H, int W, int KP, int ks, int stride, int pad) {
   if (KP % 8 || ks < 1 || ks > 7 || stride < 1 || stride > 2 || pad < 0 || pad > 3 || KP < Cin * ks * ks) return EVB_ERR_ARG;
   if (H % stride || W % stride) return EVB_ERR_ARG;
@@ -1599,6 +1665,14 @@ extern "C" int evb_im2col_nchw(const float* x, void* a, int N, int Cin, int H, i
                                void* stream) {
   if (im2col_check(N, Cin, H, W, KP, ks, stride, pad)) return EVB_ERR_ARG;
   const long long total = (long long)N * (H / stride) * (W / stride) * (KP / 8);
+  const int kg = KP / 8;
+  if (kg <= kEwThreads && (long long)Cin * H * W < (1LL << 30)) {
+    const int bt = (kEwThreads / kg) * kg;
+    const long long npix = total / kg;
+    stem_im2col_fast_kernel<false><<<ew_blocks(npix, (bt / kg) * 4), bt, 0, ST>>>(x, nullptr, nullptr, (__nv_bfloat16*)a, N, Cin,
+                                                                               H, W, KP, ks, stride, pad);
+    return LAUNCH_OK();
+  }
   stem_im2col_kernel<<<ew_blocks(total, kEwThreads), kEwThreads, 0, ST>>>(x, (__nv_bfloat16*)a, N, Cin, H, W, KP, ks, stride,
                                                                        pad);
   return LAUNCH_OK();
@@ -1607,6 +1681,14 @@ extern "C" int evb_im2col_u8(const void* x, const float* mean, const float* stdv
                              int KP, int ks, int stride, int pad, void* stream) {
   if (im2col_check(N, Cin, H, W, KP, ks, stride, pad)) return EVB_ERR_ARG;
   const long long total = (long long)N * (H / stride) * (W / stride) * (KP / 8);
+  const int kg = KP / 8;
+  if (kg <= kEwThreads && (long long)Cin * H * W < (1LL << 30)) {
+    const int bt = (kEwThreads / kg) * kg;
+    const long long npix = total / kg;
+    stem_im2col_fast_kernel<true><<<ew_blocks(npix, (bt / kg) * 4), bt, 0, ST>>>(x, mean, stdv, (__nv_bfloat16*)a, N, Cin, H, W,
+                                                                              KP, ks, stride, pad);
+    return LAUNCH_OK();
+  }
   stem_im2col_u8_kernel<<<ew_blocks(total, kEwThreads), kEwThreads, 0, ST>>>((const uint8_t*)x, mean, stdv, (__nv_bfloat16*)a,
                                                                           N, Cin, H, W, KP, ks, stride, pad);
   return LAUNCH_OK();

@@ -662,48 +662,48 @@ class FarSegEngine:
         self._join_pack()
         return feats
 
-    def _scene_mlp(self, scene, n, train):
-        """4 x (1x1 conv -> ReLU -> 1x1 conv) on the N x C5 x 1 x 1 scene embedding (fs_relation.py:22-28)."""
+    def _scene_mlp_one(self, scene, n, l1, l2, train, dscene, extra=()):
+        """one scene MLP (1x1 conv -> ReLU -> 1x1 conv on the N x C5 x 1 x 1 scene embedding, fs_relation.py:22-35) as two
+        tiny linears on the caller's stream.  Backward: d(sf) (+ the `extra` d(sf) buffers of other levels, summed in
+        order) -> both linears' parameter gradients and this MLP's own d(scene) buffer `dscene` (overwritten)."""
         L = self.L
-        outs = []
         c5 = scene.shape[1]
-        dscene = self._new(n, c5, dtype=torch.float32) if train else None
-        self._dscene_used = False
-        for (l1, l2) in self.scene:
-            co = l1.out_channels
-            hid = self._new(n, co, dtype=torch.float32)
-            sf = self._new(n, co, dtype=torch.float32)
-            check(L.evb_linear_fwd(ptr(scene), ptr(l1.weight), ptr(l1.bias), ptr(hid), c_int(n), c_int(c5), c_int(co),
-                                   c_int(1), stream()), 'evb_linear_fwd')
-            check(L.evb_linear_fwd(ptr(hid), ptr(l2.weight), ptr(l2.bias), ptr(sf), c_int(n), c_int(co), c_int(co),
-                                   c_int(0), stream()), 'evb_linear_fwd')
-            dsf = self._new(n, co, dtype=torch.float32) if train else None
-            outs.append((sf, dsf))
-            if self.scene_shared:
-                # scale_aware_proj=False (fs_relation.py:29-35,63-66): every level reads the same scene vector; each
-                # level's relation backward writes its own d(sf) buffer, summed in level order (fixed -> deterministic)
-                # before the shared MLP's backward
-                outs += [(sf, self._new(n, co, dtype=torch.float32) if train else None) for _ in range(3)]
-            if train:
-                def bwd(l1=l1, l2=l2, hid=hid, sf=sf, dsf=dsf, co=co, extra=[d for _, d in outs[1:]] if self.scene_shared else []):
-                    acc = 1 if self.accumulate else 0
-                    for d in extra:
-                        check(L.evb_copy2d_f32(ptr(d), c_int(co), ptr(dsf), c_int(co), c_int(n), c_int(co), c_int(1),
-                                               stream()), 'evb_copy2d_f32')
-                    dhid = self._new(n, co, dtype=torch.float32)
-                    check(L.evb_linear_bwd(ptr(dsf), ptr(sf), ptr(hid), ptr(l2.weight), ptr(l2.weight.grad),
-                                           ptr(l2.bias.grad), ptr(dhid), c_int(n), c_int(co), c_int(co), c_int(0),
-                                           c_int(acc), c_int(0), stream()), 'evb_linear_bwd')
-                    check(L.evb_linear_bwd(ptr(dhid), ptr(hid), ptr(scene), ptr(l1.weight), ptr(l1.weight.grad),
-                                           ptr(l1.bias.grad), ptr(dscene), c_int(n), c_int(c5), c_int(co), c_int(1),
-                                           c_int(acc), c_int(1 if self._dscene_used else 0), stream()), 'evb_linear_bwd')
-                    self._dscene_used = True
-                self.tape.append(bwd)
-        return outs, dscene
+        co = l1.out_channels
+        hid = self._new(n, co, dtype=torch.float32)
+        sf = self._new(n, co, dtype=torch.float32)
+        check(L.evb_linear_fwd(ptr(scene), ptr(l1.weight), ptr(l1.bias), ptr(hid), c_int(n), c_int(c5), c_int(co),
+                               c_int(1), stream()), 'evb_linear_fwd')
+        check(L.evb_linear_fwd(ptr(hid), ptr(l2.weight), ptr(l2.bias), ptr(sf), c_int(n), c_int(co), c_int(co),
+                               c_int(0), stream()), 'evb_linear_fwd')
+        dsf = self._new(n, co, dtype=torch.float32) if train else None
+        if train:
+            def bwd():
+                acc = 1 if self.accumulate else 0
+                for d in extra:
+                    check(L.evb_copy2d_f32(ptr(d), c_int(co), ptr(dsf), c_int(co), c_int(n), c_int(co), c_int(1),
+                                           stream()), 'evb_copy2d_f32')
+                dhid = self._new(n, co, dtype=torch.float32)
+                check(L.evb_linear_bwd(ptr(dsf), ptr(sf), ptr(hid), ptr(l2.weight), ptr(l2.weight.grad),
+                                       ptr(l2.bias.grad), ptr(dhid), c_int(n), c_int(co), c_int(co), c_int(0),
+                                       c_int(acc), c_int(0), stream()), 'evb_linear_bwd')
+                check(L.evb_linear_bwd(ptr(dhid), ptr(hid), ptr(scene), ptr(l1.weight), ptr(l1.weight.grad),
+                                       ptr(l1.bias.grad), ptr(dscene), c_int(n), c_int(c5), c_int(co), c_int(1),
+                                       c_int(acc), c_int(0), stream()), 'evb_linear_bwd')
+            self.tape.append(bwd)
+        return sf, dsf
 
-    def _level(self, i, inner_i, sf_pair, train):
-        """one pyramid level: p_i = fpn_layer(inner_i) -> FS-Relation -> decoder chain (runs on the caller's stream)"""
+    def _level(self, i, inner_i, sf_pair, train, scene=None, dscenes=None):
+        """one pyramid level: [its scene MLP ->] p_i = fpn_layer(inner_i) -> FS-Relation -> decoder chain (runs on the
+        caller's stream).  With scale_aware_proj the level owns its scene MLP (sf_pair None): the four tiny-linear chains run
+        in the parallel level branches instead of back to back on the main stream, forward and backward."""
         L = self.L
+        if sf_pair is None:
+            n_ = scene.shape[0]
+            dsc = self._new(n_, scene.shape[1], dtype=torch.float32) if train else None
+            if train:
+                dscenes.append(dsc)
+            l1, l2 = self.scene[i]
+            sf_pair = self._scene_mlp_one(scene, n_, l1, l2, train, dsc)
         p = self.conv(inner_i, self.fpn_layer[i], train=train)
         self._dbg('p%d' % (i + 2), p)
         (cc, cb), (rc, rb) = self.content[i], self.reenc[i]
@@ -763,12 +763,27 @@ class FarSegEngine:
                 g, acc = self._grad_into(c5)
                 if not acc:
                     g.zero_()
-                check(L.evb_gap_bwd(ptr(holder['dscene']), ptr(g), c_int(n), c_int(h5 * w5), c_int(cc5), stream()),
-                      'evb_gap_bwd')
+                ds = holder['dscenes']
+                for d in ds[1:]:     # d(scene) of the other scene MLPs, summed in level order (deterministic)
+                    check(L.evb_copy2d_f32(ptr(d), c_int(cc5), ptr(ds[0]), c_int(cc5), c_int(n), c_int(cc5), c_int(1),
+                                           stream()), 'evb_copy2d_f32')
+                check(L.evb_gap_bwd(ptr(ds[0]), ptr(g), c_int(n), c_int(h5 * w5), c_int(cc5), stream()), 'evb_gap_bwd')
             self.tape.append(gap_bwd)
-        sfs, dscene = self._scene_mlp(scene, n, train)
+        dscenes = []
         if train:
-            holder['dscene'] = dscene
+            holder['dscenes'] = dscenes
+        if self.scene_shared:
+            # scale_aware_proj=False (fs_relation.py:29-35,63-66): one MLP on the main stream, every level reads the same
+            # scene vector; each level's relation backward writes its own d(sf) buffer, summed before the MLP's backward
+            l1, l2 = self.scene[0]
+            extra = [self._new(n, l1.out_channels, dtype=torch.float32) if train else None for _ in range(3)]
+            dsc = self._new(n, cc5, dtype=torch.float32) if train else None
+            if train:
+                dscenes.append(dsc)
+            sf, dsf = self._scene_mlp_one(scene, n, l1, l2, train, dsc, extra=extra if train else ())
+            sfs = [(sf, dsf)] + [(sf, e) for e in extra]
+        else:
+            sfs = [None] * 4
         # ---- per pyramid level: FPN output conv -> FS-Relation -> decoder chain.  The four chains are independent:
         #      levels 1..3 (small maps, latency-bound kernels) run on their own streams = parallel graph branches
         outs = [None] * 4
@@ -785,11 +800,11 @@ class FarSegEngine:
             if st_i is not None:
                 st_i.wait_event(ev_fork)
                 with torch.cuda.stream(st_i):
-                    outs[i] = self._level(i, inner[i], sfs[i], train)
+                    outs[i] = self._level(i, inner[i], sfs[i], train, scene, dscenes)
                 if train:
                     self._tape_tags.append((t0, len(self.tape), st_i))
             else:
-                outs[i] = self._level(i, inner[i], sfs[i], train)
+                outs[i] = self._level(i, inner[i], sfs[i], train, scene, dscenes)
         if self.level_streams is not None:
             for st_i in self.level_streams:
                 main.wait_stream(st_i)

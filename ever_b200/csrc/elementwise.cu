@@ -855,9 +855,13 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
 // ------------------------------------------------------------------------------------------------ bilinear (align_corners)
 // y[N, f*h, f*w, C] = bf16( bilinear( act(x) ) ),  act(x) = bf16(relu(x*scale+shift)) when scale != null.
 // Input rows have stride ldx (>= C) elements per pixel, output ldy.
+// P2: C/8, Wo and Ho are powers of two (every FarSeg shape): the index decomposition is shifts and masks instead of
+// five integer divisions per output vector (the kernel is instruction-bound: ~40 % of its instructions were div/mod).
+template <bool P2>
 __global__ void __launch_bounds__(kEwThreads)
 bilinear_up_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-                   __nv_bfloat16* __restrict__ y, int N, int h, int w, int C, int ldx, int ldy, int f) {
+                   __nv_bfloat16* __restrict__ y, int N, int h, int w, int C, int ldx, int ldy, int f, int lg_cg, int lg_wo,
+                   int lg_ho) {
   // blockDim is a multiple of C/8: a thread's channel group is fixed, the BN fold is hoisted, UN pixels in flight
   constexpr int UN = 2;
   const int cg = C / 8, Ho = h * f, Wo = w * f;
@@ -866,7 +870,7 @@ bilinear_up_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
   const unsigned total = (unsigned)N * Ho * Wo * cg;
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned stride = gridDim.x * blockDim.x;
-  const int g = (int)(tid % cg);
+  const int g = P2 ? (int)(tid & (unsigned)(cg - 1)) : (int)(tid % cg);
   float a[8], b[8];
   if (scale) {
 #pragma unroll
@@ -880,10 +884,18 @@ bilinear_up_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     for (int u = 0; u < UN; ++u) {
       const unsigned i = i0 + u * stride;
       if (i >= total) continue;
-      unsigned p = i / cg;
-      const int ox = (int)(p % Wo); p /= Wo;
-      const int oy = (int)(p % Ho);
-      const int n = (int)(p / Ho);
+      int ox, oy, n;
+      if (P2) {
+        unsigned p = i >> lg_cg;
+        ox = (int)(p & (unsigned)(Wo - 1)); p >>= lg_wo;
+        oy = (int)(p & (unsigned)(Ho - 1));
+        n = (int)(p >> lg_ho);
+      } else {
+        unsigned p = i / cg;
+        ox = (int)(p % Wo); p /= Wo;
+        oy = (int)(p % Ho);
+        n = (int)(p / Ho);
+      }
       const float fy = sy * oy, fx = sx * ox;
       const int y0 = (int)fy, x0 = (int)fx;
       const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
@@ -1525,8 +1537,15 @@ extern "C" int evb_bilinear_up(const void* x, const float* scale, const float* s
   const long long total = (long long)N * h * f * w * f * (C / 8);
   if (C / 8 > kEwThreads) return EVB_ERR_ARG;
   const int bt = (kEwThreads / (C / 8)) * (C / 8);
-  bilinear_up_kernel<<<ew_blocks(total, bt * 2), bt, 0, ST>>>((const __nv_bfloat16*)x, scale, shift,
-                                                                           (__nv_bfloat16*)y, N, h, w, C, ldx, ldy, f);
+  const int cg = C / 8, Ho = h * f, Wo = w * f;
+  auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
+  const int lc = lg(cg), lw = lg(Wo), lh = lg(Ho);
+  if (lc >= 0 && lw >= 0 && lh >= 0)
+    bilinear_up_kernel<true><<<ew_blocks(total, bt * 2), bt, 0, ST>>>((const __nv_bfloat16*)x, scale, shift, (__nv_bfloat16*)y, N,
+                                                                    h, w, C, ldx, ldy, f, lc, lw, lh);
+  else
+    bilinear_up_kernel<false><<<ew_blocks(total, bt * 2), bt, 0, ST>>>((const __nv_bfloat16*)x, scale, shift, (__nv_bfloat16*)y,
+                                                                     N, h, w, C, ldx, ldy, f, 0, 0, 0);
   return LAUNCH_OK();
 }
 extern "C" int evb_bilinear_up_bwd(const void* dy, void* dx, int N, int h, int w, int C, int lddy, int lddx, int f,

@@ -159,6 +159,42 @@ def conv_roofline(pk):
                 ms_per_launch=ms, flop_per_launch=flop)
 
 
+def bn_roofline(pk):
+    """The largest HBM-bound kernel class of the step (in-situ cost, profiles/r01_knockout_insitu_cost.json): BatchNorm
+    backward (reduce + finalize + apply, cp.async-staged) on the 8 x 128 x 128 x 256 layer shape.  Algorithmic bytes =
+    read dy, x twice + write dx = 5 x M x C x 2 B; rotating buffer sets > L2, CUDA events on the launch stream."""
+    import ctypes
+    from ever_b200._lib import check, lib, ptr, stream
+    L = lib()
+    c_int, c_ll = ctypes.c_int, ctypes.c_longlong
+    m, c, nset = 131072, 256, 3
+    xs, dys, dxs = [[torch.randn(m, c, device='cuda').bfloat16() for _ in range(nset)] for _ in range(3)]
+    st = torch.rand(4, c, device='cuda') + 0.5
+    dg, db = torch.empty(c, device='cuda'), torch.empty(c, device='cuda')
+    ws = torch.empty(L.evb_bn_workspace(c_ll(m), c_int(c)) // 4, device='cuda')
+
+    def run(i):
+        check(L.evb_bn_bwd(ptr(dys[i]), ptr(xs[i]), None, ptr(st[0]), ptr(st[1]), ptr(st[2]), ptr(st[3]), c_int(2), c_int(0),
+                           ptr(dxs[i]), None, c_int(0), ptr(dg), ptr(db), c_int(0), c_ll(m), c_int(c), ptr(ws), stream()),
+              'evb_bn_bwd')
+    for i in range(nset):
+        run(i)
+    torch.cuda.synchronize()
+    iters = 30
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for i in range(iters):
+        run(i % nset)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    nbytes = 5.0 * m * c * 2
+    ach = nbytes / (ms * 1e-3) / 1e9
+    return dict(bound='hbm', kernel='evb_bn_bwd = bn_bwd_reduce_ca<2> + bn_bwd_finalize2 + bn_bwd_apply_ca<2> on [131072, 256] bf16',
+                achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'], traffic=134321664 + 4555776 + 134238976 + 28960768,
+                peak_source=pk['src'] + ' hbm_gbs (copy)', ms_per_launch=ms, bytes_per_launch=nbytes)
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import torch.distributed as dist
@@ -302,6 +338,7 @@ def run_b200(args):
     if rank == 0:
         pk = peaks()
         roof = conv_roofline(pk)
+        roof_hbm = bn_roofline(pk)
         cpu_val, cpu_sec, cores = cpu_reference(2, 1, 1) if world == 1 and not args.no_cpu else (None, None, None)
         tfs = value / world * GFLOP_PER_TILE / 1e3
         line = dict(metric=METRIC, value=value, unit='tiles/s', n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
@@ -312,6 +349,7 @@ def run_b200(args):
                                 parallelism='dp%d' % world, cuda_graph=graph is not None,
                                 l2='step working set (~10 GB of activations) >> 126 MB L2; no explicit flush'),
                     e2e=e2e, gpu_launches=int(per_step_launches * args.steps), clocks=clocks, roofline=roof,
+                    roofline_hbm=roof_hbm,
                     model_tflops_per_gpu=tfs, model_frac_of_sustained_peak=tfs / pk['tf_sust'], losses=loss_now)
         if cpu_val is not None:
             line['cpu_baseline'] = dict(value=cpu_val, unit='tiles/s', cores=cores, kind='port',

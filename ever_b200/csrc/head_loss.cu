@@ -305,9 +305,13 @@ loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restric
         acc[1] += 1.f;
 #pragma unroll
         for (int c = 0; c < K; ++c) {
+          // select arithmetic instead of `if (c == t) acc[..] += ..`: the compiler turned that chain into acc[2 + t] with a
+          // dynamic index, which moved acc[] and e[] to local memory (248-byte stack frame, kernel 2x slower)
           const float pc = e[c] * inv_se;
+          const float hit = (c == (int)t) ? 1.f : 0.f;
           acc[2 + K + c] += pc;
-          if (c == (int)t) { acc[2 + c] += pc; acc[2 + 2 * K + c] += 1.f; }
+          acc[2 + c] += hit * pc;
+          acc[2 + 2 * K + c] += hit;
         }
       }
     } else {
@@ -346,10 +350,11 @@ loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restric
   if (PASS == 0) {
     const int n = 2 + 3 * K;
 #pragma unroll
-    for (int i = 0; i < 2 + 3 * KA; ++i) {
-      if (i >= n) break;
-      const float v = warp_sum(acc[i]);
-      if (lane == 0) red[wid][i] = v;
+    for (int i = 0; i < 2 + 3 * KA; ++i) {   // no early break: keeps the indices static so acc[] stays in registers
+      if (i < n) {
+        const float v = warp_sum(acc[i]);
+        if (lane == 0) red[wid][i] = v;
+      }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {

@@ -270,11 +270,12 @@ class FarSegEngine:
         self._pack_desc = torch.tensor(rows, dtype=torch.int64, device=self.dev)
         self._pack_map = torch.tensor(bmap, dtype=torch.int32, device=self.dev)
         self._pack_nblk = nblk
-        # blocks of the convolutions the forward pass needs first (stem, layer1, layer2): packed on the main stream; the
-        # rest (layer3, layer4, head: ~95 % of the parameters) is packed on the side stream while those layers run
+        # optional (EVB_PACK_OVERLAP=1; measured neutral on B200, off by default): blocks of the convolutions the forward
+        # pass needs first (stem, layer1, layer2) are packed on the main stream, the rest (layer3, layer4, head: ~95 % of
+        # the parameters) on the side stream while those layers run
         first_late = self.stages[2][0]['c1'] if len(self.stages) > 2 else None
         self._pack_split = nblk
-        if first_late is not None and self.side is not None and os.environ.get('EVB_NO_PACK_OVERLAP', '0') != '1':
+        if first_late is not None and self.side is not None and os.environ.get('EVB_PACK_OVERLAP', '0') == '1':
             self._pack_split = rows[self.convs.index(first_late)][10]
         self._pack_ptrs = [cp.weight.data_ptr() for cp in self.convs]
 

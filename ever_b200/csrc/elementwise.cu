@@ -235,80 +235,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s
 }
 
 // dx = scale * (g - (dbeta + xhat * dgamma) / M) = a*g + k0 - c2*x,  g = dy * mask ;  optional dres (+)= g
-//   c2 = a * rstd * dgamma / M,  k0 = c2 * mean - a * dbeta / M   (hoisted per channel)
-__global__ void __launch_bounds__(kEwThreads)
-bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
-                    const __nv_bfloat16* __restrict__ ymask, const float* __restrict__ mean,
-                    const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
-                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, int mask_mode, int frozen,
-                    __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres, int dres_acc, long long nvec, int C,
-                    float inv_m) {
-  constexpr int UN = 2;
-  const int cg = C / 8;
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const int c0 = (int)(tid % cg) * 8;
-  float a[8], k0[8], c2[8], sh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = c0 + j;
-    a[j] = scale[c];
-    sh[j] = shift[c];
-    if (frozen) { c2[j] = 0.f; k0[j] = 0.f; }
-    else {
-      c2[j] = a[j] * rstd[c] * dgamma[c] * inv_m;
-      k0[j] = c2[j] * mean[c] - a[j] * dbeta[c] * inv_m;
-    }
-  }
-  for (long long i0 = tid; i0 < nvec; i0 += stride * UN) {
-    bf16x8 gv[UN], xv[UN], yv[UN], dv[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < nvec) {
-        gv[u] = reinterpret_cast<const bf16x8*>(dy)[i];
-        xv[u] = reinterpret_cast<const bf16x8*>(x)[i];
-        if (mask_mode == 1) yv[u] = reinterpret_cast<const bf16x8*>(ymask)[i];
-        if (dres && dres_acc) dv[u] = reinterpret_cast<const bf16x8*>(dres)[i];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < nvec) {
-        float g[8], xf[8];
-        unpack8(gv[u], g);
-        unpack8(xv[u], xf);
-        if (mask_mode == 1) {
-          float yf[8];
-          unpack8(yv[u], yf);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = yf[j] > 0.f ? g[j] : 0.f;
-        } else if (mask_mode == 2) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = bf16_round(xf[j] * a[j] + sh[j]) > 0.f ? g[j] : 0.f;
-        }
-        if (dres) {
-          float d[8];
-          if (dres_acc) {
-            unpack8(dv[u], d);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) d[j] += g[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) d[j] = g[j];
-          }
-          reinterpret_cast<bf16x8*>(dres)[i] = pack8(d);
-        }
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = a[j] * g[j] + k0[j] - c2[j] * xf[j];
-        reinterpret_cast<bf16x8*>(dx)[i] = pack8(o);
-      }
-    }
-  }
-}
-
+//   c2 = a * rstd * dgamma / M,  k0 = c2 * mean - a * dbeta / M   (hoisted per channel); kernels below
 // ------------------------------------------------------------------------------------------------
 // Narrow-vector variants of the BatchNorm streaming kernels.  A thread owns V (4 or 8) consecutive channels, so its
 // per-channel constants live in 3-4 * V registers; with V = 4 the kernels need ~half the registers of the V = 8 versions,

@@ -213,3 +213,43 @@ def test_step_loop_lr_timing_matches_reference_launcher():
         logged.append(loop.lr)
     assert [round(v, 6) for v in logged] == [0.007, 0.00486, 0.002604]
     assert [round(v, 6) for v in used] == [0.007, 0.007, 0.00486]
+
+
+def test_c_abi_rejects_bad_arguments_without_touching_the_device():
+    """Every entry point validates its arguments first and reports EVB_ERR_ARG (1) as a status code -- nothing throws across
+    the C boundary and no kernel is launched (this runs on a box without a GPU)."""
+    import ctypes
+    from ever_b200._lib import lib
+    L = lib()
+    c_int, c_ll, c_f = ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+    null = ctypes.c_void_p(0)
+    ERR_ARG = 1
+    # convolution: only 1x1 / 3x3, stride 1 / 2
+    assert L.evb_conv2d_fwd(null, c_int(1), c_int(32), c_int(32), c_int(64), null, c_int(64), c_int(5), c_int(1), null,
+                            c_int(64), null, null, c_int(0), c_int(0), null) == ERR_ARG
+    assert L.evb_conv2d_dgrad(null, c_int(1), c_int(16), c_int(16), c_int(64), null, c_int(64), c_int(3), c_int(3), null,
+                              c_int(32), c_int(32), c_int(64), c_int(0), c_int(0), null) == ERR_ARG
+    # wgrad: channel counts must be multiples of 64
+    assert L.evb_conv2d_wgrad(null, c_int(1), c_int(32), c_int(32), c_int(48), null, c_int(64), c_int(3), c_int(1), null,
+                              c_int(0), null, c_ll(0), c_int(0), c_int(0), null) == ERR_ARG
+    # epilogue statistics need their output buffers
+    assert L.evb_conv2d_fwd_stats(null, c_int(1), c_int(32), c_int(32), c_int(64), null, c_int(64), c_int(3), c_int(1), null,
+                                  c_int(64), null, null, null) == ERR_ARG
+    # BatchNorm: C % 8, mask mode, partial-column count
+    assert L.evb_bn_apply(null, null, null, null, null, c_ll(16), c_int(12), c_int(1), null) == ERR_ARG
+    assert L.evb_bn_bwd(null, null, null, null, null, null, null, c_int(3), c_int(0), null, null, c_int(0), null, null,
+                        c_int(0), c_ll(16), c_int(64), null, null) == ERR_ARG
+    assert L.evb_bn_finalize(null, c_int(0), c_ll(16), c_int(64), null, null, null, null, c_f(0.1), c_f(1e-5), null, null, null,
+                             null, null) == ERR_ARG
+    # im2col window, gather element size, canvas bounding box, loss class count
+    assert L.evb_im2col_nchw(null, null, c_int(1), c_int(3), c_int(32), c_int(32), c_int(20), c_int(3), c_int(2), c_int(1),
+                             null) == ERR_ARG
+    assert L.evb_pixel_gather(null, c_int(1), c_int(8), c_int(8), c_int(3), c_int(3), c_ll(0), null, null, c_int(1), c_int(8),
+                              c_int(8), null) == ERR_ARG
+    assert L.evb_canvas_accumulate(null, c_int(1), c_int(5), c_int(8), c_int(8), null, null, null, c_int(1), c_int(16),
+                                   c_int(16), c_int(0), c_int(32), c_int(0), c_int(16), null) == ERR_ARG
+    assert L.evb_loss_stats(null, null, c_ll(16), c_int(17), c_int(16), c_int(255), null, null, null) == ERR_ARG
+    # tuning switches validate their ranges
+    assert L.evb_set_bn_variant(c_int(5)) == ERR_ARG and L.evb_set_bn_vec(c_int(3)) == ERR_ARG
+    assert L.evb_set_igemm_variant(c_int(0)) == ERR_ARG and L.evb_set_bn_reduce_blocks(c_int(9)) == ERR_ARG
+    assert L.evb_version() >= 101

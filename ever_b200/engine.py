@@ -262,7 +262,7 @@ class FarSegEngine:
         rows, bmap, nblk = [], [], 0
         for i, cp in enumerate(self.convs):
             kk = cp.k * cp.k
-            nb = ((cp.co + 31) // 32) * ((cp.ci + 31) // 32)   # one block per 32x32 (co, ci) tile, all taps
+            nb = ((cp.co + 63) // 64) * ((cp.ci + 63) // 64)   # one block per 64x64 (co, ci) tile, all taps
             rows.append([cp.weight.data_ptr() + 4 * cp.w_off, cp.wf.data_ptr(), cp.wb.data_ptr() if cp.need_dgrad else 0,
                          cp.co, cp.ci, kk, cp.cop, cp.cip, cp.cip, cp.cop, nblk, cp.w_ld])
             bmap += [i] * nb
@@ -291,13 +291,13 @@ class FarSegEngine:
             ev.record(main)
             with torch.cuda.stream(self.side):
                 self.side.wait_event(ev)
-                check(self.L.evb_pack_weights_range(ptr(self._pack_desc), ptr(self._pack_map), c_int(self._pack_split),
+                check(self.L.evb_pack_weights_tiled(ptr(self._pack_desc), ptr(self._pack_map), c_int(self._pack_split),
                                                     c_int(self._pack_nblk - self._pack_split), stream()),
-                      'evb_pack_weights_range')
+                      'evb_pack_weights_tiled')
                 self._pack_ev = torch.cuda.Event()
                 self._pack_ev.record(self.side)
-        check(self.L.evb_pack_weights_range(ptr(self._pack_desc), ptr(self._pack_map), c_int(0), c_int(self._pack_split), st),
-              'evb_pack_weights_range')
+        check(self.L.evb_pack_weights_tiled(ptr(self._pack_desc), ptr(self._pack_map), c_int(0), c_int(self._pack_split), st),
+              'evb_pack_weights_tiled')
         for cp in self.convs:
             cp._gw = False
             if cp.bias_pad is not None:

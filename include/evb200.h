@@ -71,6 +71,9 @@ int evb_pack_weight(const float* w, int Co, int Ci, int kk, void* wf, int CoP, i
                     void* stream);
 /* every convolution of a model in one launch; desc: int64[n][12], block_map: int32[nblocks] (see elementwise.cu) */
 int evb_pack_weights_batched(const void* desc, const void* block_map, int nblocks, void* stream);
+/* same table layout with 64 x 64 (co, ci) tiles per block (block_map counts ceil(Co/64)*ceil(Ci/64) blocks per conv), bf16
+ * staging and 16-byte stores: the variant the engine uses */
+int evb_pack_weights_tiled(const void* desc, const void* block_map, int block0, int nblocks, void* stream);
 /* blocks [block0, block0 + nblocks) of the same table (first layers on the main stream, the rest on a second stream) */
 int evb_pack_weights_range(const void* desc, const void* block_map, int block0, int nblocks, void* stream);
 /* 7x7 stride-2 pad-3 stem lowered to a GEMM: x NCHW fp32 -> A[N*H/2*W/2][KP] bf16, k = c*49 + r*7 + s

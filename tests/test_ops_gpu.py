@@ -348,3 +348,43 @@ def test_u8_input_pipeline_and_confusion_matrix():
     valid = lab != 255
     ref = torch.bincount(lab[valid] * k + pred[valid].long(), minlength=k * k).view(k, k)
     assert torch.equal(cm, 2 * ref)
+
+
+@pytest.mark.parametrize('entry,tile', [('evb_pack_weights_tiled', 64), ('evb_pack_weights_range', 32)])
+def test_batched_weight_pack_bit_exact(entry, tile):
+    """fp32 OIHW master -> bf16 packs [tap][CoP][CiP] and [tap][CiP][CoP] for a table of convolutions in one launch: 3x3 and
+    1x1, channel counts that are not multiples of the tile (15, 147), zero padding, a Cin sub-range of a wider weight
+    (w_off / w_ld), and a conv without a dgrad pack.  Pure rounding + movement: bit-exact."""
+    L, check, ptr, stream = _L()
+    g = _gen(21)
+    cases = [  # (Co, Ci_total, k, ci_lo, ci_n, CoP, CiP, need_wb)
+        (256, 256, 3, 0, 256, 256, 256, True), (15, 256, 1, 0, 256, 64, 256, True), (64, 147, 1, 0, 147, 64, 192, False),
+        (16, 512, 3, 256, 256, 64, 256, True), (96, 40, 3, 0, 40, 128, 64, True)]
+    rows, bmap, nblk, keep = [], [], 0, []
+    for i, (co, cit, k, lo, cn, cop, cip, need_wb) in enumerate(cases):
+        kk = k * k
+        w = torch.randn(co, cit, k, k, device='cuda', generator=g)
+        wf = torch.zeros(kk, cop, cip, device='cuda', dtype=torch.bfloat16)
+        wb = torch.zeros(kk, cip, cop, device='cuda', dtype=torch.bfloat16) if need_wb else None
+        nb = ((co + tile - 1) // tile) * ((cn + tile - 1) // tile)
+        rows.append([w.data_ptr() + 4 * lo * kk, wf.data_ptr(), wb.data_ptr() if need_wb else 0, co, cn, kk, cop, cip, cip, cop,
+                     nblk, cit * kk if lo or cn != cit else 0])
+        bmap += [i] * nb
+        nblk += nb
+        keep.append((w, wf, wb))
+    desc = torch.tensor(rows, dtype=torch.int64, device='cuda')
+    bm = torch.tensor(bmap, dtype=torch.int32, device='cuda')
+    half = nblk // 2   # two range launches cover the table
+    check(getattr(L, entry)(ptr(desc), ptr(bm), c_int(0), c_int(half), stream()), entry)
+    check(getattr(L, entry)(ptr(desc), ptr(bm), c_int(half), c_int(nblk - half), stream()), entry)
+    torch.cuda.synchronize()
+    for (co, cit, k, lo, cn, cop, cip, need_wb), (w, wf, wb) in zip(cases, keep):
+        kk = k * k
+        sub = w[:, lo:lo + cn].reshape(co, cn, kk).bfloat16()
+        ref_f = torch.zeros(kk, cop, cip, device='cuda', dtype=torch.bfloat16)
+        ref_f[:, :co, :cn] = sub.permute(2, 0, 1)
+        assert torch.equal(wf, ref_f)
+        if need_wb:
+            ref_b = torch.zeros(kk, cip, cop, device='cuda', dtype=torch.bfloat16)
+            ref_b[:, :cn, :co] = sub.permute(2, 1, 0)
+            assert torch.equal(wb, ref_b)

@@ -22,7 +22,7 @@ CLASSES = {
     'stem_im2col': ['evb_stem_im2col'],
     'maxpool': ['evb_maxpool3x3s2_fwd', 'evb_maxpool3x3s2_bwd'],
     'relation': ['evb_relation_fwd', 'evb_relation_bwd'],
-    'pack_weights': ['evb_pack_weights_batched'],
+    'pack_weights': ['evb_pack_weights_tiled'],
     'wgrad': ['evb_conv2d_wgrad'],
     'conv_fwd': ['evb_conv2d_fwd', 'evb_conv2d_fwd_stats'],
     'dgrad': ['evb_conv2d_dgrad'],

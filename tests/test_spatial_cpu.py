@@ -129,3 +129,42 @@ def test_augment_oracle_equals_real_reference_transforms():
         np.random.seed(seed)
         oa, ob = augment_oracle(img, msk, crop_size=(36, 44), size_divisor=32)
         assert torch.equal(a2.permute(1, 2, 0), oa) and torch.equal(b2, ob)
+
+
+def test_random_op_chains_equal_torch_ops_property():
+    """property test (hypothesis): any chain of rot90 / flips / transpose / crop / bottom-right pad composes into ONE
+    PixelMap that reproduces the torch ops applied one after the other, including fill in padded regions that a later
+    crop / flip / rotation moves around"""
+    from hypothesis import given, settings, strategies as st
+
+    op = st.one_of(st.tuples(st.just('rot'), st.integers(0, 3)), st.tuples(st.just('hflip'), st.just(0)),
+                   st.tuples(st.just('vflip'), st.just(0)), st.tuples(st.just('T'), st.just(0)),
+                   st.tuples(st.just('crop'), st.tuples(st.floats(0, 1), st.floats(0, 1), st.floats(0.2, 1), st.floats(0.2, 1))),
+                   st.tuples(st.just('pad'), st.tuples(st.integers(0, 5), st.integers(0, 5))))
+
+    @settings(max_examples=150, deadline=None)
+    @given(h=st.integers(1, 9), w=st.integers(1, 9), ops=st.lists(op, min_size=1, max_size=6))
+    def run(h, w, ops):
+        x = torch.arange(1, h * w * 2 + 1).reshape(h, w, 2)
+        m, ref = PixelMap(h, w), x
+        for name, arg in ops:
+            ch, cw = ref.shape[:2]
+            if name == 'rot':
+                m, ref = m.rot90(arg), torch.rot90(ref, arg, [0, 1])
+            elif name == 'hflip':
+                m, ref = m.hflip(), torch.flip(ref, [1])
+            elif name == 'vflip':
+                m, ref = m.vflip(), torch.flip(ref, [0])
+            elif name == 'T':
+                m, ref = m.transpose(), ref.transpose(0, 1)
+            elif name == 'crop':
+                fy, fx, fh, fw = arg
+                nh, nw = max(1, int(round(fh * ch))), max(1, int(round(fw * cw)))
+                y0, x0 = int(fy * (ch - nh)), int(fx * (cw - nw))
+                m, ref = m.crop(y0, x0, nh, nw), ref[y0:y0 + nh, x0:x0 + nw]
+            else:
+                ph, pw = arg
+                m, ref = m.pad_to(ch + ph, cw + pw), F.pad(ref, [0, 0, 0, pw, 0, ph], value=-7)
+        got = m.apply_reference(x, fill=-7)
+        assert got.shape == ref.shape and torch.equal(got, ref)
+    run()

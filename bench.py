@@ -118,8 +118,8 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n_tiles = 2
-    val, sec, cores = cpu_reference(n_tiles, max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
+    n_tiles = 4
+    val, sec, cores = cpu_reference(n_tiles, max(1, min(args.steps, 5)), max(1, min(args.warmup, 1)))
     sample = '%d tiles of 3x512x512 per step (bounded sample of the 8-tile batch), fp32, torch CPU, %d threads' % (n_tiles, cores)
     line = dict(metric=METRIC, value=val, unit='tiles/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
@@ -339,7 +339,7 @@ def run_b200(args):
         pk = peaks()
         roof = conv_roofline(pk)
         roof_hbm = bn_roofline(pk)
-        cpu_val, cpu_sec, cores = cpu_reference(2, 1, 1) if world == 1 and not args.no_cpu else (None, None, None)
+        cpu_val, cpu_sec, cores = cpu_reference(4, 4, 1) if world == 1 and not args.no_cpu else (None, None, None)
         tfs = value / world * GFLOP_PER_TILE / 1e3
         line = dict(metric=METRIC, value=value, unit='tiles/s', n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                     ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic',
@@ -353,7 +353,8 @@ def run_b200(args):
                     model_tflops_per_gpu=tfs, model_frac_of_sustained_peak=tfs / pk['tf_sust'], losses=loss_now)
         if cpu_val is not None:
             line['cpu_baseline'] = dict(value=cpu_val, unit='tiles/s', cores=cores, kind='port',
-                                        sample='2 tiles of 3x512x512, 1 warm-up + 1 timed fwd+loss+bwd, fp32 torch CPU')
+                                        sample='4 tiles of 3x512x512 per step (half the 8-tile batch), 1 warm-up + 4 timed '
+                                               'fwd+loss+bwd steps (~7 s of CPU work), fp32 torch CPU, all host cores')
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

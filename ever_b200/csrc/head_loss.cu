@@ -488,10 +488,13 @@ __global__ void norm_finalize_kernel(const float* partial, int nblk, float* out 
 // torch.optim.SGD (momentum, weight decay, dampening 0, no nesterov) + clip coefficient, in place
 __global__ void __launch_bounds__(256)
 sgd_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ mom, long long n, const float* __restrict__ lr_ptr,
-           float momentum, float wd, const float* __restrict__ clip, int first_step, int zero_grad) {
+           float momentum, float wd, const float* __restrict__ clip, int first_step, int zero_grad,
+           const unsigned char* __restrict__ trainable) {
   const float c = clip ? clip[1] : 1.f;
   const float lr = *lr_ptr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    // torch.optim.SGD skips parameters without a gradient (requires_grad=False): no decay, no momentum, no update
+    if (trainable && !trainable[i]) continue;
     float d = g[i] * c + wd * w[i];
     float b = first_step ? d : momentum * mom[i] + d;
     mom[i] = b;
@@ -634,7 +637,18 @@ extern "C" int evb_sgd_step(float* w, float* g, float* mom, long long n, const f
   long long b = (n + 256 * 4 - 1) / (256 * 4);
   if (b > 148 * 8) b = 148 * 8;
   if (b < 1) b = 1;
-  sgd_kernel<<<(int)b, 256, 0, ST>>>(w, g, mom, n, lr, momentum, wd, clip, first_step, zero_grad);
+  sgd_kernel<<<(int)b, 256, 0, ST>>>(w, g, mom, n, lr, momentum, wd, clip, first_step, zero_grad, nullptr);
+  return LAUNCH_OK();
+}
+// Same with a per-slot trainable mask (uint8, 1 = update): frozen parameters (freeze_at, batchnorm_trainable=False) keep
+// their weights and momentum untouched, as torch.optim.SGD does for parameters whose grad is None.
+extern "C" int evb_sgd_step_masked(float* w, float* g, float* mom, long long n, const float* lr, float momentum, float wd,
+                                   const float* clip, int first_step, int zero_grad, const unsigned char* trainable,
+                                   void* stream) {
+  long long b = (n + 256 * 4 - 1) / (256 * 4);
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  sgd_kernel<<<(int)b, 256, 0, ST>>>(w, g, mom, n, lr, momentum, wd, clip, first_step, zero_grad, trainable);
   return LAUNCH_OK();
 }
 

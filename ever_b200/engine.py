@@ -27,11 +27,12 @@ def _ceil(a, b):
 
 class Act:
     """An activation tensor (NHWC bf16) plus its gradient slot."""
-    __slots__ = ('data', 'grad', 'has_grad', 'needs_grad', 'stats')
+    __slots__ = ('data', 'grad', 'has_grad', 'needs_grad', 'stats', 'name')
 
-    def __init__(self, data, needs_grad=True):
+    def __init__(self, data, needs_grad=True, name=None):
         self.data, self.grad, self.has_grad, self.needs_grad = data, None, False, needs_grad
         self.stats = None   # (partial sums, nblk) of BN batch statistics emitted by the producing conv's epilogue
+        self.name = name    # reference module path whose output this tensor is (teacher-forced parity tests)
 
     @property
     def shape(self):
@@ -62,6 +63,7 @@ class ConvP:
         self.need_dgrad = True
         self.gscr = self.bias_pad = self.dbias_scr = None
         self._gw = False   # weight/bias gradient already written in this step (shared convs accumulate)
+        self.name = None   # module path of the nn.Conv2d in the plugin model == the reference's (set by _collect)
 
     @staticmethod
     def from_conv(conv, cout_pad=None, as_matrix=False):
@@ -80,6 +82,7 @@ class BNP:
         self.c = cpad or bn.num_features
         self.padded = self.c != self.c_real
         self._gw = False
+        self.name = None
         if self.padded:
             dev = bn.weight.device
             self.gamma_p = torch.ones(self.c, device=dev)
@@ -103,6 +106,12 @@ class FarSegEngine:
         self.dev = p0.device
         self.world = 1
         self.rank = 0
+        try:   # the reference's Dice all_reduce_sum runs whenever torch.distributed is initialised (ever/module/loss.py:20-23)
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        except Exception:
+            pass
         self._flatten_params()
         self._collect()
         self.tape = []
@@ -124,6 +133,7 @@ class FarSegEngine:
         self._saved_for_backward = None
         self._graphs = {}
         self.debug = None            # dict -> named activations are recorded (tests / diagnostics)
+        self.tf = None               # callable(kind, name, tensor) -> teacher forcing hook (tests; see _tf_fwd)
         cfg = module.config
         self.ignore_index = int(cfg.loss.ignore_index)
         self.ce_w = float(cfg.loss.ce.weight)
@@ -146,11 +156,51 @@ class FarSegEngine:
         self.flat_g = torch.zeros(off, dtype=torch.float32, device=self.dev)
         self.params = params
         self.grad_views = []
+        self._gv = {}
+        self._slots = []   # (offset, numel) of every parameter in the arenas
         for p, o in zip(params, offs):
             self.flat_w[o:o + p.numel()].view_as(p).copy_(p.data)
             p.data = self.flat_w[o:o + p.numel()].view_as(p)
-            self.grad_views.append(self.flat_g[o:o + p.numel()].view_as(p))
+            gv = self.flat_g[o:o + p.numel()].view_as(p)
+            self.grad_views.append(gv)
+            self._gv[id(p)] = gv
+            self._slots.append((o, p.numel()))
         self.n_params = n
+        self._train_mask = None
+
+    def _g(self, p):
+        """the gradient slot of parameter p in the flat arena (None for a frozen parameter).  The engine always writes
+        here; whether ``p.grad`` aliases the slot (native path, attach_grads) or autograd accumulates a copy of it into
+        ``p.grad`` (autograd / DDP path, ever_b200.module._StepFn) is the caller's business."""
+        return self._gv[id(p)] if p.requires_grad else None
+
+    def trainable_mask(self):
+        """uint8 mask over the arena slots: 1 where the slot belongs to a parameter with requires_grad (torch.optim.SGD
+        skips parameters without a gradient: frozen weights must see neither weight decay nor momentum)."""
+        key = tuple(p.requires_grad for p in self.params)
+        if self._train_mask is None or self._train_mask[0] != key:
+            if all(key):
+                self._train_mask = (key, None)
+            else:
+                m = torch.zeros(self.flat_w.numel(), dtype=torch.uint8)
+                for (o, nel), rg in zip(self._slots, key):
+                    if rg:
+                        m[o:o + nel] = 1
+                self._train_mask = (key, m.to(self.dev))
+        return self._train_mask[1]
+
+    def accounting(self, on=True):
+        """count the algorithmic bytes / FLOPs of the C-ABI calls made from now on (ever_b200.acct); returns the counter,
+        accounting(False) restores the direct library binding"""
+        from .acct import AcctLib
+        if on:
+            if not isinstance(self.L, AcctLib):
+                self.L = AcctLib(self.L)
+            return self.L
+        if isinstance(self.L, AcctLib):
+            acct, self.L = self.L, self.L._lib
+            return acct
+        return None
 
     def set_distributed(self, rank, world):
         """Data parallel over `world` ranks: Dice statistics and the flat gradient arena are all-reduced."""
@@ -228,6 +278,14 @@ class FarSegEngine:
         self.cls = C(dec.classifier[0], cout_pad=64)
         self.cls_scale = dec.scale_factor
         self._collect_extra()
+        # reference module paths (== state_dict prefixes) of every conv / BN the engine schedules
+        wname = {id(mod.weight): path for path, mod in m.named_modules()
+                 if isinstance(getattr(mod, 'weight', None), torch.nn.Parameter)}
+        for cp in self.convs:
+            if not cp.w_ld:
+                cp.name = wname.get(id(cp.weight))
+        for bp in self.bns:
+            bp.name = wname.get(id(bp.bn.weight))
         self._alloc_packs()
 
     def _collect_extra(self):
@@ -298,6 +356,9 @@ class FarSegEngine:
                 self._pack_ev.record(self.side)
         check(self.L.evb_pack_weights_tiled(ptr(self._pack_desc), ptr(self._pack_map), c_int(0), c_int(self._pack_split), st),
               'evb_pack_weights_tiled')
+        if hasattr(self.L, 'add'):   # accounting: read the fp32 master once, write both bf16 layouts
+            self.L.add('evb_pack_weights_tiled', sum(cp.co * cp.ci * cp.kk * (4 + 2 + (2 if cp.need_dgrad else 0))
+                                                     for cp in self.convs))
         for cp in self.convs:
             cp._gw = False
             if cp.bias_pad is not None:
@@ -359,6 +420,21 @@ class FarSegEngine:
         if self.debug is not None:
             self.debug[name] = t.data if isinstance(t, Act) else t
 
+    def _tf_fwd(self, act, name=None):
+        """teacher forcing (parity tests): hand the freshly computed activation to ``self.tf('fwd', name, tensor)``, which
+        compares it with the reference's tensor of that module path and overwrites it, so that every op is checked on the
+        reference's own inputs (no error amplification through the ~50-layer ReLU/BN chain)."""
+        if name is not None:
+            act.name = name
+        if self.tf is not None and act.name is not None:
+            self.tf('fwd', act.name, act.data)
+        return act
+
+    def _tf_bwd(self, act):
+        """same for the completed gradient of an activation, at the top of the backward closure of its producer"""
+        if self.tf is not None and act.name is not None and act.grad is not None:
+            self.tf('bwd', act.name, act.grad)
+
     def _new(self, *shape, dtype=BF16):
         return torch.empty(shape, dtype=dtype, device=self.dev)
 
@@ -375,40 +451,40 @@ class FarSegEngine:
         """weight gradient of one conv use; shared convs (used twice in a step) accumulate."""
         L = self.L
         st = stream()
-        if cp.weight.grad is None:
+        if self._g(cp.weight) is None:
             return
         ho, wo = h // stride, w // stride
         nbytes = L.evb_conv2d_wgrad_workspace(c_int(n), c_int(ho), c_int(wo), c_int(cin), c_int(cout), c_int(cp.k), c_int(0),
                                               c_int(0))
         ws = self._ws(nbytes)
         acc = self.accumulate or cp._gw
-        target = cp.weight.grad if cp.direct_grad else cp.gscr
+        target = self._g(cp.weight) if cp.direct_grad else cp.gscr
         check(L.evb_conv2d_wgrad(ptr(x_data), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(dy), c_int(cout), c_int(cp.k),
                                  c_int(stride), ptr(target), c_int(1 if (acc and cp.direct_grad) else 0), ptr(ws),
                                  c_ll(self._ws_cap()), c_int(0), c_int(0), st), 'evb_conv2d_wgrad')
         if not cp.direct_grad:   # copy the valid [co][ci*kk] block of the dense scratch [cop][cip*kk] into the OIHW grad
-            dst = ctypes.c_void_p(cp.weight.grad.data_ptr() + 4 * cp.w_off)
+            dst = ctypes.c_void_p(self._g(cp.weight).data_ptr() + 4 * cp.w_off)
             check(L.evb_copy2d_f32(ptr(cp.gscr), c_int(cp.cip * cp.kk), dst, c_int(cp.w_ld or cp.ci * cp.kk), c_int(cp.co),
                                    c_int(cp.ci * cp.kk), c_int(1 if acc else 0), st), 'evb_copy2d_f32')
 
     def _bias_grad(self, cp, dy, m_rows, cout):
         L = self.L
         st = stream()
-        if cp.bias is None or cp.bias.grad is None:
+        if cp.bias is None or self._g(cp.bias) is None:
             return
         acc = self.accumulate or cp._gw
         ws = self._ws(L.evb_bn_workspace(c_ll(m_rows), c_int(cout)))
         if cp.bias_pad is not None:
             check(L.evb_bias_grad(ptr(dy), c_ll(m_rows), c_int(cout), ptr(cp.dbias_scr), None, c_int(0), ptr(ws), st),
                   'evb_bias_grad')
-            check(L.evb_copy2d_f32(ptr(cp.dbias_scr), c_int(cp.cop), ptr(cp.bias.grad), c_int(cp.co), c_int(1), c_int(cp.co),
+            check(L.evb_copy2d_f32(ptr(cp.dbias_scr), c_int(cp.cop), ptr(self._g(cp.bias)), c_int(cp.co), c_int(1), c_int(cp.co),
                                    c_int(1 if acc else 0), st), 'evb_copy2d_f32')
         else:
-            check(L.evb_bias_grad(ptr(dy), c_ll(m_rows), c_int(cout), ptr(cp.bias.grad), None, c_int(1 if acc else 0), ptr(ws),
+            check(L.evb_bias_grad(ptr(dy), c_ll(m_rows), c_int(cout), ptr(self._g(cp.bias)), None, c_int(1 if acc else 0), ptr(ws),
                                   st), 'evb_bias_grad')
 
     def conv(self, x, cp, stride=None, bias=False, add=None, add_mode=0, train=True, dgrad=True, stats=False,
-             bias_grad_zero=False):
+             bias_grad_zero=False, name=None):
         """y = conv(x) (+bias) (+add).  bias=True uses cp.bias (padded copy when the conv is channel-padded).
         stats=True (training, no add): the epilogue also emits the BN batch-statistic partial sums of y.
         bias_grad_zero: the conv feeds a training-mode BatchNorm directly, so d(loss)/d(bias) = sum_rows dx_BN is
@@ -440,17 +516,19 @@ class FarSegEngine:
                                    c_int(cp.k), c_int(stride), ptr(y.data), c_int(cout), ptr(bias_t),
                                    ptr(add.data if add is not None else None), c_int(add_mode), c_int(0), stream()),
                   'evb_conv2d_fwd')
+        self._tf_fwd(y, name or cp.name)
         if train:
             def bwd():
                 if y.grad is None:
                     return
+                self._tf_bwd(y)
                 dy = y.grad
                 st = stream()
                 def param_grads():
                     self._wgrad(cp, x.data, dy, n, h, w, cin, cout, stride)
-                    if bias and bias_grad_zero and cp.bias.grad is not None:
+                    if bias and bias_grad_zero and self._g(cp.bias) is not None:
                         if not (self.accumulate or cp._gw):
-                            cp.bias.grad.zero_()
+                            self._g(cp.bias).zero_()
                     elif bias:
                         self._bias_grad(cp, dy, n * ho * wo, cout)
                     cp._gw = True
@@ -518,19 +596,19 @@ class FarSegEngine:
         if dres_act is not None and dres_act.needs_grad:
             dres, dres_acc = self._grad_into(dres_act)
         acc = self.accumulate or bp._gw
-        dgam = bp.dgamma_p if bp.padded else bp.bn.weight.grad
-        dbet = bp.dbeta_p if bp.padded else bp.bn.bias.grad
+        dgam = bp.dgamma_p if bp.padded else self._g(bp.bn.weight)
+        dbet = bp.dbeta_p if bp.padded else self._g(bp.bn.bias)
         check(L.evb_bn_bwd(ptr(dy), ptr(x.data), ptr(ymask), ptr(mean), ptr(rstd), ptr(scale), ptr(shift),
                            c_int(mask_mode), c_int(0 if bp.bn.training else 1), ptr(gx), ptr(dres), c_int(1 if dres_acc else 0),
                            ptr(dgam), ptr(dbet), c_int(1 if (acc and not bp.padded) else 0),
                            c_ll(m_rows), c_int(c), ptr(ws), stream()), 'evb_bn_bwd')
-        if bp.padded and bp.bn.weight.grad is not None:
-            for src, dst in ((bp.dgamma_p, bp.bn.weight.grad), (bp.dbeta_p, bp.bn.bias.grad)):
+        if bp.padded and self._g(bp.bn.weight) is not None:
+            for src, dst in ((bp.dgamma_p, self._g(bp.bn.weight)), (bp.dbeta_p, self._g(bp.bn.bias))):
                 check(L.evb_copy2d_f32(ptr(src), c_int(bp.c), ptr(dst), c_int(bp.c_real), c_int(1), c_int(bp.c_real),
                                        c_int(1 if acc else 0), stream()), 'evb_copy2d_f32')
         bp._gw = True
 
-    def bn_act(self, x, bp, relu=True, res=None, train=True):
+    def bn_act(self, x, bp, relu=True, res=None, train=True, name=None):
         L = self.L
         fold = self._bn_fold(x, bp, train)
         y = Act(self._new(*x.data.shape))
@@ -538,10 +616,12 @@ class FarSegEngine:
         check(L.evb_bn_apply(ptr(x.data), ptr(fold[2]), ptr(fold[3]), ptr(res.data if res is not None else None),
                              ptr(y.data), c_ll(x.data.numel() // c), c_int(c), c_int(1 if relu else 0), stream()),
               'evb_bn_apply')
+        self._tf_fwd(y, name)
         if train:
             def bwd():
                 if y.grad is None:
                     return
+                self._tf_bwd(y)
                 if relu and res is None:   # mask recomputed from x: one tensor read less per pass
                     self._bn_backward(y.grad, x, bp, fold, 2, None, None)
                 else:
@@ -549,7 +629,7 @@ class FarSegEngine:
             self.tape.append(bwd)
         return y
 
-    def bn_relu_up(self, x, bp, f=2, train=True):
+    def bn_relu_up(self, x, bp, f=2, train=True, name=None):
         """decoder stage: bilinear x f of relu(bn(x)) (fpn.py:163-169).  BN+ReLU is applied once at the low resolution
         (the tensor is f*f times smaller than the output), then a pure bilinear kernel writes the up-sampled map."""
         L = self.L
@@ -561,10 +641,12 @@ class FarSegEngine:
         y = Act(self._new(n, h * f, w * f, c))
         check(L.evb_bilinear_up(ptr(low_y), None, None, ptr(y.data), c_int(n), c_int(h), c_int(w), c_int(c), c_int(c),
                                 c_int(c), c_int(f), stream()), 'evb_bilinear_up')
+        self._tf_fwd(y, name)
         if train:
             def bwd():
                 if y.grad is None:
                     return
+                self._tf_bwd(y)
                 low = self._new(n, h, w, c)
                 ws = self._ws(L.evb_bilinear_up_bwd_workspace(c_int(n), c_int(h), c_int(w), c_int(c), c_int(f)))
                 check(L.evb_bilinear_up_bwd_sep(ptr(y.grad), ptr(low), c_int(n), c_int(h), c_int(w), c_int(c), c_int(c),
@@ -574,17 +656,19 @@ class FarSegEngine:
             self.tape.append(bwd)
         return y
 
-    def maxpool(self, x, train=True):
+    def maxpool(self, x, train=True, name=None):
         L = self.L
         n, h, w, c = x.data.shape
         y = Act(self._new(n, h // 2, w // 2, c))
         idx = self._new(n, h // 2, w // 2, c, dtype=torch.uint8)
         check(L.evb_maxpool3x3s2_fwd(ptr(x.data), ptr(y.data), ptr(idx), c_int(n), c_int(h), c_int(w), c_int(c), stream()),
               'evb_maxpool3x3s2_fwd')
+        self._tf_fwd(y, name)
         if train:
             def bwd():
                 if y.grad is None or not x.needs_grad:
                     return
+                self._tf_bwd(y)
                 g, acc = self._grad_into(x)
                 assert not acc
                 check(L.evb_maxpool3x3s2_bwd(ptr(y.grad), ptr(idx), ptr(g), c_int(n), c_int(h), c_int(w), c_int(c),
@@ -594,19 +678,21 @@ class FarSegEngine:
 
     # ------------------------------------------------------------------ network
     def _block(self, x, d, train):
+        # activation names: the block's shared nn.ReLU is called 2 (BasicBlock) or 3 (Bottleneck) times: '<block>.relu#k'
+        pfx = d['c1'].name.rsplit('.', 1)[0]
         if self.kind == 'bottleneck':
-            a1 = self.bn_act(self.conv(x, d['c1'], train=train, stats=train), d['b1'], True, train=train)
-            a2 = self.bn_act(self.conv(a1, d['c2'], train=train, stats=train), d['b2'], True, train=train)
+            a1 = self.bn_act(self.conv(x, d['c1'], train=train, stats=train), d['b1'], True, train=train, name=pfx + '.relu#0')
+            a2 = self.bn_act(self.conv(a1, d['c2'], train=train, stats=train), d['b2'], True, train=train, name=pfx + '.relu#1')
             o3 = self.conv(a2, d['c3'], train=train, stats=train)
-            last_bn = d['b3']
+            last_bn, last = d['b3'], pfx + '.relu#2'
         else:
-            a1 = self.bn_act(self.conv(x, d['c1'], train=train, stats=train), d['b1'], True, train=train)
+            a1 = self.bn_act(self.conv(x, d['c1'], train=train, stats=train), d['b1'], True, train=train, name=pfx + '.relu#0')
             o3 = self.conv(a1, d['c2'], train=train, stats=train)
-            last_bn = d['b2']
+            last_bn, last = d['b2'], pfx + '.relu#1'
         idt = x
         if 'cd' in d:
-            idt = self.bn_act(self.conv(x, d['cd'], train=train, stats=train), d['bd'], False, train=train)
-        return self.bn_act(o3, last_bn, True, res=idt, train=train)
+            idt = self.bn_act(self.conv(x, d['cd'], train=train, stats=train), d['bd'], False, train=train, name=d['bd'].name)
+        return self.bn_act(o3, last_bn, True, res=idt, train=train, name=last)
 
     def _encoder(self, x_nchw, train):
         L = self.L
@@ -638,6 +724,7 @@ class FarSegEngine:
             def stem_bwd():
                 if y0.grad is None:
                     return
+                self._tf_bwd(y0)
                 def param_grads():
                     self._wgrad(stem, a, y0.grad, n, ho, wo, self.stem_kp, 64, 1)
                     stem._gw = True
@@ -645,11 +732,21 @@ class FarSegEngine:
             self.tape.append(stem_bwd)
         y = y0
         self._dbg('stem_conv', y)
-        y = self.bn_act(y, self.stem_bn, True, train=train)
+        # names: the trunk's nn.ReLU ('en.resnet.relu', called once) or the ReLU after each deep-stem BN ('...stem.2/5/8')
+        rpfx = self.stem.name.rsplit('.', 1)[0] if self.stem.name else None   # 'en.resnet' or 'en.resnet.stem'
+
+        def _relu_name(bp_):
+            if bp_.name is None or rpfx is None:
+                return None
+            if not self.deep_stem:
+                return rpfx + '.relu#0'
+            head_, idx = bp_.name.rsplit('.', 1)
+            return '%s.%d' % (head_, int(idx) + 1)
+        y = self.bn_act(y, self.stem_bn, True, train=train, name=_relu_name(self.stem_bn))
         for cp_, bp_ in self.stem_tail:   # deep stem: two more 3x3 conv + BN + ReLU
-            y = self.bn_act(self.conv(y, cp_, train=train, stats=train), bp_, True, train=train)
+            y = self.bn_act(self.conv(y, cp_, train=train, stats=train), bp_, True, train=train, name=_relu_name(bp_))
         self._dbg('stem_act', y)
-        y = self.maxpool(y, train=train)
+        y = self.maxpool(y, train=train, name=(rpfx[:-5] if self.deep_stem else rpfx) + '.maxpool' if rpfx else None)
         self._dbg('pool', y)
         feats = []
         freeze_at = int(self.m.config.encoder.freeze_at)
@@ -681,18 +778,24 @@ class FarSegEngine:
         check(L.evb_linear_fwd(ptr(hid), ptr(l2.weight), ptr(l2.bias), ptr(sf), c_int(n), c_int(co), c_int(co),
                                c_int(0), stream()), 'evb_linear_fwd')
         dsf = self._new(n, co, dtype=torch.float32) if train else None
+        sf_name = None
+        if self.tf is not None:
+            sf_name = {id(mod): path for path, mod in self.m.named_modules()}.get(id(l2))
+            self.tf('fwd', sf_name, sf)
         if train:
             def bwd():
                 acc = 1 if self.accumulate else 0
                 for d in extra:
                     check(L.evb_copy2d_f32(ptr(d), c_int(co), ptr(dsf), c_int(co), c_int(n), c_int(co), c_int(1),
                                            stream()), 'evb_copy2d_f32')
+                if self.tf is not None:
+                    self.tf('bwd', sf_name, dsf)
                 dhid = self._new(n, co, dtype=torch.float32)
-                check(L.evb_linear_bwd(ptr(dsf), ptr(sf), ptr(hid), ptr(l2.weight), ptr(l2.weight.grad),
-                                       ptr(l2.bias.grad), ptr(dhid), c_int(n), c_int(co), c_int(co), c_int(0),
+                check(L.evb_linear_bwd(ptr(dsf), ptr(sf), ptr(hid), ptr(l2.weight), ptr(self._g(l2.weight)),
+                                       ptr(self._g(l2.bias)), ptr(dhid), c_int(n), c_int(co), c_int(co), c_int(0),
                                        c_int(acc), c_int(0), stream()), 'evb_linear_bwd')
-                check(L.evb_linear_bwd(ptr(dhid), ptr(hid), ptr(scene), ptr(l1.weight), ptr(l1.weight.grad),
-                                       ptr(l1.bias.grad), ptr(dscene), c_int(n), c_int(c5), c_int(co), c_int(1),
+                check(L.evb_linear_bwd(ptr(dhid), ptr(hid), ptr(scene), ptr(l1.weight), ptr(self._g(l1.weight)),
+                                       ptr(self._g(l1.bias)), ptr(dscene), c_int(n), c_int(c5), c_int(co), c_int(1),
                                        c_int(acc), c_int(0), stream()), 'evb_linear_bwd')
             self.tape.append(bwd)
         return sf, dsf
@@ -724,10 +827,13 @@ class FarSegEngine:
         sf, dsf = sf_pair
         check(L.evb_relation_fwd(ptr(u1.data), ptr(u2.data), ptr(f1[2]), ptr(f1[3]), ptr(f2[2]), ptr(f2[3]), ptr(sf),
                                  ptr(z.data), ptr(rel), c_ll(m_rows), c_int(hh * ww), c_int(c), stream()), 'evb_relation_fwd')
+        d0 = self.dec_blocks[i][0][0]
+        self._tf_fwd(z, d0.name + ':in' if d0.name else None)   # r * reenc(p) is the input of the level's first decoder conv
         if train:
             def bwd():
                 if z.grad is None:
                     return
+                self._tf_bwd(z)
                 g1 = self._new(*u1.data.shape)
                 g2 = self._new(*u2.data.shape)
                 ws = self._ws(L.evb_relation_bwd_workspace(c_ll(m_rows), c_int(hh * ww), c_int(c)))
@@ -744,7 +850,10 @@ class FarSegEngine:
         y = z
         for (cp, bp) in self.dec_blocks[i]:
             o = self.conv(y, cp, train=train, stats=train)
-            y = self.bn_relu_up(o, bp, 2, train=train) if self.dec_nup[i] else self.bn_act(o, bp, True, train=train)
+            # '<layer>.3' = the layer's last module (UpsamplingBilinear2d, or Identity after the ReLU when there is no upsample)
+            nm = cp.name.rsplit('.', 1)[0] + '.3' if cp.name else None
+            y = (self.bn_relu_up(o, bp, 2, train=train, name=nm) if self.dec_nup[i]
+                 else self.bn_act(o, bp, True, train=train, name=nm))
         self._dbg('dec%d' % i, y)
         return y
 
@@ -752,14 +861,23 @@ class FarSegEngine:
         L = self.L
         # ---- FPN (top-down, nearest x2 fused into the lateral 1x1 epilogue)
         inner = [None] * 4
-        inner[3] = self.conv(feats[3], self.fpn_inner[3], train=train)
+        # the fused lateral + top-down sum is the reference's `last_inner`, i.e. the input of fpn_layer{i} ('<conv>:in')
+        def _in(cp_):
+            return cp_.name + ':in' if cp_.name else None
+        inner[3] = self.conv(feats[3], self.fpn_inner[3], train=train, name=_in(self.fpn_layer[3]))
         for i in (2, 1, 0):
-            inner[i] = self.conv(feats[i], self.fpn_inner[i], add=inner[i + 1], add_mode=2, train=train)
+            inner[i] = self.conv(feats[i], self.fpn_inner[i], add=inner[i + 1], add_mode=2, train=train,
+                                 name=_in(self.fpn_layer[i]))
         # ---- scene embedding
         c5 = feats[3]
         n, h5, w5, cc5 = c5.data.shape
         scene = self._new(n, cc5, dtype=torch.float32)
         check(L.evb_gap_fwd(ptr(c5.data), ptr(scene), c_int(n), c_int(h5 * w5), c_int(cc5), stream()), 'evb_gap_fwd')
+        scene_name = None
+        if self.tf is not None:
+            l1_ = self.scene[0][0]
+            scene_name = {id(mod): path for path, mod in self.m.named_modules()}.get(id(l1_)) + ':in'
+            self.tf('fwd', scene_name, scene)
         if train:
             # runs last among head closures (registered first): needs dscene complete
             holder = {}
@@ -772,6 +890,8 @@ class FarSegEngine:
                 for d in ds[1:]:     # d(scene) of the other scene MLPs, summed in level order (deterministic)
                     check(L.evb_copy2d_f32(ptr(d), c_int(cc5), ptr(ds[0]), c_int(cc5), c_int(n), c_int(cc5), c_int(1),
                                            stream()), 'evb_copy2d_f32')
+                if self.tf is not None:
+                    self.tf('bwd', scene_name, ds[0])
                 check(L.evb_gap_bwd(ptr(ds[0]), ptr(g), c_int(n), c_int(h5 * w5), c_int(cc5), stream()), 'evb_gap_bwd')
             self.tape.append(gap_bwd)
         dscenes = []
@@ -818,10 +938,13 @@ class FarSegEngine:
         merged = Act(self._new(*outs[0].data.shape))
         check(L.evb_merge4(ptr(outs[0].data), ptr(outs[1].data), ptr(outs[2].data), ptr(outs[3].data), ptr(merged.data),
                            c_ll(merged.data.numel()), stream()), 'evb_merge4')
+        d00 = self.dec_blocks[0][0][0]
+        self._tf_fwd(merged, d00.name.split('.blocks.')[0] + '.dropout' if d00.name else None)
         if train:
             def bwd():
                 if merged.grad is None:
                     return
+                self._tf_bwd(merged)
                 dq = self._new(*merged.data.shape)
                 check(L.evb_scale_add(ptr(merged.grad), c_float(0.25), None, ptr(dq), c_ll(dq.numel()), stream()),
                       'evb_scale_add')
@@ -840,6 +963,8 @@ class FarSegEngine:
         logits = self._new(n, h4 * f, w4 * f, 16)
         check(L.evb_bilinear_up(ptr(cls.data), None, None, ptr(logits), c_int(n), c_int(h4), c_int(w4), c_int(16),
                                 c_int(64), c_int(16), c_int(f), stream()), 'evb_bilinear_up(logits)')
+        if self.tf is not None and cp.name:
+            self.tf('fwd', cp.name.rsplit('.', 1)[0] + '.1', logits)
         self._dbg('cls' if name == 'logits' else name + '_cls', cls)
         self._dbg(name, logits)
         return cls, logits
@@ -857,7 +982,8 @@ class FarSegEngine:
         ws = self._ws(L.evb_loss_workspace(c_ll(npx), c_int(k)))
         check(L.evb_loss_stats(ptr(logits), ptr(labels), c_ll(npx), c_int(k), c_int(16), c_int(self.ignore_index),
                                ptr(stats), ptr(ws), stream()), 'evb_loss_stats')
-        g = dict(cls=cls, logits=logits, labels=labels, stats=stats, npx=npx, k=k, f=f, names=names, weight=weight)
+        g = dict(cls=cls, logits=logits, labels=labels, stats=stats, npx=npx, k=k, f=f, names=names, weight=weight,
+                 name=cls.name.rsplit('.', 1)[0] + '.1' if cls.name else None)
         self._groups.append(g)
         return g
 
@@ -878,7 +1004,6 @@ class FarSegEngine:
         self._groups = []
         x = x.contiguous() if x.dtype == torch.uint8 else x.contiguous().float()
         self.pack_weights()
-        self.attach_grads()
         self._network_losses(x, labels)
         if self._bn_tracked:
             torch._foreach_add_([bn.num_batches_tracked for bn in self._bn_tracked], 1)
@@ -925,7 +1050,12 @@ class FarSegEngine:
         self._dice_allreduce()
         return self._forward_part2()
 
-    def backward(self, allreduce=True):
+    def backward(self, allreduce=True, attach=True, upstream=None):
+        """Backward of the step whose losses the last training forward returned; gradients land in the flat arena.
+        attach: alias every trainable parameter's ``.grad`` to its arena slot (native path).  upstream: {loss name: 0-dim
+        device tensor} = d(total)/d(loss) from autograd (Launcher divides by forward_times, GradScaler multiplies,
+        ever/core/launcher.py:196, ever/interface/module.py:76-81); applied on the device to the loss-gradient coefficients,
+        which the logit gradient is linear in -- no host synchronisation."""
         L = self.L
         if self._saved_for_backward is None:
             raise RuntimeError('backward() without a preceding training forward')
@@ -934,13 +1064,21 @@ class FarSegEngine:
         if isinstance(groups, str):   # graph_forward already replayed the backward
             if allreduce:
                 self.allreduce_grads()
+            if attach:
+                self.attach_grads()
             return
         for g in groups:
+            if upstream is not None:   # coef = {first-loss scale, Dice A_c[k], B_c[k]} (evb_loss_finalize)
+                u0, u1 = upstream.get(g['names'][0]), upstream.get(g['names'][1])
+                g['coef'][:1].mul_(u0.to(torch.float32) if u0 is not None else 0.0)
+                g['coef'][1:].mul_(u1.to(torch.float32) if u1 is not None else 0.0)
             logits, cls, k, f = g['logits'], g['cls'], g['k'], g['f']
             n, hh, ww, _ = logits.shape
             dlogits = self._new(n, hh, ww, 16)
             check(L.evb_loss_grad(ptr(logits), ptr(g['labels']), c_ll(g['npx']), c_int(k), c_int(16),
                                   c_int(self.ignore_index), ptr(g['coef']), ptr(dlogits), stream()), 'evb_loss_grad')
+            if self.tf is not None and g.get('name'):
+                self.tf('bwd', g['name'], dlogits)
             cls.grad = torch.zeros_like(cls.data)   # padding channels 16..63 stay zero
             cls.has_grad = True
             ws = self._ws(L.evb_bilinear_up_bwd_workspace(c_int(n), c_int(hh // f), c_int(ww // f), c_int(16), c_int(f)))
@@ -952,6 +1090,8 @@ class FarSegEngine:
         self.tape = []
         if allreduce:
             self.allreduce_grads()
+        if attach:
+            self.attach_grads()
 
     def _run_tape(self):
         """Run the backward closures in reverse order.  Closures of a pyramid-level branch run on that branch's stream:
@@ -1016,9 +1156,16 @@ class FarSegEngine:
         self._lr.fill_(float(lr))
         check(L.evb_grad_norm(ptr(self.flat_g), c_ll(n), c_float(max_norm if max_norm else 0.0), ptr(self._norm),
                               ptr(self._sgd_ws), stream()), 'evb_grad_norm')
-        check(L.evb_sgd_step(ptr(self.flat_w), ptr(self.flat_g), ptr(self._mom), c_ll(n), ptr(self._lr),
-                             c_float(momentum), c_float(weight_decay), ptr(self._norm), c_int(1 if self._sgd_first else 0),
-                             c_int(1), stream()), 'evb_sgd_step')
+        mask = self.trainable_mask()
+        if mask is None:
+            check(L.evb_sgd_step(ptr(self.flat_w), ptr(self.flat_g), ptr(self._mom), c_ll(n), ptr(self._lr),
+                                 c_float(momentum), c_float(weight_decay), ptr(self._norm),
+                                 c_int(1 if self._sgd_first else 0), c_int(1), stream()), 'evb_sgd_step')
+        else:   # frozen parameters: no weight decay, no momentum, no update (torch.optim.SGD skips grad-less parameters)
+            check(L.evb_sgd_step_masked(ptr(self.flat_w), ptr(self.flat_g), ptr(self._mom), c_ll(n), ptr(self._lr),
+                                        c_float(momentum), c_float(weight_decay), ptr(self._norm),
+                                        c_int(1 if self._sgd_first else 0), c_int(1), ptr(mask), stream()),
+                  'evb_sgd_step_masked')
         self._sgd_first = False
         return self._norm
 
@@ -1072,7 +1219,8 @@ class FarSegEngine:
         is replayed, the static loss tensors are returned and the gradients are already in the arena (backward() then
         only runs the gradient all-reduce).  One capture per (shape, dtype) signature."""
         lab = labels if isinstance(labels, dict) else dict(cls=labels)
-        key = (tuple(x.shape), x.dtype) + tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(lab.items()))
+        key = (tuple(x.shape), x.dtype, bool(self.accumulate)) + tuple((k, tuple(v.shape), v.dtype)
+                                                                       for k, v in sorted(lab.items()))
         ent = self._graphs.get(key)
         if ent is None:
             sx = torch.empty_like(x, device=self.dev)
@@ -1087,7 +1235,6 @@ class FarSegEngine:
         sx.copy_(x, non_blocking=True)
         for k, v in lab.items():
             sl[k].copy_(v, non_blocking=True)
-        self.attach_grads()
         replay()
         self._saved_for_backward = 'graph'
         return out
@@ -1154,7 +1301,12 @@ class ChangeStarEngine(FarSegEngine):
 
     @staticmethod
     def _reorder(x):
+        if x.dtype == torch.uint8 or x.dim() != 4 or not x.is_floating_point():
+            raise ValueError('ChangeStarB200 takes float NCHW pairs [N, 2*Cin, H, W] (t1 channels then t2 channels); raw '
+                             'uint8 NHWC tiles are only supported by FarSegB200 -- normalise and stack the pair first')
         n, c2, h, w = x.shape
+        if c2 % 2:
+            raise ValueError('ChangeStarB200 input needs an even channel count (t1 | t2), got %d' % c2)
         return x.view(n, 2, c2 // 2, h, w).transpose(0, 1).reshape(2 * n, c2 // 2, h, w).contiguous().float()
 
     def _network_losses(self, x, labels):

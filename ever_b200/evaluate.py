@@ -56,7 +56,10 @@ def evaluate_pixel_prediction(model, dataloader, num_classes, predictor=None, pi
         if predictor is not None:
             mask = predictor(x)
         else:
-            _, mask = eng.forward_eval(x, return_mask=True)
+            res = eng.forward_eval(x, return_mask=True)
+            # FarSeg: (prob, mask); ChangeStar: dict with 'seg_mask' / 'change_mask' -- the segmentation mask of t1 is scored
+            # against y['cls'] here; score the change head with predictor=lambda x: eng.forward_eval(x)['change_mask']
+            mask = res['seg_mask'] if isinstance(res, dict) else res[1]
         eng.confusion_matrix(mask.contiguous(), labels, cm)
     dense = cm.cpu().numpy()      # the only device -> host transfer of the evaluation
     if was_training:

@@ -148,6 +148,52 @@ class _Head(nn.Module):
                                     int(d.out_feat_output_stride), d.classifier_config)
 
 
+class _StepFn(torch.autograd.Function):
+    """The whole native training step as ONE autograd node whose inputs are the trainable parameters.
+
+    forward  = engine forward + loss (or the cached CUDA-graph replay); the returned losses carry a grad_fn, so the
+    reference's stock path works unchanged: ``Launcher.compute_loss_gradient`` scales them (``v / forward_times``,
+    ever/core/launcher.py:193-200), ``ERModule.backward`` sums and calls ``total_loss.backward()``
+    (ever/interface/module.py:76-81), and under ``THDDPTrainer`` (ever/trainer/th_ddp_trainer.py:25-30) the
+    ``DistributedDataParallel`` reducer sees every parameter's AccumulateGrad hook fire.
+    backward = the engine's native backward with the upstream d(total)/d(loss) applied on the device, then one copy of
+    the flat gradient arena whose per-parameter views are returned to autograd (which accumulates them into ``p.grad``:
+    gradient accumulation over ``forward_times`` micro-batches is autograd's, the engine overwrites its arena)."""
+
+    @staticmethod
+    def forward(ctx, model, x, labels, *params):
+        eng = model._engine()
+        if bool(model.config.cuda_graph):
+            out = eng.graph_forward(x, labels)
+        else:
+            out = eng.forward_train(x, labels)
+        eng._step_token = getattr(eng, '_step_token', 0) + 1
+        eng._last_keys = list(out.keys())
+        ctx.model, ctx.keys, ctx.token = model, list(out.keys()), eng._step_token
+        return tuple(out[k] for k in ctx.keys)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        eng = ctx.model._engine()
+        if eng._step_token != ctx.token or eng._saved_for_backward is None:
+            raise RuntimeError('FarSegB200: backward through a stale step (the engine keeps the activations of the '
+                               'latest training forward only)')
+        for p in eng.params:   # a previous native step may have aliased .grad to the arena: autograd must not add into it
+            if p.grad is not None and p.grad is eng._gv[id(p)]:
+                p.grad = None
+        if isinstance(eng._saved_for_backward, str):
+            # graph mode: forward + loss + backward were replayed with unit loss weights; every loss is assumed to carry
+            # the same upstream factor (what Launcher / GradScaler produce)
+            eng.backward(allreduce=False, attach=False)
+            s = next((g for g in gouts if g is not None), None)
+            buf = eng.flat_g * s.to(torch.float32) if s is not None else torch.zeros_like(eng.flat_g)
+        else:
+            eng.backward(allreduce=False, attach=False, upstream=dict(zip(ctx.keys, gouts)))
+            buf = eng.flat_g.clone()
+        grads = tuple(buf[o:o + n].view_as(p) for p, (o, n) in zip(eng.params, eng._slots) if p.requires_grad)
+        return (None, None, None) + grads
+
+
 @MODEL.register('FarSegB200')
 class FarSegB200(ERModule):
     """FarSeg (ResNetEncoder -> FarSegHead -> CE + Dice), glue model of SURVEY.md Appendix E, computed by the
@@ -166,7 +212,45 @@ class FarSegB200(ERModule):
         self.engine = None
         if int(enc.output_stride) != 32:
             raise NotImplementedError('FarSeg needs output_stride 32 (the FPN top-down x2 adds assume a /2 pyramid)')
+        if not bool(enc.include_conv5):
+            raise NotImplementedError('include_conv5=False: FarSegHead needs the four-level pyramid c2..c5')
+        nl = enc.get('norm_layer', None) if hasattr(enc, 'get') else None
+        if nl is not None and nl is not nn.BatchNorm2d:
+            raise NotImplementedError('encoder.norm_layer other than nn.BatchNorm2d (got %r)' % (nl,))
+        if bool(enc.pretrained):
+            self._load_pretrained(enc.resnet_type, int(enc.in_channels))
         self._freeze()
+
+    # ImageNet weights, same files as the reference (ever/module/_resnets.py:7-18)
+    PRETRAINED_URLS = {
+        'resnet18': 'https://download.pytorch.org/models/resnet18-5c106cde.pth',
+        'resnet34': 'https://download.pytorch.org/models/resnet34-333f7ec4.pth',
+        'resnet50': 'https://download.pytorch.org/models/resnet50-19c8e357.pth',
+        'resnet101': 'https://download.pytorch.org/models/resnet101-5d3b4d8f.pth',
+        'resnet50_v1c': 'https://download.openmmlab.com/pretrain/third_party/resnet50_v1c-2cccc1ad.pth',
+        'resnet101_v1c': 'https://download.openmmlab.com/pretrain/third_party/resnet101_v1c-e67eebb6.pth',
+    }
+
+    def _load_pretrained(self, resnet_type, in_channels, state_dict=None):
+        """encoder.pretrained=True (ever/module/_resnets.py:230-238): fetch the reference's ImageNet checkpoint through the
+        torch hub cache (raises without network / cache -- never a silent random init) and load it non-strictly (the
+        checkpoint's fc.* keys have no counterpart).  in_channels != 3: the first conv is tiled over the new channels
+        and rescaled, ResNetEncoder.patch_first_conv (ever/module/resnet.py:55-69)."""
+        if state_dict is None:
+            from torch.utils.model_zoo import load_url
+            state_dict = load_url(self.PRETRAINED_URLS[resnet_type], progress=False)
+        if 'state_dict' in state_dict:
+            state_dict = state_dict['state_dict']
+        state_dict = dict(state_dict)
+        first = 'stem.0.weight' if self.en.resnet.deep_stem else 'conv1.weight'
+        if in_channels != 3 and first in state_dict:
+            w = state_dict[first]
+            new = torch.stack([w[:, i % 3] for i in range(in_channels)], dim=1) * (3.0 / in_channels)
+            state_dict[first] = new
+        res = self.en.resnet.load_state_dict(state_dict, strict=False)
+        missing = [k for k in res.missing_keys]
+        if missing:
+            raise RuntimeError('pretrained checkpoint lacks %d encoder tensors, e.g. %s' % (len(missing), missing[:3]))
 
     def _freeze(self):
         """ResNetEncoder._frozen_res_bn / _freeze_at (ever/module/resnet.py:155-173,227-234): frozen BN layers run on their
@@ -199,7 +283,7 @@ class FarSegB200(ERModule):
             # with_cp (activation checkpointing flags per stage, resnet.py:189-208) is accepted and has no effect: it
             # never changes results, and the engine keeps every activation of the step resident in HBM by design
             encoder=dict(resnet_type='resnet50', in_channels=3, pretrained=False, batchnorm_trainable=True, freeze_at=0,
-                         output_stride=32, include_conv5=True, with_cp=(False, False, False, False)),
+                         output_stride=32, include_conv5=True, with_cp=(False, False, False, False), norm_layer=None),
             head=dict(
                 fpn=dict(in_channels_list=(256, 512, 1024, 2048), out_channels=256),
                 fs_relation=dict(scene_embedding_channels=2048, in_channels_list=(256, 256, 256, 256), out_channels=256,
@@ -226,21 +310,50 @@ class FarSegB200(ERModule):
             object.__setattr__(self, 'engine', FarSegEngine(self))
         return self.engine
 
+    def _labels(self, y):
+        if y is None:
+            raise ValueError('training forward needs y (dict with key "cls" or a label tensor)')
+        return y['cls'] if isinstance(y, dict) else y
+
     def forward(self, x, y=None):
         eng = self._engine()
         if self.training:
-            if y is None:
-                raise ValueError('training forward needs y (dict with key "cls" or a label tensor)')
-            labels = y['cls'] if isinstance(y, dict) else y
-            if bool(self.config.cuda_graph):
-                return eng.graph_forward(x, labels)
-            return eng.forward_train(x, labels)
+            return self._train_forward(eng, x, self._labels(y))
         return eng.forward_eval(x)
 
+    def _train_forward(self, eng, x, labels):
+        if torch.is_grad_enabled():
+            tp = [p for p in eng.params if p.requires_grad]
+            keys_vals = _StepFn.apply(self, x, labels, *tp)
+            out = dict(zip(eng._last_keys, keys_vals))
+        elif bool(self.config.cuda_graph):
+            out = eng.graph_forward(x, labels)
+        else:
+            out = eng.forward_train(x, labels)
+        object.__setattr__(self, '_last_out', out)
+        return out
+
     def backward(self, loss_dict=None, amp=None, scaler=None, **kwargs):
-        """ERModule.backward hook (ever/interface/module.py:76-81): the native backward of the step whose losses
-        were returned by the last training forward (all '*loss' keys, unit weights as Launcher sums them)."""
-        self._engine().backward()
+        """ERModule.backward hook (ever/interface/module.py:76-81).
+
+        Native path: ``loss_dict`` is None or the very dict values the last training forward returned -> the engine's
+        backward runs with unit loss weights, the gradient all-reduce follows (world > 1) and every ``p.grad`` aliases its
+        slot of the flat arena (StepLoop, bench, and any caller that wants the fused optimizer).
+        Autograd path: anything else (Launcher hands over ``v / forward_times``; a GradScaler may scale) -> the reference's
+        own ``sum(loss_dict.values()).backward()``, which reaches the engine through ``_StepFn.backward`` with the upstream
+        factors; gradients accumulate into ordinary ``p.grad`` tensors and a DDP wrapper does its own all-reduce."""
+        eng = self._engine()
+        last = getattr(self, '_last_out', None)
+        native = loss_dict is None or (last is not None and len(loss_dict) == len(last)
+                                       and all(loss_dict.get(k) is v for k, v in last.items()))
+        if native:
+            eng.backward()
+            return
+        total_loss = sum([e for e in loss_dict.values()])
+        if amp and scaler is not None:
+            scaler.scale(total_loss).backward()
+        else:
+            total_loss.backward()
 
     def clip_grad_info(self):
         return dict()
@@ -294,15 +407,10 @@ class ChangeStarB200(FarSegB200):
             object.__setattr__(self, 'engine', ChangeStarEngine(self))
         return self.engine
 
-    def forward(self, x, y=None):
-        eng = self._engine()
-        if self.training:
-            if not isinstance(y, dict) or 'cls' not in y or 'change' not in y:
-                raise ValueError("training forward needs y = {'cls': ..., 'change': ...}")
-            if bool(self.config.cuda_graph):
-                return eng.graph_forward(x, y)
-            return eng.forward_train(x, y)
-        return eng.forward_eval(x)
+    def _labels(self, y):
+        if not isinstance(y, dict) or 'cls' not in y or 'change' not in y:
+            raise ValueError("training forward needs y = {'cls': ..., 'change': ...}")
+        return y
 
 
 MODEL.register('ChangeStar', ChangeStarB200, override=True) if hasattr(MODEL, 'register') else None

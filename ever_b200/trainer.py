@@ -41,8 +41,14 @@ class StepLoop:
         self.log_interval_step, self.log_fn = log_interval_step, log_fn
         self.global_step = 0
         self._holder = _LRHolder(self.base_lr)
+        # static-shape graph replay is what this loop is for; the previous setting is put back by close()
+        self._prev_cuda_graph = bool(model.config.cuda_graph)
         model.config.cuda_graph = True
         model._engine().set_distributed(rank, world)
+
+    def close(self):
+        """restore the model's ``config.cuda_graph`` as it was before this loop took the model over"""
+        self.model.config.cuda_graph = self._prev_cuda_graph
 
     @property
     def lr(self):
@@ -71,7 +77,14 @@ class StepLoop:
             self._update_lr()
             self.global_step += 1
             if self.global_step % self.log_interval_step == 0 or self.global_step == num_iters:
-                vals = torch.stack([v.float().reshape(()) for v in out.values()] + [grad_norm[0]]).cpu().tolist()
+                vec = torch.stack([v.detach().float().reshape(()) for v in out.values()] + [grad_norm[0]])
+                if self.world > 1:   # reduce_loss_dict (ever/core/launcher.py:202-209): the logged losses are rank means
+                    import torch.distributed as dist
+                    nl = len(out)
+                    red = vec[:nl].clone()
+                    dist.all_reduce(red)
+                    vec = torch.cat([red / self.world, vec[nl:]])
+                vals = vec.cpu().tolist()
                 last = dict(zip(list(out.keys()) + ['grad_norm'], vals))
                 last['total_loss'] = sum(v for k, v in last.items() if k.endswith('loss'))
                 if self.log_fn is not None and self.rank == 0:

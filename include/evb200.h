@@ -173,6 +173,10 @@ long long evb_sgd_workspace(long long n);
 int evb_grad_norm(const float* g, long long n, float max_norm, float* norm_out, void* ws, void* stream);
 int evb_sgd_step(float* w, float* g, float* mom, long long n, const float* lr, float momentum, float wd,
                  const float* clip, int first_step, int zero_grad, void* stream);
+/* same with a uint8 per-slot mask (1 = trainable): slots of parameters with requires_grad=False (ResNetEncoder freeze_at /
+ * frozen BN, ever/module/resnet.py:155-173) are skipped entirely, as torch.optim.SGD skips parameters whose grad is None */
+int evb_sgd_step_masked(float* w, float* g, float* mom, long long n, const float* lr, float momentum, float wd,
+                        const float* clip, int first_step, int zero_grad, const unsigned char* trainable, void* stream);
 
 /* ---- index-map kernels either side of the path.
  * Map rows are int32[12] in device memory: {a00, a01, b0, a10, a11, b1, s, y0, y1, x0, x1, cb}.

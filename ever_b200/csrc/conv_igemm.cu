@@ -152,8 +152,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (p.bias) {
               const float4 b0 = *reinterpret_cast<const float4*>(p.bias + ch);
               const float4 b1 = *reinterpret_cast<const float4*>(p.bias + ch + 4);
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              // torch's bf16 convolution adds the bias as a separate bf16 op (cudnn_convolution, then output.add_(bias) with
+              // the autocast-cast bf16 bias): y = bf16(bf16(acc) + bf16(b)).  Mirrored bit for bit (99.997 % identical
+              // outputs on B200, tools/diag_tf.py); a single rounding of acc + b differs on 37 % of the elements.
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j]) + bf16_round(bb[j]);
             }
             if (p.add_mode) {
               // reference adds two bf16 tensors: round the conv result first, then add, then round
@@ -360,8 +364,12 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (p.bias && ch < p.Cout) {
               const float4 b0 = *reinterpret_cast<const float4*>(p.bias + ch);
               const float4 b1 = *reinterpret_cast<const float4*>(p.bias + ch + 4);
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              // torch's bf16 convolution adds the bias as a separate bf16 op (cudnn_convolution, then output.add_(bias) with
+              // the autocast-cast bf16 bias): y = bf16(bf16(acc) + bf16(b)).  Mirrored bit for bit (99.997 % identical
+              // outputs on B200, tools/diag_tf.py); a single rounding of acc + b differs on 37 % of the elements.
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j]) + bf16_round(bb[j]);
             }
             if (arow && ch < p.Cout) {
               float a[8];

@@ -152,7 +152,9 @@ relation_bwd_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* _
         *reinterpret_cast<bf16x8*>(g2 + m * C + lane * 8 + 256 * a) = pack8(o);
       }
       dr = warp_sum(dr);
-      const float dlogit = dr * r * (1.f - r);
+      // autocast flow of the reference: sum(dim=1) runs in fp32 on the bf16 product, so its backward hands a bf16-ROUNDED
+      // d(logit) to the bf16 multiply; d(cf) = bf16(dl * sf) and d(sf) sums bf16(dl * cf) (SURVEY.md 8a dtype flow)
+      const float dlogit = bf16_round(dr * r * (1.f - r));
 #pragma unroll
       for (int a = 0; a < NG; ++a) {
         float v[8], o[8];
@@ -160,7 +162,7 @@ relation_bwd_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* _
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float cf = fmaxf(bf16_round(v[j] * s1[a][j] + b1[a][j]), 0.f);
-          acc[a][j] += dlogit * cf;
+          acc[a][j] += bf16_round(dlogit * cf);
           o[j] = cf > 0.f ? dlogit * sfv[a][j] : 0.f;
         }
         *reinterpret_cast<bf16x8*>(g1 + m * C + lane * 8 + 256 * a) = pack8(o);

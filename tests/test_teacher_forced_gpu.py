@@ -11,6 +11,7 @@ the reference's inputs by exactly the code the product runs, and must agree to <
 """
 import json
 import os
+import re
 
 import pytest
 import torch
@@ -21,6 +22,11 @@ from _helpers import RefCapture, TeacherForcing, rel_l2
 pytestmark = pytest.mark.gpu
 
 GATE = 1e-2
+# Conv2d(bias=True) -> training-mode BatchNorm2d of the FS-Relation encoders (ever/module/fs_relation.py:41-52)
+ZERO_BIAS = re.compile(r'head\.fs_relation\.(content_encoders|feature_reencoders)\.\d+\.0\.bias$')
+# (conv, BN, ReLU) module paths of the BatchNorm + ReLU in front of the max-pool
+STEM_BN = dict(plain=('en.resnet.conv1', 'en.resnet.bn1', 'en.resnet.relu#0'),
+               v1c=('en.resnet.stem.6', 'en.resnet.stem.7', 'en.resnet.stem.8'))
 
 
 def _build(resnet, k, dec, **opts):
@@ -99,12 +105,33 @@ def test_teacher_forced_step(case):
     grads = {}
     for name, p in pm.items():
         g_ref = pr[name].grad
-        if float(g_ref.norm()) < 1e-6 * gmax:
-            # conv bias directly before a training-mode BN: exactly zero in exact arithmetic; the reference holds rounding
-            # noise there, the engine writes zeros
-            assert float(p.grad.norm()) < 1e-4 * gmax, name
+        if ZERO_BIAS.match(name):
+            # conv bias directly before a training-mode BN: exactly zero in exact arithmetic (BN backward removes the
+            # per-channel mean of its input gradient).  The reference holds bf16 rounding noise there (1e-3 .. 1e-6 of the
+            # other gradients), the engine writes exact zeros
+            assert float(g_ref.norm()) < 2e-3 * gmax, (name, float(g_ref.norm()), gmax)
+            assert float(p.grad.norm()) == 0.0, name
             continue
         grads[name] = rel_l2(p.grad, g_ref)
+    # The BN in front of the max-pool: its d-gamma / d-beta are sums of the SPARSE max-pool gradient with a cancellation
+    # factor of ~400 (sum|g| / |sum g|); torch's own bf16 batch-norm backward is 1-2 % away from the exact sums there
+    # (tools/diag_tf.py: oracle vs fp64 1.8e-2, engine vs fp64 2e-8).  For these two tensors the engine is held to the
+    # fp64 recomputation from the reference's own captured tensors (<= 1e-3) instead of to the reference's noise.
+    conv_nm, bn_nm, relu_nm = STEM_BN['v1c' if resnet.endswith('_v1c') else 'plain']
+    xs = cap.fwd[conv_nm].double().requires_grad_(True)
+    gam = pr[bn_nm + '.weight'].detach().double().requires_grad_(True)
+    bet = pr[bn_nm + '.bias'].detach().double().requires_grad_(True)
+    F.relu(F.batch_norm(xs, None, None, gam, bet, True, 0.1, 1e-5)).backward(cap.bwd[relu_nm].double())
+    truth = {bn_nm + '.weight': gam.grad, bn_nm + '.bias': bet.grad}
+    stem_rep = {}
+    for nm, t in truth.items():
+        stem_rep[nm] = dict(engine_vs_fp64=rel_l2(pm[nm].grad, t), reference_vs_fp64=rel_l2(pr[nm].grad, t),
+                            engine_vs_reference=grads[nm])
+        assert stem_rep[nm]['engine_vs_fp64'] <= 1e-3, stem_rep
+        if grads[nm] > GATE:
+            assert stem_rep[nm]['reference_vs_fp64'] > 0.5 * grads[nm], stem_rep   # the distance IS the reference's error
+            grads.pop(nm)
+    print(json.dumps(dict(stem_bn_vs_fp64=stem_rep)))
     tag = '%s_k%d_%dx%dx%d' % (resnet, k, n, h, w)
     s = summarize(tf, grads, tag)
     assert not tf.missing, tf.missing[:5]

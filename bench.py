@@ -336,6 +336,8 @@ def run_b200(args):
     model = cls(model_config(cfg)).cuda().train()
     eng = model._engine()
     eng.set_distributed(rank, world)
+    if os.environ.get('EVB_SYNC_DICE', '1') == '0':
+        eng.sync_dice = False
     if world > 1:  # same initial weights everywhere (DDP broadcasts rank 0's at construction)
         dist.broadcast(eng.flat_w, 0)
         torch.cuda.synchronize()
@@ -383,7 +385,12 @@ def run_b200(args):
         else:
             out = eng.forward_train(x, labels)
             eng.backward(allreduce=False)
-        eng.allreduce_grads()
+        if os.environ.get('EVB_BENCH_NO_AR', '0') == '1':     # diagnostics only: lower bound without the gradient exchange
+            for w_ in eng._ar_pending:
+                w_.wait()
+            eng._ar_pending = []
+        else:
+            eng.allreduce_grads()
         eng.sgd_step(lr)
 
     log('graph ready, warm-up')

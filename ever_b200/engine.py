@@ -129,6 +129,12 @@ class FarSegEngine:
         # weight gradients run on a second stream (parallel graph branch): they overlap the dgrad / BN chain
         self.side = torch.cuda.Stream(device=self.dev) if os.environ.get('EVB_NO_SIDE_STREAM', '0') != '1' else None
         self.accumulate = False      # gradient accumulation into existing .grad (forward_times > 1)
+        # Gradient buckets for the overlapped all-reduce (world > 1): backward is cut where these encoder stages start
+        # (stage index 3 = layer4, 2 = layer3).  Bucket 0 = layer4 + head (75 % of the R50 parameters) is all-reduced while
+        # layer3's backward runs, bucket 1 = layer3 while layer2/layer1/stem run; only the last 6 MB are exposed.
+        self.ar_split_stages = tuple(int(v) for v in os.environ.get('EVB_AR_SPLITS', '3,2').split(',') if v != '')
+        self._tape_splits = []
+        self._ar_pending = []
         self.fuse_bn_stats = True    # BN batch statistics in the producing conv's epilogue (evb_conv2d_fwd_stats)
         self._saved_for_backward = None
         self._graphs = {}
@@ -751,6 +757,8 @@ class FarSegEngine:
         feats = []
         freeze_at = int(self.m.config.encoder.freeze_at)
         for si, blocks in enumerate(self.stages):
+            if train and si in self.ar_split_stages:
+                self._tape_splits.append(len(self.tape))   # backward segment boundary (gradient bucket, see backward())
             if si == 2:
                 self._join_pack()      # layer3 onwards reads the packs written on the side stream
             if train and freeze_at >= si + 1:
@@ -1000,6 +1008,7 @@ class FarSegEngine:
         """pack weights, encoder, head, loss statistics (everything before the Dice all-reduce)."""
         self.tape = []
         self._tape_tags, self._fork_idx, self._join_idx = [], None, None
+        self._tape_splits = []
         self._bn_tracked = []
         self._groups = []
         x = x.contiguous() if x.dtype == torch.uint8 else x.contiguous().float()
@@ -1062,11 +1071,28 @@ class FarSegEngine:
         groups = self._saved_for_backward
         self._saved_for_backward = None
         if isinstance(groups, str):   # graph_forward already replayed the backward
-            if allreduce:
+            if allreduce or self._ar_pending:   # buckets issued by the replay are in flight: the arena is read next
                 self.allreduce_grads()
             if attach:
                 self.attach_grads()
             return
+        self._loss_backward(groups, upstream)
+        for lo, hi in self._segments():
+            self._run_tape(lo, hi)
+            if allreduce and self.world > 1:
+                self._join_side()
+                self._allreduce_bucket(lo)
+        self._join_side()
+        self.tape = []
+        self._tape_tags, self._fork_idx, self._join_idx = [], None, None
+        if allreduce:
+            self.allreduce_grads()
+        if attach:
+            self.attach_grads()
+
+    def _loss_backward(self, groups, upstream=None):
+        """d(loss)/d(logits) of every loss group and its bilinear backward into the classifier outputs"""
+        L = self.L
         for g in groups:
             if upstream is not None:   # coef = {first-loss scale, Dice A_c[k], B_c[k]} (evb_loss_finalize)
                 u0, u1 = upstream.get(g['names'][0]), upstream.get(g['names'][1])
@@ -1085,15 +1111,44 @@ class FarSegEngine:
             check(L.evb_bilinear_up_bwd_sep(ptr(dlogits), ptr(cls.grad), c_int(n), c_int(hh // f), c_int(ww // f), c_int(16),
                                             c_int(16), c_int(64), c_int(f), ptr(ws), c_ll(self._ws_cap()), stream()),
                   'evb_bilinear_up_bwd_sep')
-        self._run_tape()
-        self._join_side()
-        self.tape = []
-        if allreduce:
-            self.allreduce_grads()
-        if attach:
-            self.attach_grads()
 
-    def _run_tape(self):
+    def _segments(self):
+        """[(lo, hi)] tape ranges in the order backward runs them (last segment of the forward first)"""
+        cuts = sorted(set(c for c in self._tape_splits if 0 < c < len(self.tape)))
+        bounds = [0] + cuts + [len(self.tape)]
+        return [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 2, -1, -1)]
+
+    def _bucket_ranges(self):
+        """arena ranges of the gradient buckets, in backward order: one per encoder split (ar_split_stages) + the rest.
+        Parameters are laid out in forward order, so 'everything from the first parameter of stage s on' is a contiguous
+        tail of the arena."""
+        if getattr(self, '_buckets', None) is None:
+            names = [n for n, _ in self.m.named_parameters()]
+            offs = []
+            for st in sorted(self.ar_split_stages):
+                pfx = 'en.resnet.layer%d.' % (st + 1)
+                idx = next((i for i, n in enumerate(names) if n.startswith(pfx)), None)
+                if idx is not None and idx > 0:
+                    offs.append(self._slots[idx][0])
+            bounds = [0] + sorted(set(offs)) + [self.flat_g.numel()]
+            self._buckets = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 2, -1, -1)]
+        return self._buckets
+
+    def _allreduce_bucket(self, seg_lo):
+        """asynchronous NCCL all-reduce (mean) of the bucket whose gradients the segment starting at tape index seg_lo has
+        just completed; it runs on NCCL's stream behind the current stream's work and overlaps the next segment"""
+        import torch.distributed as dist
+        cuts = sorted(set(c for c in self._tape_splits if 0 < c < max(len(self.tape), 1)), reverse=True)
+        order = cuts + [0]
+        buckets = self._bucket_ranges()
+        if len(buckets) != len(order):      # split points and buckets disagree (e.g. frozen stages): single bucket at the end
+            if seg_lo == 0:
+                self._ar_pending.append(dist.all_reduce(self.flat_g, op=dist.ReduceOp.AVG, async_op=True))
+            return
+        a, b = buckets[order.index(seg_lo)]
+        self._ar_pending.append(dist.all_reduce(self.flat_g[a:b], op=dist.ReduceOp.AVG, async_op=True))
+
+    def _run_tape(self, lo=0, hi=None):
         """Run the backward closures in reverse order.  Closures of a pyramid-level branch run on that branch's stream:
         entering the branch region the branch streams wait for the main stream (dq is ready), leaving it the main stream
         waits for all of them (dsf_i and inner_i.grad are complete) -- the mirror image of the forward fork/join."""
@@ -1104,7 +1159,8 @@ class FarSegEngine:
         main = torch.cuda.current_stream()
         fork_idx, join_idx = self._fork_idx, self._join_idx
         use = self.level_streams is not None and fork_idx is not None
-        for idx in range(len(self.tape) - 1, -1, -1):
+        hi = len(self.tape) if hi is None else hi
+        for idx in range(hi - 1, lo - 1, -1):
             if use and idx == join_idx - 1:      # about to enter the branch region (from the loss side)
                 ev = torch.cuda.Event()
                 ev.record(main)
@@ -1119,13 +1175,17 @@ class FarSegEngine:
             if use and idx == fork_idx:          # all branch closures are enqueued: join
                 for st_ in self.level_streams:
                     main.wait_stream(st_)
-        self._tape_tags, self._fork_idx, self._join_idx = [], None, None
 
     def allreduce_grads(self):
         """The one gradient exchange of the step: NCCL all-reduce (mean) of the flat fp32 gradient arena
         (reference: DDP bucketed all-reduce, ever/trainer/th_ddp_trainer.py:25-30)."""
         if self.world > 1:
             import torch.distributed as dist
+            if self._ar_pending:     # the buckets were issued during backward: make the current stream wait for them
+                for w in self._ar_pending:
+                    w.wait()
+                self._ar_pending = []
+                return
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.AVG)
 
     def confusion_matrix(self, mask, labels, cm):
@@ -1172,8 +1232,9 @@ class FarSegEngine:
     # ------------------------------------------------------------------ CUDA-graph step
     def capture_step(self, x, labels):
         """Capture forward + loss + backward for fixed-shape device inputs into CUDA graph(s).
-        Returns (replay_fn, losses dict).  NCCL is never captured: with world > 1 the step is two graphs with the
-        (eager) Dice-statistics all-reduce between them; the gradient all-reduce and the optimizer run after."""
+        Returns (replay_fn, losses dict).  NCCL is never captured: with world > 1 the step is a chain of graphs with the
+        eager Dice-statistics all-reduce and the asynchronous gradient-bucket all-reduces between them (see below);
+        allreduce_grads() then only waits for the buckets, and the optimizer runs after."""
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -1189,7 +1250,7 @@ class FarSegEngine:
                 b.copy_(s_)
         cur.wait_stream(side)
         torch.cuda.synchronize()
-        split = self.world > 1 and self.sync_dice
+        split = self.world > 1
         pool = torch.cuda.graph_pool_handle()
         cap_stream = torch.cuda.Stream(device=self.dev, priority=self._prio) if self._prio else None
         g1 = torch.cuda.CUDAGraph()
@@ -1198,19 +1259,44 @@ class FarSegEngine:
                 out = self.forward_train(x, labels)
                 self.backward(allreduce=False)
             return g1.replay, out
-        g2 = torch.cuda.CUDAGraph()
+        # world > 1: [forward + loss statistics] | eager Dice all-reduce | [loss + backward of bucket 0] | async all-reduce
+        # of bucket 0 | [backward of bucket 1] | async all-reduce of bucket 1 | ...  Every bracket is one CUDA graph; the
+        # bucket all-reduces run on NCCL's stream and overlap the graphs that follow (allreduce_grads() waits for them).
         with torch.cuda.graph(g1, pool=pool, stream=cap_stream):
             self._forward_part1(x, labels)
         self._dice_allreduce()
         torch.cuda.synchronize()
+        seg_graphs = []
+        segs = None
+        g2 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g2, pool=pool, stream=cap_stream):
             out = self._forward_part2()
-            self.backward(allreduce=False)
+            groups, self._saved_for_backward = self._saved_for_backward, None
+            self._loss_backward(groups)
+            segs = self._segments()
+            self._run_tape(*segs[0])
+            self._join_side()
+        seg_graphs.append(g2)
+        for lo, hi in segs[1:]:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool, stream=cap_stream):
+                self._run_tape(lo, hi)
+                self._join_side()
+            seg_graphs.append(g)
+        self.tape = []
+        self._tape_tags, self._fork_idx, self._join_idx = [], None, None
+        buckets = self._bucket_ranges()
+        bucketed = len(buckets) == len(seg_graphs) and os.environ.get('EVB_AR_OVERLAP', '1') == '1'
 
         def replay():
+            import torch.distributed as dist
             g1.replay()
             self._dice_allreduce()
-            g2.replay()
+            for i, g in enumerate(seg_graphs):
+                g.replay()
+                if bucketed:
+                    a, b = buckets[i]
+                    self._ar_pending.append(dist.all_reduce(self.flat_g[a:b], op=dist.ReduceOp.AVG, async_op=True))
         return replay, out
 
     def graph_forward(self, x, labels):

@@ -82,8 +82,13 @@ def _run(rank, world, port, out_path):
     eng.tf = None
     gmax = max(float(g.norm()) for g in ref_grads.values())
     grads = {}
+    import re
+    # conv bias in front of a training-mode BN: exactly zero (engine) vs rounding noise (reference); and the BN in front of
+    # the max-pool, whose d-gamma / d-beta are cancellation-limited in torch's own bf16 backward -- both analysed against
+    # fp64 in tests/test_teacher_forced_gpu.py
+    skip = re.compile(r'head\.fs_relation\.(content_encoders|feature_reencoders)\.\d+\.0\.bias$|en\.resnet\.bn1\.')
     for nm, p in mine.named_parameters():
-        if float(ref_grads[nm].norm()) < 1e-6 * gmax:
+        if float(ref_grads[nm].norm()) < 1e-6 * gmax or skip.match(nm):
             continue
         grads[nm] = rel_l2(p.grad, ref_grads[nm])
     loss_err = {kk: abs(float(out[kk]) - ref_losses[kk]) / abs(ref_losses[kk]) for kk in ref_losses}

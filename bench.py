@@ -428,6 +428,8 @@ def run_b200(args):
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     state = dict(i=0)
+    loss_host = [torch.empty(len(out), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
 
     def prefetch(slot):
         with torch.cuda.stream(copy_stream):
@@ -454,7 +456,14 @@ def run_b200(args):
         consumed[slot].record(cur)
         model.backward(o, None, None)
         eng.sgd_step(lr)
-        return torch.stack([v.detach() for v in o.values()]).cpu()
+        # D2H read of this step's losses into pinned memory, every step; the host blocks on the PREVIOUS step's copy, so the
+        # read-back is pipelined one step deep (the host launches step i+1 while step i's losses travel) instead of
+        # draining the GPU at every step
+        loss_host[slot].copy_(torch.stack([v.detach() for v in o.values()]), non_blocking=True)
+        loss_ready[slot].record(cur)
+        if state['i'] > 1:
+            loss_ready[slot ^ 1].synchronize()
+            state['last_loss'] = loss_host[slot ^ 1].tolist()
 
     model.config.cuda_graph = use_graph
     for _ in range(3):
@@ -463,6 +472,8 @@ def run_b200(args):
     e0.record()
     for _ in range(e2e_steps):
         e2e_step()
+    loss_ready[(state['i'] - 1) & 1].synchronize()     # the last step's losses have arrived on the host
+    state['last_loss'] = loss_host[(state['i'] - 1) & 1].tolist()
     e1.record()
     barrier()
     ms2 = e0.elapsed_time(e1) / e2e_steps
@@ -474,7 +485,7 @@ def run_b200(args):
     e2e = dict(value=world * n_tiles / (ms2 * 1e-3), unit='tiles/s', h2d_bytes_per_step=h2d,
                d2h_bytes_per_step=4 * len(out), ms_per_step=ms2, steps=e2e_steps,
                api='%s.forward(x, y) + .backward() via libevb200.so C ABI; pinned host inputs, double-buffered H2D on a copy '
-                   'stream, D2H read of the losses every step' % cls.__name__)
+                   'stream, D2H read of the losses every step (pinned, host waits one step behind)' % cls.__name__)
 
     if rank == 0:
         pk = peaks()
@@ -517,10 +528,23 @@ def run_b200(args):
             line['gpu_incumbent'] = gpu_incumbent(cfg, n_units, variants)
         print(json.dumps(line))
     if world > 1:
+        # the captured step graph holds NCCL kernel nodes: release every graph before the communicator goes away, and never
+        # let a stuck teardown (seen with live captured collectives) keep the job from exiting after the line is printed
+        sys.stdout.flush()
+        graph = None
+        eng._graphs.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():
+    if os.environ.get('EVB_BENCH_WATCHDOG'):   # diagnostics: dump every thread's stack and exit if the run hangs
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ['EVB_BENCH_WATCHDOG']), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)

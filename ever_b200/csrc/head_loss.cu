@@ -256,17 +256,17 @@ linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ y, c
 // ------------------------------------------------------------------------------------------------ CE + Dice
 // logits: [P, LD] bf16 (NHWC, first K channels are classes), labels: int64 [P], 255 (ignore_index) = ignored.
 // stats layout (fp32): [0]=sum of -log p_t over valid, [1]=n_valid, [2..2+K)=I_c, [2+K..2+2K)=sum p_c, [2+2K..2+3K)=sum y_c
-constexpr int kMaxK = 16;
+constexpr int kMaxK = 64;   // classes per loss group (logit rows of LD = 16 / 32 / 64 bf16)
 
-template <int PASS, int KT>
+template <int PASS, int KT, int KMAX = 16>
 __global__ void __launch_bounds__(256)
 loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restrict__ labels, long long P, int Krt, int LD,
             int ignore_index, float* __restrict__ partial, const float* __restrict__ coef,
             __nv_bfloat16* __restrict__ dlogits) {
   // PASS 0: statistics -> partial[block][2+3K];  PASS 1: dlogits from coef = {inv_nvalid, A_c[K], B_c[K]}
-  // KT > 0: K is a compile-time constant (arrays stay in registers); KT == 0: generic K <= kMaxK
+  // KT > 0: K is a compile-time constant (arrays stay in registers); KT == 0: generic K <= KMAX (16 / 32 / 64)
   const int K = KT > 0 ? KT : Krt;
-  constexpr int KA = KT > 0 ? KT : kMaxK;
+  constexpr int KA = KT > 0 ? KT : KMAX;
   __shared__ float red[8][2 + 3 * KA];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float acc[2 + 3 * KA];
@@ -340,13 +340,15 @@ loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restric
         for (int c = 0; c < K; ++c) d[c] = 0.f;
       }
 #pragma unroll
-      for (int c0 = 0; c0 < 16; c0 += 8) {
+      for (int c0 = 0; c0 < (KA + 7) / 8 * 8 || c0 < 16; c0 += 8) {
         if (c0 >= LD) break;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = (c0 + j < K) ? d[c0 + j] : 0.f;
         *reinterpret_cast<bf16x8*>(dlogits + p * LD + c0) = pack8(v);
       }
+      for (int c0 = ((KA + 7) / 8 * 8 > 16 ? (KA + 7) / 8 * 8 : 16); c0 < LD; c0 += 8)   // padding channels up to LD
+        *reinterpret_cast<uint4*>(dlogits + p * LD + c0) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
   if (PASS == 0) {
@@ -576,7 +578,7 @@ extern "C" long long evb_loss_workspace(long long P, int K) { return (long long)
 // Pass A: statistics of softmax-CE + Dice over valid pixels -> stats[2+3K] (device, fp32).
 extern "C" int evb_loss_stats(const void* logits, const void* labels, long long P, int K, int LD, int ignore_index,
                               float* stats, void* ws, void* stream) {
-  if (K < 1 || K > kMaxK || LD != 16) return EVB_ERR_ARG;
+  if (K < 1 || K > kMaxK || (LD != 16 && LD != 32 && LD != 64) || K > LD) return EVB_ERR_ARG;
   const int nb = loss_blocks(P), n = 2 + 3 * K;
   if (K == 1) {
     loss_binary_kernel<0><<<nb, 256, 0, ST>>>((const __nv_bfloat16*)logits, (const long long*)labels, P, LD, ignore_index,
@@ -590,7 +592,10 @@ extern "C" int evb_loss_stats(const void* logits, const void* labels, long long 
     case 7: loss_kernel<PASS_, 7><<<GRID_, 256, 0, ST>>>(__VA_ARGS__); break;                    \
     case 5: loss_kernel<PASS_, 5><<<GRID_, 256, 0, ST>>>(__VA_ARGS__); break;                    \
     case 2: loss_kernel<PASS_, 2><<<GRID_, 256, 0, ST>>>(__VA_ARGS__); break;                    \
-    default: loss_kernel<PASS_, 0><<<GRID_, 256, 0, ST>>>(__VA_ARGS__);                          \
+    default:                                                                                     \
+      if (K <= 16) loss_kernel<PASS_, 0, 16><<<GRID_, 256, 0, ST>>>(__VA_ARGS__);                \
+      else if (K <= 32) loss_kernel<PASS_, 0, 32><<<GRID_, 256, 0, ST>>>(__VA_ARGS__);           \
+      else loss_kernel<PASS_, 0, 64><<<GRID_, 256, 0, ST>>>(__VA_ARGS__);                        \
   }
   EVB_LOSS_LAUNCH(0, nb, (const __nv_bfloat16*)logits, (const long long*)labels, P, K, LD, ignore_index, (float*)ws,
                   nullptr, nullptr)
@@ -607,7 +612,7 @@ extern "C" int evb_loss_finalize(const float* stats, const float* dice_stats, in
 // Pass B: dlogits[P, LD] bf16 (padding channels zeroed).
 extern "C" int evb_loss_grad(const void* logits, const void* labels, long long P, int K, int LD, int ignore_index,
                              const float* coef, void* dlogits, void* stream) {
-  if (K < 1 || K > kMaxK || LD != 16) return EVB_ERR_ARG;
+  if (K < 1 || K > kMaxK || (LD != 16 && LD != 32 && LD != 64) || K > LD) return EVB_ERR_ARG;
   if (K == 1) {
     loss_binary_kernel<1><<<loss_blocks(P), 256, 0, ST>>>((const __nv_bfloat16*)logits, (const long long*)labels, P, LD,
                                                           ignore_index, nullptr, coef, (__nv_bfloat16*)dlogits);
@@ -657,6 +662,7 @@ extern "C" int evb_sgd_step_masked(float* w, float* g, float* mom, long long n, 
 // prob[N,K,H,W] fp32 = softmax over the K class channels of logits[P, LD] bf16 (eval path: logit.softmax(dim=1)),
 // mask[P] uint8 = argmax (lowest index wins ties, as torch.argmax on CUDA).
 namespace evb {
+template <int KMAX>
 __global__ void softmax_nchw_kernel(const __nv_bfloat16* __restrict__ logits, float* __restrict__ prob,
                                     uint8_t* __restrict__ mask, long long P, int HW, int K, int LD) {
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
@@ -667,7 +673,7 @@ __global__ void softmax_nchw_kernel(const __nv_bfloat16* __restrict__ logits, fl
       if (mask) mask[p] = pr > 0.5f ? 1 : 0;
       continue;
     }
-    float z[kMaxK];
+    float z[KMAX];
     for (int c = 0; c < K; ++c) z[c] = __bfloat162float(row[c]);
     float mx = z[0];
     int am = 0;
@@ -687,6 +693,9 @@ extern "C" int evb_softmax_nchw(const void* logits, float* prob, void* mask, lon
   if (K < 1 || K > kMaxK) return EVB_ERR_ARG;
   long long b = (P + 255) / 256;
   if (b > 148 * 8) b = 148 * 8;
-  softmax_nchw_kernel<<<(int)b, 256, 0, ST>>>((const __nv_bfloat16*)logits, prob, (uint8_t*)mask, P, HW, K, LD);
+  const __nv_bfloat16* lg = (const __nv_bfloat16*)logits;
+  if (K <= 16) softmax_nchw_kernel<16><<<(int)b, 256, 0, ST>>>(lg, prob, (uint8_t*)mask, P, HW, K, LD);
+  else if (K <= 32) softmax_nchw_kernel<32><<<(int)b, 256, 0, ST>>>(lg, prob, (uint8_t*)mask, P, HW, K, LD);
+  else softmax_nchw_kernel<64><<<(int)b, 256, 0, ST>>>(lg, prob, (uint8_t*)mask, P, HW, K, LD);
   return LAUNCH_OK();
 }

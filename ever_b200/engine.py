@@ -130,11 +130,13 @@ class FarSegEngine:
         self.side = torch.cuda.Stream(device=self.dev) if os.environ.get('EVB_NO_SIDE_STREAM', '0') != '1' else None
         self.accumulate = False      # gradient accumulation into existing .grad (forward_times > 1)
         # Gradient buckets for the overlapped all-reduce (world > 1): backward is cut where these encoder stages start
-        # (stage index 3 = layer4, 2 = layer3).  Bucket 0 = layer4 + head (75 % of the R50 parameters) is all-reduced while
-        # layer3's backward runs, bucket 1 = layer3 while layer2/layer1/stem run; only the last 6 MB are exposed.
-        self.ar_split_stages = tuple(int(v) for v in os.environ.get('EVB_AR_SPLITS', '3,2').split(',') if v != '')
+        # (stage index 3 = layer4, 2 = layer3, 1 = layer2).  Bucket 0 = layer4 + head (75 % of the R50 parameters) is
+        # all-reduced while layer3's backward runs, bucket 1 = layer3 while layer2 runs, ...; only the last ~1 MB (layer1 +
+        # stem) is exposed.  Measured at 2 GPUs: 9.53 ms/step monolithic -> 9.37 (profiles/r02_allreduce_overlap.md).
+        self.ar_split_stages = tuple(int(v) for v in os.environ.get('EVB_AR_SPLITS', '3,2,1').split(',') if v != '')
         self._tape_splits = []
         self._ar_pending = []
+        self._reduced_in_graph = False
         self.fuse_bn_stats = True    # BN batch statistics in the producing conv's epilogue (evb_conv2d_fwd_stats)
         self._saved_for_backward = None
         self._graphs = {}
@@ -147,6 +149,10 @@ class FarSegEngine:
         self.smooth = float(cfg.loss.dice.smooth)
         self.sync_dice = bool(cfg.loss.dice.sync_statistics)
         self.K = module.head.fpn_decoder.num_classes
+        if self.K > 64:
+            raise NotImplementedError('more than 64 classes (the classifier runs as one 64-channel tensor-core tile)')
+        # elements per pixel of the logit / logit-gradient rows [N, H, W, ld] (bf16): 16 covers K <= 16 with 32-byte rows
+        self.ld = 16 if self.K <= 16 else 32 if self.K <= 32 else 64
         # K == 1: binary head -> masked BCE-with-logits + sigmoid Dice (ever/module/loss.py:66-68,229-235)
 
     # ------------------------------------------------------------------ parameters
@@ -968,9 +974,10 @@ class FarSegEngine:
         L = self.L
         cls = self.conv(feat, cp, bias=True, train=train)
         n, h4, w4, _ = cls.data.shape
-        logits = self._new(n, h4 * f, w4 * f, 16)
-        check(L.evb_bilinear_up(ptr(cls.data), None, None, ptr(logits), c_int(n), c_int(h4), c_int(w4), c_int(16),
-                                c_int(64), c_int(16), c_int(f), stream()), 'evb_bilinear_up(logits)')
+        ld = self.ld if cp is self.cls else 16
+        logits = self._new(n, h4 * f, w4 * f, ld)
+        check(L.evb_bilinear_up(ptr(cls.data), None, None, ptr(logits), c_int(n), c_int(h4), c_int(w4), c_int(ld),
+                                c_int(64), c_int(ld), c_int(f), stream()), 'evb_bilinear_up(logits)')
         if self.tf is not None and cp.name:
             self.tf('fwd', cp.name.rsplit('.', 1)[0] + '.1', logits)
         self._dbg('cls' if name == 'logits' else name + '_cls', cls)
@@ -988,7 +995,7 @@ class FarSegEngine:
         npx = n * hh * ww
         stats = self._new(2 + 3 * k, dtype=torch.float32)
         ws = self._ws(L.evb_loss_workspace(c_ll(npx), c_int(k)))
-        check(L.evb_loss_stats(ptr(logits), ptr(labels), c_ll(npx), c_int(k), c_int(16), c_int(self.ignore_index),
+        check(L.evb_loss_stats(ptr(logits), ptr(labels), c_ll(npx), c_int(k), c_int(logits.shape[-1]), c_int(self.ignore_index),
                                ptr(stats), ptr(ws), stream()), 'evb_loss_stats')
         g = dict(cls=cls, logits=logits, labels=labels, stats=stats, npx=npx, k=k, f=f, names=names, weight=weight,
                  name=cls.name.rsplit('.', 1)[0] + '.1' if cls.name else None)
@@ -1080,7 +1087,6 @@ class FarSegEngine:
         for lo, hi in self._segments():
             self._run_tape(lo, hi)
             if allreduce and self.world > 1:
-                self._join_side()
                 self._allreduce_bucket(lo)
         self._join_side()
         self.tape = []
@@ -1099,17 +1105,17 @@ class FarSegEngine:
                 g['coef'][:1].mul_(u0.to(torch.float32) if u0 is not None else 0.0)
                 g['coef'][1:].mul_(u1.to(torch.float32) if u1 is not None else 0.0)
             logits, cls, k, f = g['logits'], g['cls'], g['k'], g['f']
-            n, hh, ww, _ = logits.shape
-            dlogits = self._new(n, hh, ww, 16)
-            check(L.evb_loss_grad(ptr(logits), ptr(g['labels']), c_ll(g['npx']), c_int(k), c_int(16),
+            n, hh, ww, ld = logits.shape
+            dlogits = self._new(n, hh, ww, ld)
+            check(L.evb_loss_grad(ptr(logits), ptr(g['labels']), c_ll(g['npx']), c_int(k), c_int(ld),
                                   c_int(self.ignore_index), ptr(g['coef']), ptr(dlogits), stream()), 'evb_loss_grad')
             if self.tf is not None and g.get('name'):
                 self.tf('bwd', g['name'], dlogits)
             cls.grad = torch.zeros_like(cls.data)   # padding channels 16..63 stay zero
             cls.has_grad = True
-            ws = self._ws(L.evb_bilinear_up_bwd_workspace(c_int(n), c_int(hh // f), c_int(ww // f), c_int(16), c_int(f)))
-            check(L.evb_bilinear_up_bwd_sep(ptr(dlogits), ptr(cls.grad), c_int(n), c_int(hh // f), c_int(ww // f), c_int(16),
-                                            c_int(16), c_int(64), c_int(f), ptr(ws), c_ll(self._ws_cap()), stream()),
+            ws = self._ws(L.evb_bilinear_up_bwd_workspace(c_int(n), c_int(hh // f), c_int(ww // f), c_int(ld), c_int(f)))
+            check(L.evb_bilinear_up_bwd_sep(ptr(dlogits), ptr(cls.grad), c_int(n), c_int(hh // f), c_int(ww // f), c_int(ld),
+                                            c_int(ld), c_int(64), c_int(f), ptr(ws), c_ll(self._ws_cap()), stream()),
                   'evb_bilinear_up_bwd_sep')
 
     def _segments(self):
@@ -1143,10 +1149,27 @@ class FarSegEngine:
         buckets = self._bucket_ranges()
         if len(buckets) != len(order):      # split points and buckets disagree (e.g. frozen stages): single bucket at the end
             if seg_lo == 0:
-                self._ar_pending.append(dist.all_reduce(self.flat_g, op=dist.ReduceOp.AVG, async_op=True))
+                self._issue_allreduce(0, self.flat_g.numel())
             return
         a, b = buckets[order.index(seg_lo)]
-        self._ar_pending.append(dist.all_reduce(self.flat_g[a:b], op=dist.ReduceOp.AVG, async_op=True))
+        self._issue_allreduce(a, b)
+
+    def _issue_allreduce(self, a, b):
+        """async all-reduce (mean) of arena[a:b], ordered behind BOTH the main stream (BatchNorm / bias / linear gradients)
+        and the weight-gradient side stream -- without stalling the main stream: the side stream waits for an event of the
+        main stream and the collective is issued from the side stream's context, so NCCL's stream depends on the side
+        stream only; the main chain (dgrad -> BN backward) runs on."""
+        import torch.distributed as dist
+        if self.side is None:
+            self._ar_pending.append(dist.all_reduce(self.flat_g[a:b], op=dist.ReduceOp.AVG, async_op=True))
+            return
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            self._ar_pending.append(dist.all_reduce(self.flat_g[a:b], op=dist.ReduceOp.AVG, async_op=True))
+        self._side_used = True
 
     def _run_tape(self, lo=0, hi=None):
         """Run the backward closures in reverse order.  Closures of a pyramid-level branch run on that branch's stream:
@@ -1181,6 +1204,9 @@ class FarSegEngine:
         (reference: DDP bucketed all-reduce, ever/trainer/th_ddp_trainer.py:25-30)."""
         if self.world > 1:
             import torch.distributed as dist
+            if self._reduced_in_graph:   # the replayed graph contains the bucket all-reduces and their joins
+                self._reduced_in_graph = False
+                return
             if self._ar_pending:     # the buckets were issued during backward: make the current stream wait for them
                 for w in self._ar_pending:
                     w.wait()
@@ -1243,9 +1269,9 @@ class FarSegEngine:
         bufs = [b for b in self.m.buffers()]
         saved = [b.detach().clone() for b in bufs]
         with torch.cuda.stream(side):
-            for _ in range(2):  # warm-up: sets kernel attributes, sizes the workspace
+            for _ in range(2):  # warm-up: sets kernel attributes, sizes the workspace (and NCCL's buffers for the buckets)
                 self.forward_train(x, labels)
-                self.backward(allreduce=False)
+                self.backward(allreduce=self.world > 1, attach=False)
             for b, s_ in zip(bufs, saved):
                 b.copy_(s_)
         cur.wait_stream(side)
@@ -1259,6 +1285,19 @@ class FarSegEngine:
                 out = self.forward_train(x, labels)
                 self.backward(allreduce=False)
             return g1.replay, out
+        if os.environ.get('EVB_CAPTURE_NCCL', '1') == '1':
+            # world > 1, ONE graph: the Dice-statistics all-reduce and the gradient-bucket all-reduces are captured NCCL
+            # nodes.  A bucket's node depends on the weight-gradient branch (and through it on the main chain up to the
+            # bucket boundary) and is joined only at the end, so it overlaps the rest of backward without cutting the graph.
+            # thread_local: NCCL's watchdog thread polls CUDA events while this thread captures
+            with torch.cuda.graph(g1, pool=pool, stream=cap_stream, capture_error_mode='thread_local'):
+                out = self.forward_train(x, labels)
+                self.backward(allreduce=True, attach=False)
+
+            def replay_one():
+                g1.replay()
+                self._reduced_in_graph = True
+            return replay_one, out
         # world > 1: [forward + loss statistics] | eager Dice all-reduce | [loss + backward of bucket 0] | async all-reduce
         # of bucket 0 | [backward of bucket 1] | async all-reduce of bucket 1 | ...  Every bracket is one CUDA graph; the
         # bucket all-reduces run on NCCL's stream and overlap the graphs that follow (allreduce_grads() waits for them).
@@ -1338,7 +1377,7 @@ class FarSegEngine:
         prob = self._new(n, self.K, hh, ww, dtype=torch.float32)
         mask = self._new(n, hh, ww, dtype=torch.uint8)
         check(L.evb_softmax_nchw(ptr(logits), ptr(prob), ptr(mask), c_ll(n * hh * ww), c_int(hh * ww), c_int(self.K),
-                                 c_int(16), stream()), 'evb_softmax_nchw')
+                                 c_int(logits.shape[-1]), stream()), 'evb_softmax_nchw')
         self.last_logits = logits
         if return_mask:
             return prob, mask
@@ -1423,8 +1462,8 @@ class ChangeStarEngine(FarSegEngine):
             nn_, hh, ww, _ = lg.shape
             prob = self._new(nn_, k, hh, ww, dtype=torch.float32)
             mask = self._new(nn_, hh, ww, dtype=torch.uint8)
-            check(L.evb_softmax_nchw(ptr(lg), ptr(prob), ptr(mask), c_ll(nn_ * hh * ww), c_int(hh * ww), c_int(k), c_int(16),
-                                     stream()), 'evb_softmax_nchw')
+            check(L.evb_softmax_nchw(ptr(lg), ptr(prob), ptr(mask), c_ll(nn_ * hh * ww), c_int(hh * ww), c_int(k),
+                                     c_int(lg.shape[-1]), stream()), 'evb_softmax_nchw')
             out[key] = prob
             out[key + '_mask'] = mask
         return out

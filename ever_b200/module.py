@@ -122,8 +122,11 @@ class _Decoder(nn.Module):
         self.num_classes = int(cc.get('num_classes', 1))
         self.scale_factor = int(cc.get('scale_factor', 1))
         ks = int(cc.get('kernel_size', 1))
-        if ks != 1:
-            raise NotImplementedError('classifier kernel_size 1 only')
+        if ks not in (1, 3):
+            raise NotImplementedError('classifier kernel_size 1 or 3 (got %d)' % ks)
+        if float(cc.get('dropout_rate', -1)) > 0:
+            raise NotImplementedError('classifier dropout_rate > 0 (nn.Dropout on the merged decoder features, '
+                                      'ever/module/fpn.py:175-176) is not built')
         self.num_upsample = []
         self.blocks = nn.ModuleList()
         for os_ in in_feat_output_strides:
@@ -133,7 +136,7 @@ class _Decoder(nn.Module):
             self.blocks.append(nn.Sequential(*[
                 nn.Sequential(nn.Conv2d(in_channels if j == 0 else out_channels, out_channels, 3, 1, 1, bias=False),
                               nn.BatchNorm2d(out_channels), nn.ReLU(True), nn.Identity()) for j in range(nl)]))
-        self.classifier = nn.Sequential(nn.Conv2d(out_channels, self.num_classes, 1), nn.Identity())
+        self.classifier = nn.Sequential(nn.Conv2d(out_channels, self.num_classes, ks, padding=(ks - 1) // 2), nn.Identity())
 
 
 class _Head(nn.Module):

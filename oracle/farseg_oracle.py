@@ -289,11 +289,12 @@ class FarSegHeadOracle(nn.Module):
     """FarSegHead.forward, reference ever/module/fs_relation.py:166-206."""
 
     def __init__(self, in_channels_list=(256, 512, 1024, 2048), fpn_channels=256, decoder_channels=256, num_classes=1,
-                 scale_aware_proj=True):
+                 scale_aware_proj=True, classifier_kernel_size=1):
         super().__init__()
         self.fpn = FPNOracle(in_channels_list, fpn_channels)
         self.fs_relation = FSRelationOracle(in_channels_list[-1], (fpn_channels,) * 4, fpn_channels, scale_aware_proj)
-        self.fpn_decoder = DecoderOracle(fpn_channels, decoder_channels, num_classes=num_classes)
+        self.fpn_decoder = DecoderOracle(fpn_channels, decoder_channels, num_classes=num_classes,
+                                         kernel_size=classifier_kernel_size)
 
     def forward(self, feats):
         ps = self.fpn(feats)
@@ -340,10 +341,11 @@ class FarSegOracle(nn.Module):
     in training, softmax probabilities in eval."""
 
     def __init__(self, resnet_type='resnet50', num_classes=15, decoder_channels=256, in_channels=3, freeze_at=0,
-                 batchnorm_trainable=True, scale_aware_proj=True):
+                 batchnorm_trainable=True, scale_aware_proj=True, classifier_kernel_size=1):
         super().__init__()
         self.en = ResNetEncoderOracle(resnet_type, in_channels, freeze_at, batchnorm_trainable)
-        self.head = FarSegHeadOracle(self.en.out_channels, 256, decoder_channels, num_classes, scale_aware_proj)
+        self.head = FarSegHeadOracle(self.en.out_channels, 256, decoder_channels, num_classes, scale_aware_proj,
+                                     classifier_kernel_size)
         self.dice_all_reduce = None
 
     def logits(self, x):

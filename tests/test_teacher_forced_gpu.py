@@ -35,7 +35,8 @@ def _build(resnet, k, dec, **opts):
     ora = deterministic_fill(FarSegOracle(resnet, k, dec, **opts), 0)
     mine = FarSegB200(dict(encoder=dict(resnet_type=resnet, in_channels=opts.get('in_channels', 3)),
                            head=dict(fs_relation=dict(scale_aware_proj=opts.get('scale_aware_proj', True)),
-                                     fpn_decoder=dict(out_channels=dec, classifier_config=dict(num_classes=k)))))
+                                     fpn_decoder=dict(out_channels=dec, classifier_config=dict(
+                                         num_classes=k, kernel_size=opts.get('classifier_kernel_size', 1))))))
     mine.load_state_dict(ora.state_dict(), strict=True)
     return ora.cuda().train(), mine.cuda().train()
 
@@ -80,10 +81,13 @@ CASES = [
     # deep stem + shared scene encoder + binary head share the remaining op variants
     ('resnet50_v1c', 5, 128, 2, 256, 256, {}),
     ('resnet18', 1, 128, 2, 128, 128, dict(scale_aware_proj=False)),
+    # 3x3 classifier (classifier_config.kernel_size, ever/module/fpn.py:172-181) and more than 16 classes (32- / 64-wide logit rows)
+    ('resnet18', 21, 128, 2, 128, 128, dict(classifier_kernel_size=3)),
+    ('resnet18', 40, 128, 2, 128, 128, {}),
 ]
 
 
-@pytest.mark.parametrize('case', CASES, ids=lambda c: '%s_k%d_%dx%d' % (c[0], c[1], c[3], c[4]))
+@pytest.mark.parametrize('case', CASES, ids=lambda c: '%s_k%d_%dx%d' % (c[0], c[1], c[3], c[4]) if isinstance(c, tuple) else None)
 def test_teacher_forced_step(case):
     from oracle.farseg_oracle import synthetic_batch
     resnet, k, dec, n, h, w, opts = case

@@ -19,12 +19,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 // cf = relu(bn1(u1)), pf = relu(bn2(u2)); r = sigmoid(sum_c bf16(sf_c * cf_c)); z = bf16(r * pf).
 // One warp per pixel, C = 256*NG: lane owns channel groups [lane*8 + 256*a, +8); the per-channel BN folds are hoisted
 // into registers and PX pixels are in flight per warp.
-template <int NG, int PX>
+// PR: the product sf_c * cf_c is a bf16 tensor in the reference (FSRelation: bf16 scene vector, :57-73); FSRelationV2's scene
+// vector leaves its GroupNorm in fp32 (autocast runs group_norm in fp32), so there the product stays fp32 (PR = false).
+// ldz: elements per pixel of the output rows (FSRelationV2 writes z into the first half of its concat buffer).
+template <int NG, int PX, bool PR>
 __global__ void __launch_bounds__(256)
 relation_fwd_kernel(const __nv_bfloat16* __restrict__ u1, const __nv_bfloat16* __restrict__ u2,
                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ scale2,
                     const float* __restrict__ shift2, const float* __restrict__ sf, __nv_bfloat16* __restrict__ z,
-                    float* __restrict__ rel, long long M, int HW) {
+                    float* __restrict__ rel, long long M, int HW, int ldz) {
   constexpr int C = 256 * NG;
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -67,7 +70,10 @@ relation_fwd_kernel(const __nv_bfloat16* __restrict__ u1, const __nv_bfloat16* _
         float v[8];
         unpack8(q1[p][a], v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dot += bf16_round(sfv[a][j] * fmaxf(bf16_round(v[j] * s1[a][j] + b1[a][j]), 0.f));
+        for (int j = 0; j < 8; ++j) {
+          const float pr_ = sfv[a][j] * fmaxf(bf16_round(v[j] * s1[a][j] + b1[a][j]), 0.f);
+          dot += PR ? bf16_round(pr_) : pr_;
+        }
       }
       dot = warp_sum(dot);
       const float r = 1.f / (1.f + __expf(-dot));
@@ -78,7 +84,7 @@ relation_fwd_kernel(const __nv_bfloat16* __restrict__ u1, const __nv_bfloat16* _
         unpack8(q2[p][a], v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = r * fmaxf(bf16_round(v[j] * s2[a][j] + b2[a][j]), 0.f);
-        *reinterpret_cast<bf16x8*>(z + m * C + lane * 8 + 256 * a) = pack8(v);
+        *reinterpret_cast<bf16x8*>(z + m * ldz + lane * 8 + 256 * a) = pack8(v);
       }
     }
   }
@@ -86,13 +92,13 @@ relation_fwd_kernel(const __nv_bfloat16* __restrict__ u1, const __nv_bfloat16* _
 
 // g1/g2 [M,C] = gradient w.r.t. the two BN outputs (ReLU masks applied); dsf_part[warp][c] = sum over the warp's pixels
 // of dlogit * cf (px_per_warp divides HW, so a warp never straddles two images; reduced deterministically afterwards).
-template <int NG, int PX>
+template <int NG, int PX, bool PR>
 __global__ void __launch_bounds__(256, NG == 1 ? 2 : 1)
 relation_bwd_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ u1,
                     const __nv_bfloat16* __restrict__ u2, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ scale2, const float* __restrict__ shift2, const float* __restrict__ sf,
                     const float* __restrict__ rel, __nv_bfloat16* __restrict__ g1, __nv_bfloat16* __restrict__ g2,
-                    float* __restrict__ dsf_part, long long M, int HW, int px_per_warp) {
+                    float* __restrict__ dsf_part, long long M, int HW, int px_per_warp, int lddz) {
   constexpr int C = 256 * NG;
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -121,7 +127,7 @@ relation_bwd_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* _
           const long long off = (m0 + p) * C + lane * 8 + 256 * a;
           q1[p][a] = *reinterpret_cast<const bf16x8*>(u1 + off);
           q2[p][a] = *reinterpret_cast<const bf16x8*>(u2 + off);
-          qd[p][a] = *reinterpret_cast<const bf16x8*>(dz + off);
+          qd[p][a] = *reinterpret_cast<const bf16x8*>(dz + (m0 + p) * lddz + lane * 8 + 256 * a);
         }
       }
 #pragma unroll
@@ -154,7 +160,9 @@ relation_bwd_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* _
       dr = warp_sum(dr);
       // autocast flow of the reference: sum(dim=1) runs in fp32 on the bf16 product, so its backward hands a bf16-ROUNDED
       // d(logit) to the bf16 multiply; d(cf) = bf16(dl * sf) and d(sf) sums bf16(dl * cf) (SURVEY.md 8a dtype flow)
-      const float dlogit = bf16_round(dr * r * (1.f - r));
+      // (PR = false, FSRelationV2: the product and the scene vector are fp32, nothing is rounded before d(cf) is stored)
+      const float dl_ = dr * r * (1.f - r);
+      const float dlogit = PR ? bf16_round(dl_) : dl_;
 #pragma unroll
       for (int a = 0; a < NG; ++a) {
         float v[8], o[8];
@@ -162,7 +170,7 @@ relation_bwd_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* _
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float cf = fmaxf(bf16_round(v[j] * s1[a][j] + b1[a][j]), 0.f);
-          acc[a][j] += bf16_round(dlogit * cf);
+          acc[a][j] += PR ? bf16_round(dlogit * cf) : dlogit * cf;
           o[j] = cf > 0.f ? dlogit * sfv[a][j] : 0.f;
         }
         *reinterpret_cast<bf16x8*>(g1 + m * C + lane * 8 + 256 * a) = pack8(o);
@@ -513,18 +521,30 @@ using namespace evb;
 #define ST ((cudaStream_t)stream)
 #define LAUNCH_OK() (cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA)
 
-extern "C" int evb_relation_fwd(const void* u1, const void* u2, const float* scale1, const float* shift1,
-                                const float* scale2, const float* shift2, const float* sf, void* z, float* rel, long long M,
-                                int HW, int C, void* stream) {
-  if (C != 256 && C != 512 && C != 1024) return EVB_ERR_ARG;
+template <bool PR>
+static int relation_fwd_launch(const void* u1, const void* u2, const float* scale1, const float* shift1, const float* scale2,
+                               const float* shift2, const float* sf, void* z, float* rel, long long M, int HW, int C, int ldz,
+                               void* stream) {
+  if ((C != 256 && C != 512 && C != 1024) || ldz < C || ldz % 8) return EVB_ERR_ARG;
   long long blocks = (M + 31) / 32;  // 8 warps x 4 pixels
   if (blocks > 148 * 8) blocks = 148 * 8;
   const __nv_bfloat16 *a = (const __nv_bfloat16*)u1, *b = (const __nv_bfloat16*)u2;
   __nv_bfloat16* zz = (__nv_bfloat16*)z;
-  if (C == 256) relation_fwd_kernel<1, 4><<<(int)blocks, 256, 0, ST>>>(a, b, scale1, shift1, scale2, shift2, sf, zz, rel, M, HW);
-  else if (C == 512) relation_fwd_kernel<2, 2><<<(int)blocks, 256, 0, ST>>>(a, b, scale1, shift1, scale2, shift2, sf, zz, rel, M, HW);
-  else relation_fwd_kernel<4, 1><<<(int)blocks, 256, 0, ST>>>(a, b, scale1, shift1, scale2, shift2, sf, zz, rel, M, HW);
+  if (C == 256) relation_fwd_kernel<1, 4, PR><<<(int)blocks, 256, 0, ST>>>(a, b, scale1, shift1, scale2, shift2, sf, zz, rel, M, HW, ldz);
+  else if (C == 512) relation_fwd_kernel<2, 2, PR><<<(int)blocks, 256, 0, ST>>>(a, b, scale1, shift1, scale2, shift2, sf, zz, rel, M, HW, ldz);
+  else relation_fwd_kernel<4, 1, PR><<<(int)blocks, 256, 0, ST>>>(a, b, scale1, shift1, scale2, shift2, sf, zz, rel, M, HW, ldz);
   return LAUNCH_OK();
+}
+extern "C" int evb_relation_fwd(const void* u1, const void* u2, const float* scale1, const float* shift1,
+                                const float* scale2, const float* shift2, const float* sf, void* z, float* rel, long long M,
+                                int HW, int C, void* stream) {
+  return relation_fwd_launch<true>(u1, u2, scale1, shift1, scale2, shift2, sf, z, rel, M, HW, C, C, stream);
+}
+// FSRelationV2 flavour (ever/module/fs_relation.py:142-163): fp32 scene vector / fp32 product, z rows of ldz elements
+extern "C" int evb_relation_fwd_v2(const void* u1, const void* u2, const float* scale1, const float* shift1,
+                                   const float* scale2, const float* shift2, const float* sf, void* z, int ldz, float* rel,
+                                   long long M, int HW, int C, void* stream) {
+  return relation_fwd_launch<false>(u1, u2, scale1, shift1, scale2, shift2, sf, z, rel, M, HW, C, ldz, stream);
 }
 static int relation_px_per_warp(int HW) {
   int p = 16;
@@ -535,10 +555,12 @@ extern "C" long long evb_relation_bwd_workspace(long long M, int HW, int C) {
   return (M / relation_px_per_warp(HW)) * (long long)C * sizeof(float);
 }
 // dsf[N][C] is overwritten: per-warp partial sums go to `ws` and are reduced in a fixed order (deterministic).
-extern "C" int evb_relation_bwd(const void* dz, const void* u1, const void* u2, const float* scale1, const float* shift1,
-                                const float* scale2, const float* shift2, const float* sf, const float* rel, void* g1,
-                                void* g2, float* dsf, long long M, int HW, int C, void* ws, void* stream) {
-  if ((C != 256 && C != 512 && C != 1024) || M % HW) return EVB_ERR_ARG;
+template <bool PR>
+static int relation_bwd_launch(const void* dz, int lddz, const void* u1, const void* u2, const float* scale1,
+                               const float* shift1, const float* scale2, const float* shift2, const float* sf,
+                               const float* rel, void* g1, void* g2, float* dsf, long long M, int HW, int C, void* ws,
+                               void* stream) {
+  if ((C != 256 && C != 512 && C != 1024) || M % HW || lddz < C || lddz % 8) return EVB_ERR_ARG;
   const int px_per_warp = relation_px_per_warp(HW);
   const long long warps = M / px_per_warp;
   const long long blocks = (warps + 7) / 8;
@@ -546,13 +568,25 @@ extern "C" int evb_relation_bwd(const void* dz, const void* u1, const void* u2, 
   __nv_bfloat16 *o1 = (__nv_bfloat16*)g1, *o2 = (__nv_bfloat16*)g2;
   float* part = (float*)ws;
   if (C == 256)
-    relation_bwd_kernel<1, 2><<<(int)blocks, 256, 0, ST>>>(d, a, b, scale1, shift1, scale2, shift2, sf, rel, o1, o2, part, M, HW, px_per_warp);
+    relation_bwd_kernel<1, 2, PR><<<(int)blocks, 256, 0, ST>>>(d, a, b, scale1, shift1, scale2, shift2, sf, rel, o1, o2, part, M, HW, px_per_warp, lddz);
   else if (C == 512)
-    relation_bwd_kernel<2, 1><<<(int)blocks, 256, 0, ST>>>(d, a, b, scale1, shift1, scale2, shift2, sf, rel, o1, o2, part, M, HW, px_per_warp);
+    relation_bwd_kernel<2, 1, PR><<<(int)blocks, 256, 0, ST>>>(d, a, b, scale1, shift1, scale2, shift2, sf, rel, o1, o2, part, M, HW, px_per_warp, lddz);
   else
-    relation_bwd_kernel<4, 1><<<(int)blocks, 256, 0, ST>>>(d, a, b, scale1, shift1, scale2, shift2, sf, rel, o1, o2, part, M, HW, px_per_warp);
+    relation_bwd_kernel<4, 1, PR><<<(int)blocks, 256, 0, ST>>>(d, a, b, scale1, shift1, scale2, shift2, sf, rel, o1, o2, part, M, HW, px_per_warp, lddz);
   relation_dsf_reduce_kernel<<<dim3(C / 32, (unsigned)(M / HW)), dim3(32, 8), 0, ST>>>(part, dsf, HW / px_per_warp, C);
   return LAUNCH_OK();
+}
+extern "C" int evb_relation_bwd(const void* dz, const void* u1, const void* u2, const float* scale1, const float* shift1,
+                                const float* scale2, const float* shift2, const float* sf, const float* rel, void* g1,
+                                void* g2, float* dsf, long long M, int HW, int C, void* ws, void* stream) {
+  return relation_bwd_launch<true>(dz, C, u1, u2, scale1, shift1, scale2, shift2, sf, rel, g1, g2, dsf, M, HW, C, ws, stream);
+}
+extern "C" int evb_relation_bwd_v2(const void* dz, int lddz, const void* u1, const void* u2, const float* scale1,
+                                   const float* shift1, const float* scale2, const float* shift2, const float* sf,
+                                   const float* rel, void* g1, void* g2, float* dsf, long long M, int HW, int C, void* ws,
+                                   void* stream) {
+  return relation_bwd_launch<false>(dz, lddz, u1, u2, scale1, shift1, scale2, shift2, sf, rel, g1, g2, dsf, M, HW, C, ws,
+                                    stream);
 }
 
 extern "C" int evb_linear_fwd(const float* x, const float* W, const float* b, float* y, int N, int I, int O, int relu,

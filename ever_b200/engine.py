@@ -126,6 +126,9 @@ class FarSegEngine:
         self._prio = -1 if os.environ.get('EVB_PRIORITY', '1') == '1' else 0
         self.level_streams = ([torch.cuda.Stream(device=self.dev, priority=self._prio) for _ in range(3)]
                               if os.environ.get('EVB_NO_LEVEL_STREAMS', '0') != '1' else None)
+        if self.fs_v2 and self.scene_shared:
+            # a shared FSRelationV2 `project` BatchNorm updates its running statistics once per level: keep the level order
+            self.level_streams = None
         # weight gradients run on a second stream (parallel graph branch): they overlap the dgrad / BN chain
         self.side = torch.cuda.Stream(device=self.dev) if os.environ.get('EVB_NO_SIDE_STREAM', '0') != '1' else None
         self.accumulate = False      # gradient accumulation into existing .grad (forward_times > 1)
@@ -284,6 +287,16 @@ class FarSegEngine:
                       else [(s[0], s[2]) for s in fs.scene_encoder])
         self.content = [(C(s[0]), BNP_(s[1])) for s in fs.content_encoders]
         self.reenc = [(C(s[0]), BNP_(s[1])) for s in fs.feature_reencoders]
+        # FSRelationV2 (fs_relation.py:76-163): GroupNorm scene encoder, `project` conv on cat([r * p, p]), Dropout2d
+        self.fs_v2 = getattr(fs, 'version', 1) == 2
+        self.project, self.drop_p = None, 0.0
+        if self.fs_v2:
+            encs = [fs.scene_encoder] if self.scene_shared else list(fs.scene_encoder)
+            self.scene = [(s[0], s[1], s[3], s[4], s[5]) for s in encs]     # conv, GN, conv, GN, final ReLU (its name)
+            projs = [fs.project] if self.scene_shared else list(fs.project)
+            pj = [(C(s[0]), BNP_(s[1]), s[3]) for s in projs]
+            self.project = pj * 4 if self.scene_shared else pj
+            self.drop_p = float(fs.dropout_p)
         dec = h.fpn_decoder
         self.dec_blocks = [[(C(layer[0]), BNP_(layer[1])) for layer in blk] for blk in dec.blocks]
         self.dec_nup = list(dec.num_upsample)
@@ -814,6 +827,72 @@ class FarSegEngine:
             self.tape.append(bwd)
         return sf, dsf
 
+    def _scene_mlp_v2(self, scene, n, mods, train, dscene, extra=()):
+        """FSRelationV2 scene encoder (fs_relation.py:86-96): 1x1 conv -> GroupNorm(32) -> ReLU, twice, on the N x C5 scene
+        vector; the second ReLU output stays fp32 (autocast runs group_norm in fp32), the first is consumed by a bf16 conv."""
+        L = self.L
+        l1, g1, l2, g2, last = mods
+        c5, co, G = scene.shape[1], l1.out_channels, g1.num_groups
+        h1, a1, h2, sf = (self._new(n, co, dtype=torch.float32) for _ in range(4))
+        st1, st2 = self._new(n, G, 2, dtype=torch.float32), self._new(n, G, 2, dtype=torch.float32)
+        st = stream()
+        check(L.evb_linear_fwd(ptr(scene), ptr(l1.weight), ptr(l1.bias), ptr(h1), c_int(n), c_int(c5), c_int(co), c_int(0), st),
+              'evb_linear_fwd')
+        check(L.evb_groupnorm_relu_fwd(ptr(h1), ptr(g1.weight), ptr(g1.bias), ptr(a1), ptr(st1), c_int(n), c_int(co), c_int(G),
+                                       c_float(g1.eps), c_int(1), st), 'evb_groupnorm_relu_fwd')
+        check(L.evb_linear_fwd(ptr(a1), ptr(l2.weight), ptr(l2.bias), ptr(h2), c_int(n), c_int(co), c_int(co), c_int(0), st),
+              'evb_linear_fwd')
+        check(L.evb_groupnorm_relu_fwd(ptr(h2), ptr(g2.weight), ptr(g2.bias), ptr(sf), ptr(st2), c_int(n), c_int(co), c_int(G),
+                                       c_float(g2.eps), c_int(0), st), 'evb_groupnorm_relu_fwd')
+        dsf = self._new(n, co, dtype=torch.float32) if train else None
+        sf_name = None
+        if self.tf is not None:
+            sf_name = {id(mod): path for path, mod in self.m.named_modules()}.get(id(last))
+            self.tf('fwd', sf_name, sf)
+        if train:
+            def bwd():
+                acc = c_int(1 if self.accumulate else 0)
+                st_ = stream()
+                for d in extra:
+                    check(L.evb_copy2d_f32(ptr(d), c_int(co), ptr(dsf), c_int(co), c_int(n), c_int(co), c_int(1), st_),
+                          'evb_copy2d_f32')
+                if self.tf is not None:
+                    self.tf('bwd', sf_name, dsf)
+                dh2, da1, dh1 = (self._new(n, co, dtype=torch.float32) for _ in range(3))
+                check(L.evb_groupnorm_relu_bwd(ptr(dsf), ptr(h2), ptr(sf), ptr(g2.weight), ptr(st2), ptr(dh2),
+                                               ptr(self._g(g2.weight)), ptr(self._g(g2.bias)), c_int(n), c_int(co), c_int(G), acc,
+                                               st_), 'evb_groupnorm_relu_bwd')
+                check(L.evb_linear_bwd(ptr(dh2), ptr(h2), ptr(a1), ptr(l2.weight), ptr(self._g(l2.weight)), ptr(self._g(l2.bias)),
+                                       ptr(da1), c_int(n), c_int(co), c_int(co), c_int(0), acc, c_int(0), st_), 'evb_linear_bwd')
+                check(L.evb_groupnorm_relu_bwd(ptr(da1), ptr(h1), ptr(a1), ptr(g1.weight), ptr(st1), ptr(dh1),
+                                               ptr(self._g(g1.weight)), ptr(self._g(g1.bias)), c_int(n), c_int(co), c_int(G), acc,
+                                               st_), 'evb_groupnorm_relu_bwd')
+                check(L.evb_linear_bwd(ptr(dh1), ptr(h1), ptr(scene), ptr(l1.weight), ptr(self._g(l1.weight)),
+                                       ptr(self._g(l1.bias)), ptr(dscene), c_int(n), c_int(c5), c_int(co), c_int(0), acc, c_int(0),
+                                       st_), 'evb_linear_bwd')
+            self.tape.append(bwd)
+        return sf, dsf
+
+    def dropout2d(self, x, mask, name=None):
+        """nn.Dropout2d in training mode: y = bf16(x * mask[n, c]); the backward is the same map on the gradient"""
+        L = self.L
+        n, h, w, c = x.data.shape
+        y = Act(self._new(n, h, w, c))
+        check(L.evb_channel_scale(ptr(x.data), ptr(mask), ptr(y.data), c_int(n), c_ll(h * w), c_int(c), stream()),
+              'evb_channel_scale')
+        self._tf_fwd(y, name)
+
+        def bwd():
+            if y.grad is None:
+                return
+            self._tf_bwd(y)
+            g, acc = self._grad_into(x)
+            assert not acc
+            check(L.evb_channel_scale(ptr(y.grad), ptr(mask), ptr(g), c_int(n), c_ll(h * w), c_int(c), stream()),
+                  'evb_channel_scale')
+        self.tape.append(bwd)
+        return y
+
     def _level(self, i, inner_i, sf_pair, train, scene=None, dscenes=None):
         """one pyramid level: [its scene MLP ->] p_i = fpn_layer(inner_i) -> FS-Relation -> decoder chain (runs on the
         caller's stream).  With scale_aware_proj the level owns its scene MLP (sf_pair None): the four tiny-linear chains run
@@ -824,8 +903,11 @@ class FarSegEngine:
             dsc = self._new(n_, scene.shape[1], dtype=torch.float32) if train else None
             if train:
                 dscenes.append(dsc)
-            l1, l2 = self.scene[i]
-            sf_pair = self._scene_mlp_one(scene, n_, l1, l2, train, dsc)
+            if self.fs_v2:
+                sf_pair = self._scene_mlp_v2(scene, n_, self.scene[i], train, dsc)
+            else:
+                l1, l2 = self.scene[i]
+                sf_pair = self._scene_mlp_one(scene, n_, l1, l2, train, dsc)
         p = self.conv(inner_i, self.fpn_layer[i], train=train)
         self._dbg('p%d' % (i + 2), p)
         (cc, cb), (rc, rb) = self.content[i], self.reenc[i]
@@ -836,9 +918,11 @@ class FarSegEngine:
         f2 = self._bn_fold(u2, rb, train)
         nn_, hh, ww, c = u1.data.shape
         m_rows = nn_ * hh * ww
+        sf, dsf = sf_pair
+        if self.fs_v2:
+            return self._level_v2(i, p, u1, u2, cb, rb, f1, f2, sf, dsf, train)
         z = Act(self._new(nn_, hh, ww, c))
         rel = self._new(m_rows, dtype=torch.float32)
-        sf, dsf = sf_pair
         check(L.evb_relation_fwd(ptr(u1.data), ptr(u2.data), ptr(f1[2]), ptr(f1[3]), ptr(f2[2]), ptr(f2[3]), ptr(sf),
                                  ptr(z.data), ptr(rel), c_ll(m_rows), c_int(hh * ww), c_int(c), stream()), 'evb_relation_fwd')
         d0 = self.dec_blocks[i][0][0]
@@ -861,6 +945,52 @@ class FarSegEngine:
         self._dbg('z%d' % i, z)
         self._dbg('rel%d' % i, rel)
         self._dbg('sf%d' % i, sf)
+        return self._decoder_chain(i, z, train)
+
+    def _level_v2(self, i, p, u1, u2, cb, rb, f1, f2, sf, dsf, train):
+        """FSRelationV2 tail of a level (fs_relation.py:142-163): cat([r * reenc(p), p]) -> project (1x1 conv 2C -> C, BN,
+        ReLU, Dropout2d) -> decoder chain.  The concatenation is one [N, H, W, 2C] buffer: the relation kernel writes its
+        first half, a strided copy the second; backward splits the buffer's gradient the same way."""
+        L = self.L
+        nn_, hh, ww, c = u1.data.shape
+        m_rows = nn_ * hh * ww
+        pc, pb, drop_mod = self.project[i]
+        named = pc.name is not None and not self.scene_shared    # a shared `project` is called once per level: no unique path
+        cat = Act(self._new(nn_, hh, ww, 2 * c))
+        rel = self._new(m_rows, dtype=torch.float32)
+        second = ctypes.c_void_p(cat.data.data_ptr() + 2 * c)
+        check(L.evb_relation_fwd_v2(ptr(u1.data), ptr(u2.data), ptr(f1[2]), ptr(f1[3]), ptr(f2[2]), ptr(f2[3]), ptr(sf),
+                                    ptr(cat.data), c_int(2 * c), ptr(rel), c_ll(m_rows), c_int(hh * ww), c_int(c), stream()),
+              'evb_relation_fwd_v2')
+        check(L.evb_copy2d_bf16(ptr(p.data), c_int(c), second, c_int(2 * c), c_ll(m_rows), c_int(c), c_int(0), stream()),
+              'evb_copy2d_bf16')
+        self._tf_fwd(cat, pc.name + ':in' if named else None)
+        if train:
+            def bwd():
+                if cat.grad is None:
+                    return
+                self._tf_bwd(cat)
+                g1 = self._new(*u1.data.shape)
+                g2 = self._new(*u2.data.shape)
+                ws = self._ws(L.evb_relation_bwd_workspace(c_ll(m_rows), c_int(hh * ww), c_int(c)))
+                check(L.evb_relation_bwd_v2(ptr(cat.grad), c_int(2 * c), ptr(u1.data), ptr(u2.data), ptr(f1[2]), ptr(f1[3]),
+                                            ptr(f2[2]), ptr(f2[3]), ptr(sf), ptr(rel), ptr(g1), ptr(g2), ptr(dsf), c_ll(m_rows),
+                                            c_int(hh * ww), c_int(c), ptr(ws), stream()), 'evb_relation_bwd_v2')
+                gp, acc = self._grad_into(p)    # d(cat)[..., C:] flows straight into d(p)
+                check(L.evb_copy2d_bf16(ctypes.c_void_p(cat.grad.data_ptr() + 2 * c), c_int(2 * c), ptr(gp), c_int(c),
+                                        c_ll(m_rows), c_int(c), c_int(1 if acc else 0), stream()), 'evb_copy2d_bf16')
+                self._bn_backward(g1, u1, cb, f1, 0, None, None)
+                self._bn_backward(g2, u2, rb, f2, 0, None, None)
+            self.tape.append(bwd)
+        q = self.conv(cat, pc, train=train, stats=train)
+        pfx = pc.name.rsplit('.', 1)[0] if named else None
+        y = self.bn_act(q, pb, True, train=train, name=pfx + '.2' if pfx else None)
+        if train and self.drop_p > 0 and drop_mod.training:
+            y = self.dropout2d(y, self._drop_masks[i], name=pfx + '.3' if pfx else None)
+        self._dbg('z%d' % i, y)
+        return self._decoder_chain(i, y, train)
+
+    def _decoder_chain(self, i, z, train):
         y = z
         for (cp, bp) in self.dec_blocks[i]:
             o = self.conv(y, cp, train=train, stats=train)
@@ -914,15 +1044,26 @@ class FarSegEngine:
         if self.scene_shared:
             # scale_aware_proj=False (fs_relation.py:29-35,63-66): one MLP on the main stream, every level reads the same
             # scene vector; each level's relation backward writes its own d(sf) buffer, summed before the MLP's backward
-            l1, l2 = self.scene[0]
+            l1 = self.scene[0][0]
             extra = [self._new(n, l1.out_channels, dtype=torch.float32) if train else None for _ in range(3)]
             dsc = self._new(n, cc5, dtype=torch.float32) if train else None
             if train:
                 dscenes.append(dsc)
-            sf, dsf = self._scene_mlp_one(scene, n, l1, l2, train, dsc, extra=extra if train else ())
+            if self.fs_v2:
+                sf, dsf = self._scene_mlp_v2(scene, n, self.scene[0], train, dsc, extra=extra if train else ())
+            else:
+                sf, dsf = self._scene_mlp_one(scene, n, l1, self.scene[0][1], train, dsc, extra=extra if train else ())
             sfs = [(sf, dsf)] + [(sf, e) for e in extra]
         else:
             sfs = [None] * 4
+        if self.fs_v2 and train and self.drop_p > 0:
+            # Dropout2d channel masks of the four `project` blocks, drawn in level order from torch's generator exactly as
+            # feature_dropout does (bf16 noise of shape [N, C, 1, 1]: bernoulli_(1 - p) then div_(1 - p)), so a run seeded
+            # like the reference drops the same channels
+            keep = 1.0 - self.drop_p
+            cdrop = self.project[0][0].co
+            self._drop_masks = [torch.empty(n, cdrop, 1, 1, dtype=BF16, device=self.dev).bernoulli_(keep).div_(keep)
+                                .float().view(n, cdrop).contiguous() for _ in range(4)]
         # ---- per pyramid level: FPN output conv -> FS-Relation -> decoder chain.  The four chains are independent:
         #      levels 1..3 (small maps, latency-bound kernels) run on their own streams = parallel graph branches
         outs = [None] * 4

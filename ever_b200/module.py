@@ -114,6 +114,36 @@ class _FSRelation(nn.Module):
             [nn.Sequential(nn.Conv2d(c, out_channels, 1), nn.BatchNorm2d(out_channels), nn.ReLU(True)) for c in in_channels_list])
 
 
+class _FSRelationV2(nn.Module):
+    """Parameter container of FSRelationV2 (ever/module/fs_relation.py:76-139): scene encoder = conv1x1 -> GroupNorm(32) ->
+    ReLU, twice; `project` = conv1x1(2C -> C, no bias) -> BN -> ReLU -> Dropout2d(0.1) on cat([r * p, p])."""
+    version = 2
+    dropout_p = 0.1
+
+    def __init__(self, scene_embedding_channels, in_channels_list, out_channels, scale_aware_proj=True):
+        super().__init__()
+        self.scale_aware_proj = bool(scale_aware_proj)
+
+        def scene():
+            return nn.Sequential(nn.Conv2d(scene_embedding_channels, out_channels, 1), nn.GroupNorm(32, out_channels),
+                                 nn.ReLU(True), nn.Conv2d(out_channels, out_channels, 1), nn.GroupNorm(32, out_channels),
+                                 nn.ReLU(True))
+
+        def project():
+            return nn.Sequential(nn.Conv2d(out_channels * 2, out_channels, 1, bias=False), nn.BatchNorm2d(out_channels),
+                                 nn.ReLU(True), nn.Dropout2d(p=self.dropout_p))
+        if self.scale_aware_proj:
+            self.scene_encoder = nn.ModuleList([scene() for _ in in_channels_list])
+            self.project = nn.ModuleList([project() for _ in in_channels_list])
+        else:
+            self.scene_encoder = scene()
+            self.project = project()
+        self.content_encoders = nn.ModuleList(
+            [nn.Sequential(nn.Conv2d(c, out_channels, 1), nn.BatchNorm2d(out_channels), nn.ReLU(True)) for c in in_channels_list])
+        self.feature_reencoders = nn.ModuleList(
+            [nn.Sequential(nn.Conv2d(c, out_channels, 1), nn.BatchNorm2d(out_channels), nn.ReLU(True)) for c in in_channels_list])
+
+
 class _Decoder(nn.Module):
     def __init__(self, in_channels, out_channels, in_feat_output_strides=(4, 8, 16, 32), out_feat_output_stride=4,
                  classifier_config=None):
@@ -144,8 +174,14 @@ class _Head(nn.Module):
         super().__init__()
         self.fpn = _FPN(tuple(cfg.fpn.in_channels_list), int(cfg.fpn.out_channels))
         fs = cfg.fs_relation
-        self.fs_relation = _FSRelation(int(fs.scene_embedding_channels), tuple(fs.in_channels_list), int(fs.out_channels),
-                                       bool(fs.scale_aware_proj))
+        # fs_relation.version = 2 selects FSRelationV2 (the reference's FarSegHead hard-wires FSRelation, fs_relation.py:171;
+        # heads built on FSRelationV2 -- FarSeg++ -- construct it with the same keyword arguments)
+        ver = int(fs.get('version', 1)) if hasattr(fs, 'get') else 1
+        if ver not in (1, 2):
+            raise ValueError('head.fs_relation.version must be 1 (FSRelation) or 2 (FSRelationV2)')
+        rel_cls = _FSRelationV2 if ver == 2 else _FSRelation
+        self.fs_relation = rel_cls(int(fs.scene_embedding_channels), tuple(fs.in_channels_list), int(fs.out_channels),
+                                   bool(fs.scale_aware_proj))
         d = cfg.fpn_decoder
         self.fpn_decoder = _Decoder(int(d.in_channels), int(d.out_channels), tuple(d.in_feat_output_strides),
                                     int(d.out_feat_output_stride), d.classifier_config)
@@ -290,7 +326,7 @@ class FarSegB200(ERModule):
             head=dict(
                 fpn=dict(in_channels_list=(256, 512, 1024, 2048), out_channels=256),
                 fs_relation=dict(scene_embedding_channels=2048, in_channels_list=(256, 256, 256, 256), out_channels=256,
-                                 scale_aware_proj=True),
+                                 scale_aware_proj=True, version=1),
                 fpn_decoder=dict(in_channels=256, out_channels=256, in_feat_output_strides=(4, 8, 16, 32),
                                  out_feat_output_stride=4,
                                  classifier_config=dict(scale_factor=4.0, num_classes=1, kernel_size=1))),

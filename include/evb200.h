@@ -150,6 +150,27 @@ long long evb_relation_bwd_workspace(long long M, int HW, int C);
 int evb_relation_bwd(const void* dz, const void* u1, const void* u2, const float* scale1, const float* shift1,
                      const float* scale2, const float* shift2, const float* sf, const float* rel, void* g1, void* g2,
                      float* dsf, long long M, int HW, int C, void* ws, void* stream);
+/* FSRelationV2 (ever/module/fs_relation.py:76-163).  Relation with an fp32 scene vector / fp32 product (the scene encoder
+ * ends in GroupNorm + ReLU, which autocast runs in fp32) and strided rows: z is written into the first C of ldz elements per
+ * pixel (the [r * p, p] concatenation buffer, :156), dz is read with row stride lddz. */
+int evb_relation_fwd_v2(const void* u1, const void* u2, const float* scale1, const float* shift1, const float* scale2,
+                        const float* shift2, const float* sf, void* z, int ldz, float* rel, long long M, int HW, int C,
+                        void* stream);
+int evb_relation_bwd_v2(const void* dz, int lddz, const void* u1, const void* u2, const float* scale1, const float* shift1,
+                        const float* scale2, const float* shift2, const float* sf, const float* rel, void* g1, void* g2,
+                        float* dsf, long long M, int HW, int C, void* ws, void* stream);
+/* y = relu(GroupNorm(G)(x)) on the N x C scene vector (nn.GroupNorm(32, C) + nn.ReLU, fs_relation.py:89-94); stat[N][G][2] =
+ * {mean, rstd} saved for the backward; dgamma / dbeta (+)= sums over the batch in fixed order */
+int evb_groupnorm_relu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* stat, int N, int C, int G,
+                           float eps, int round_out_bf16, void* stream);
+int evb_groupnorm_relu_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* stat, float* dx,
+                           float* dgamma, float* dbeta, int N, int C, int G, int accumulate, void* stream);
+/* dst[r][0:cols] (+)= src[r][0:cols] for bf16 rows with strides lds / ldd (elements; all % 8): torch.cat(dim=1) of NHWC
+ * tensors and its backward split (fs_relation.py:156) */
+int evb_copy2d_bf16(const void* src, int lds, void* dst, int ldd, long long rows, int cols, int accumulate, void* stream);
+/* y[n,hw,c] = bf16(x[n,hw,c] * m[n,c]): nn.Dropout2d (fs_relation.py:101,118) forward and backward; m = the {0, 1/(1-p)}
+ * channel mask the caller draws with torch's own generator (same Philox stream as the reference's feature_dropout) */
+int evb_channel_scale(const void* x, const float* m, void* y, int N, long long HW, int C, void* stream);
 int evb_linear_fwd(const float* x, const float* W, const float* b, float* y, int N, int I, int O, int relu, void* stream);
 int evb_linear_bwd(const float* dy, const float* y, const float* x, const float* W, float* dW, float* db, float* dx, int N,
                    int I, int O, int relu, int acc_w, int acc_x, void* stream);

@@ -257,6 +257,50 @@ class FSRelationOracle(nn.Module):
         return [r * p for r, p in zip(rel, pfs)]
 
 
+class FSRelationV2Oracle(nn.Module):
+    """FSRelationV2, reference ever/module/fs_relation.py:76-163: scene encoder = (1x1 conv, GroupNorm(32), ReLU) x 2
+    (:86-96 / :107-114), relation as in FSRelation (:142-152), refined = cat([r * p, o]) (:156), `project` = 1x1 conv
+    (2C -> C, no bias) + BN + ReLU + Dropout2d(0.1) (:97-104 / :115-120, applied :158-161)."""
+
+    def __init__(self, scene_embedding_channels, in_channels_list, out_channels, scale_aware_proj=True):
+        super().__init__()
+        self.scale_aware_proj = scale_aware_proj
+
+        def scene():
+            return nn.Sequential(nn.Conv2d(scene_embedding_channels, out_channels, 1), nn.GroupNorm(32, out_channels),
+                                 nn.ReLU(True), nn.Conv2d(out_channels, out_channels, 1), nn.GroupNorm(32, out_channels),
+                                 nn.ReLU(True))
+
+        def project():
+            return nn.Sequential(nn.Conv2d(out_channels * 2, out_channels, 1, bias=False), nn.BatchNorm2d(out_channels),
+                                 nn.ReLU(True), nn.Dropout2d(p=0.1))
+        if scale_aware_proj:
+            self.scene_encoder = nn.ModuleList([scene() for _ in in_channels_list])
+            self.project = nn.ModuleList([project() for _ in in_channels_list])
+        else:
+            self.scene_encoder = scene()
+            self.project = project()
+        self.content_encoders = nn.ModuleList()
+        self.feature_reencoders = nn.ModuleList()
+        for c in in_channels_list:
+            self.content_encoders.append(nn.Sequential(nn.Conv2d(c, out_channels, 1), nn.BatchNorm2d(out_channels), nn.ReLU(True)))
+            self.feature_reencoders.append(nn.Sequential(nn.Conv2d(c, out_channels, 1), nn.BatchNorm2d(out_channels), nn.ReLU(True)))
+
+    def forward(self, scene, feats):
+        cfs = [enc(p) for enc, p in zip(self.content_encoders, feats)]
+        if self.scale_aware_proj:
+            sfs = [enc(scene) for enc in self.scene_encoder]
+            rel = [torch.sigmoid((sf * cf).sum(dim=1, keepdim=True)) for sf, cf in zip(sfs, cfs)]
+        else:
+            sf = self.scene_encoder(scene)
+            rel = [torch.sigmoid((sf * cf).sum(dim=1, keepdim=True)) for cf in cfs]
+        pfs = [enc(p) for enc, p in zip(self.feature_reencoders, feats)]
+        refined = [torch.cat([r * p, o], dim=1) for r, p, o in zip(rel, pfs, feats)]
+        if self.scale_aware_proj:
+            return [op(x) for op, x in zip(self.project, refined)]
+        return [self.project(x) for x in refined]
+
+
 class DecoderOracle(nn.Module):
     """AssymetricDecoder, reference ever/module/fpn.py:144-193."""
 
@@ -289,10 +333,11 @@ class FarSegHeadOracle(nn.Module):
     """FarSegHead.forward, reference ever/module/fs_relation.py:166-206."""
 
     def __init__(self, in_channels_list=(256, 512, 1024, 2048), fpn_channels=256, decoder_channels=256, num_classes=1,
-                 scale_aware_proj=True, classifier_kernel_size=1):
+                 scale_aware_proj=True, classifier_kernel_size=1, fs_version=1):
         super().__init__()
         self.fpn = FPNOracle(in_channels_list, fpn_channels)
-        self.fs_relation = FSRelationOracle(in_channels_list[-1], (fpn_channels,) * 4, fpn_channels, scale_aware_proj)
+        rel_cls = FSRelationV2Oracle if fs_version == 2 else FSRelationOracle
+        self.fs_relation = rel_cls(in_channels_list[-1], (fpn_channels,) * 4, fpn_channels, scale_aware_proj)
         self.fpn_decoder = DecoderOracle(fpn_channels, decoder_channels, num_classes=num_classes,
                                          kernel_size=classifier_kernel_size)
 
@@ -341,11 +386,11 @@ class FarSegOracle(nn.Module):
     in training, softmax probabilities in eval."""
 
     def __init__(self, resnet_type='resnet50', num_classes=15, decoder_channels=256, in_channels=3, freeze_at=0,
-                 batchnorm_trainable=True, scale_aware_proj=True, classifier_kernel_size=1):
+                 batchnorm_trainable=True, scale_aware_proj=True, classifier_kernel_size=1, fs_version=1):
         super().__init__()
         self.en = ResNetEncoderOracle(resnet_type, in_channels, freeze_at, batchnorm_trainable)
         self.head = FarSegHeadOracle(self.en.out_channels, 256, decoder_channels, num_classes, scale_aware_proj,
-                                     classifier_kernel_size)
+                                     classifier_kernel_size, fs_version)
         self.dice_all_reduce = None
 
     def logits(self, x):

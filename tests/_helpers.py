@@ -34,7 +34,7 @@ class RefCapture:
         import torch.nn as nn
         self.fwd, self.bwd, self.handles, self._calls = {}, {}, [], {}
         for name, mod in model.named_modules():
-            leafish = isinstance(mod, (nn.Conv2d, nn.ReLU, nn.MaxPool2d, nn.Identity)) or \
+            leafish = isinstance(mod, (nn.Conv2d, nn.ReLU, nn.MaxPool2d, nn.Identity, nn.Dropout2d)) or \
                 type(mod).__name__ in ('_Fp32Around', 'Bf16compatible') or \
                 (isinstance(mod, nn.BatchNorm2d) and '.downsample.' in name)
             if not leafish:

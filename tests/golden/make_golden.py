@@ -31,7 +31,10 @@ CASES = {
     # deep-stem ResNet (three 3x3 convs, _resnets.py:137-147)
     'r50v1c_k5_1x64': ('resnet50_v1c', 5, 1, 64, 64, 128),
     'r18_k5_c8_shared_2x64': ('resnet18', 5, 2, 64, 64, 128, dict(in_channels=8, scale_aware_proj=False)),
+    # FSRelationV2 (fs_relation.py:76-163) swapped into the head; Dropout2d draws from torch.manual_seed(DROP_SEED)
+    'r18_k5_v2_2x64': ('resnet18', 5, 2, 64, 64, 128, dict(fs_version=2)),
 }
+DROP_SEED = 20240
 
 
 class RefFarSeg(er.ERModule):
@@ -39,6 +42,9 @@ class RefFarSeg(er.ERModule):
         super().__init__(config)
         self.en = erm.ResNetEncoder(self.config.encoder)
         self.head = erm.FarSegHead(self.config.head)
+        if int(self.config.get('fs_version', 1)) == 2:   # the reference's own FSRelationV2 in place of FSRelation
+            from ever.module.fs_relation import FSRelationV2
+            self.head.fs_relation = FSRelationV2(**self.head.config.fs_relation)
 
     def forward(self, x, y=None):
         logit = self.head(self.en(x))
@@ -51,9 +57,9 @@ class RefFarSeg(er.ERModule):
         self.config.update(dict(encoder=dict(), head=dict()))
 
 
-def ref_config(resnet, k, dec, in_channels=3, scale_aware_proj=True):
+def ref_config(resnet, k, dec, in_channels=3, scale_aware_proj=True, fs_version=1):
     chans = (64, 128, 256, 512) if resnet in ('resnet18', 'resnet34') else (256, 512, 1024, 2048)
-    return dict(encoder=dict(resnet_type=resnet, in_channels=in_channels),
+    return dict(fs_version=fs_version, encoder=dict(resnet_type=resnet, in_channels=in_channels),
                 head=dict(fpn=dict(in_channels_list=chans, out_channels=256),
                           fs_relation=dict(scene_embedding_channels=chans[-1], scale_aware_proj=scale_aware_proj),
                           fpn_decoder=dict(out_channels=dec, classifier_config=dict(num_classes=k, scale_factor=4.0, kernel_size=1))))
@@ -74,6 +80,7 @@ def run_case(name):
                       dice_loss=dice_loss_with_logits(logit, y, ignore_index=255))
     else:
         m.train()
+        torch.manual_seed(DROP_SEED)
         losses, logit = m(x, dict(cls=y))
     sum(losses.values()).backward()
     gsum = {kk: float(p.grad.double().sum()) for kk, p in m.named_parameters()}

@@ -46,12 +46,16 @@ def test_sass_has_tcgen05_and_tma():
 
 @pytest.mark.parametrize('resnet,k,dec,opts', [('resnet18', 5, 128, {}), ('resnet50', 15, 256, {}), ('resnet101', 7, 256, {}),
                                                ('resnet18', 5, 128, dict(in_channels=8, scale_aware_proj=False)),
-                                               ('resnet50_v1c', 5, 128, {})])
+                                               ('resnet50_v1c', 5, 128, {}),
+                                               # FSRelationV2 (per-level and shared), keys as ever/module/fs_relation.py:76-139
+                                               ('resnet18', 5, 128, dict(fs_version=2)),
+                                               ('resnet18', 5, 128, dict(fs_version=2, scale_aware_proj=False))])
 def test_state_dict_contract(resnet, k, dec, opts):
     from ever_b200.module import FarSegB200
     from oracle.farseg_oracle import FarSegOracle
     m = FarSegB200(dict(encoder=dict(resnet_type=resnet, in_channels=opts.get('in_channels', 3), with_cp=(True, True, False, False)),
-                        head=dict(fs_relation=dict(scale_aware_proj=opts.get('scale_aware_proj', True)),
+                        head=dict(fs_relation=dict(scale_aware_proj=opts.get('scale_aware_proj', True),
+                                                   version=opts.get('fs_version', 1)),
                                   fpn_decoder=dict(out_channels=dec, classifier_config=dict(num_classes=k)))))
     o = FarSegOracle(resnet, k, dec, **opts)
     a = [(n, tuple(v.shape), v.dtype) for n, v in m.state_dict().items()]

@@ -12,7 +12,8 @@ import torch.nn.functional as F
 from oracle.farseg_oracle import (FarSegOracle, bce_loss_oracle, deterministic_fill, dice_loss_oracle,
                                   synthetic_batch)
 
-CASES = ['r18_k5_2x64', 'r50_k15_1x64', 'r18_k1_2x64', 'r18_k5_c8_shared_2x64', 'r50v1c_k5_1x64']
+CASES = ['r18_k5_2x64', 'r50_k15_1x64', 'r18_k1_2x64', 'r18_k5_c8_shared_2x64', 'r50v1c_k5_1x64', 'r18_k5_v2_2x64']
+DROP_SEED = 20240   # tests/golden/make_golden.py
 
 
 def _run_oracle(case):
@@ -25,6 +26,7 @@ def _run_oracle(case):
         logit = m.logits(x)
         losses = dict(bce_loss=bce_loss_oracle(logit, y), dice_loss=dice_loss_oracle(logit, y))
     else:
+        torch.manual_seed(DROP_SEED)
         logit = m.logits(x)
         losses = dict(ce_loss=F.cross_entropy(logit, y.long(), ignore_index=255), dice_loss=dice_loss_oracle(logit, y))
     sum(losses.values()).backward()
@@ -55,7 +57,7 @@ def test_oracle_matches_golden(name, golden_dir):
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/ever'), reason='reference tree only exists in the build container')
-@pytest.mark.parametrize('name', ['r18_k5_2x64', 'r18_k5_c8_shared_2x64', 'r50v1c_k5_1x64'])
+@pytest.mark.parametrize('name', ['r18_k5_2x64', 'r18_k5_c8_shared_2x64', 'r50v1c_k5_1x64', 'r18_k5_v2_2x64'])
 def test_oracle_bit_exact_vs_reference(name, golden_dir):
     for p_ in ('/root/reference', os.path.join(golden_dir, '_stubs'), golden_dir):
         if p_ not in sys.path:
@@ -69,7 +71,9 @@ def test_oracle_bit_exact_vs_reference(name, golden_dir):
     x, y = synthetic_batch(n, h, w, k, in_channels=opts.get('in_channels', 3))
     ref.train(), ora.train()
     torch.set_num_threads(8)
+    torch.manual_seed(DROP_SEED)
     lr, _ = ref(x, dict(cls=y))
+    torch.manual_seed(DROP_SEED)
     lo = ora(x, dict(cls=y))
     # ResNet-18 cases are bit-reproducible on the CPU; the ResNet-50 case is not even reference-vs-reference (a fresh copy
     # of the real reference differs from itself by ~3e-6 in 165 gradients: threaded MKL-DNN reductions), so it is compared

@@ -34,7 +34,8 @@ def _build(resnet, k, dec, **opts):
     from oracle.farseg_oracle import FarSegOracle, deterministic_fill
     ora = deterministic_fill(FarSegOracle(resnet, k, dec, **opts), 0)
     mine = FarSegB200(dict(encoder=dict(resnet_type=resnet, in_channels=opts.get('in_channels', 3)),
-                           head=dict(fs_relation=dict(scale_aware_proj=opts.get('scale_aware_proj', True)),
+                           head=dict(fs_relation=dict(scale_aware_proj=opts.get('scale_aware_proj', True),
+                                                      version=opts.get('fs_version', 1)),
                                      fpn_decoder=dict(out_channels=dec, classifier_config=dict(
                                          num_classes=k, kernel_size=opts.get('classifier_kernel_size', 1))))))
     mine.load_state_dict(ora.state_dict(), strict=True)
@@ -84,10 +85,15 @@ CASES = [
     # 3x3 classifier (classifier_config.kernel_size, ever/module/fpn.py:172-181) and more than 16 classes (32- / 64-wide logit rows)
     ('resnet18', 21, 128, 2, 128, 128, dict(classifier_kernel_size=3)),
     ('resnet18', 40, 128, 2, 128, 128, {}),
+    # FSRelationV2 (ever/module/fs_relation.py:76-163): GroupNorm scene encoder, concat + project conv, Dropout2d (both runs
+    # draw their channel masks from the same torch seed, so the same channels are dropped)
+    ('resnet18', 5, 128, 2, 128, 128, dict(fs_version=2)),
+    ('resnet50', 7, 256, 2, 256, 256, dict(fs_version=2)),
 ]
+DROP_SEED = 4242
 
 
-@pytest.mark.parametrize('case', CASES, ids=lambda c: '%s_k%d_%dx%d' % (c[0], c[1], c[3], c[4]) if isinstance(c, tuple) else None)
+@pytest.mark.parametrize('case', CASES, ids=lambda c: '%s_k%d_%dx%d%s' % (c[0], c[1], c[3], c[4], '_v2' if c[6].get('fs_version') == 2 else '') if isinstance(c, tuple) else None)
 def test_teacher_forced_step(case):
     from oracle.farseg_oracle import synthetic_batch
     resnet, k, dec, n, h, w, opts = case
@@ -96,10 +102,12 @@ def test_teacher_forced_step(case):
     ora, mine = _build(resnet, k, dec, **opts)
     x, y = synthetic_batch(n, h, w, max(k, 2))
     x, y = x.cuda(), y.cuda()
+    torch.manual_seed(DROP_SEED)
     cap, loss_ref = oracle_step_captured(ora, x, y)
     eng = mine._engine()
     tf = TeacherForcing(cap, force=True)
     eng.tf = tf
+    torch.manual_seed(DROP_SEED)
     out = mine(x, dict(cls=y))
     mine.backward(out, None, None)
     torch.cuda.synchronize()

@@ -13,9 +13,15 @@ def _conv_fwd(a):
     n, h, w, cin, cop, k, s, cout = _v(a[1]), _v(a[2]), _v(a[3]), _v(a[4]), _v(a[6]), _v(a[7]), _v(a[8]), _v(a[10])
     ho, wo = h // s, w // s
     b = 2 * (n * h * w * cin + n * ho * wo * cout + k * k * cop * cin)
-    if len(a) >= 16 and _v(a[12]):       # evb_conv2d_fwd: fused add operand (mode 2 = nearest-x2 of the coarser map)
-        b += 2 * n * ho * wo * cout // (4 if _v(a[13]) == 2 else 1)
     return b, 2 * n * ho * wo * cout * cin * k * k
+
+
+def _conv_fwd_add(a):   # evb_conv2d_fwd: optional fused add operand (mode 2 = nearest-x2 of the coarser map)
+    b, f = _conv_fwd(a)
+    if _v(a[12]):
+        n, h, w, s, cout = _v(a[1]), _v(a[2]), _v(a[3]), _v(a[8]), _v(a[10])
+        b += 2 * n * (h // s) * (w // s) * cout // (4 if _v(a[13]) == 2 else 1)
+    return b, f
 
 
 def _conv_dgrad(a):
@@ -76,12 +82,15 @@ def _im2col(kp_i, elem):
 
 
 TABLE = {
-    'evb_conv2d_fwd': _conv_fwd, 'evb_conv2d_fwd_stats': _conv_fwd, 'evb_conv2d_fwd_bias_stats': _conv_fwd,
+    'evb_conv2d_fwd': _conv_fwd_add, 'evb_conv2d_fwd_stats': _conv_fwd, 'evb_conv2d_fwd_bias_stats': _conv_fwd,
     'evb_conv2d_dgrad': _conv_dgrad, 'evb_conv2d_wgrad': _conv_wgrad,
     'evb_bn_apply': _bn_apply, 'evb_bn_bwd': _bn_bwd, 'evb_bn_stats': _rows_c(1, 2, 1),
     'evb_maxpool3x3s2_fwd': _maxpool_fwd, 'evb_maxpool3x3s2_bwd': _maxpool_bwd,
     'evb_bilinear_up': _bilinear, 'evb_bilinear_up_bwd_sep': _bilinear_bwd,
     'evb_relation_fwd': _rows_c(9, 11, 3), 'evb_relation_bwd': _rows_c(12, 14, 5),
+    'evb_relation_fwd_v2': _rows_c(10, 12, 3), 'evb_relation_bwd_v2': _rows_c(13, 15, 5),
+    'evb_copy2d_bf16': lambda a: (4 * _v(a[4]) * _v(a[5]), 0),
+    'evb_channel_scale': lambda a: (4 * _v(a[3]) * _v(a[4]) * _v(a[5]), 0),
     'evb_merge4': lambda a: (2 * 5 * _v(a[5]), 0),
     'evb_scale_add': lambda a: (2 * _v(a[4]) * (3 if _v(a[2]) else 2), 0),
     'evb_sumpool2': lambda a: (2 * _v(a[2]) * _v(a[3]) * _v(a[4]) * _v(a[5]) * (6 if _v(a[6]) else 5), 0),

@@ -45,7 +45,7 @@ CONFIGS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the ncu --set full capture
 # summarised in profiles/ (None until captured)
-NCU_TRAFFIC_BYTES = 68309248 + 24216576  # profiles/r01_ncu_full_prof_igemm2_3x3.txt
+NCU_TRAFFIC_BYTES = 68308480 + 23763968  # profiles/r02_ncu_full_igemm2_3x3_256_128.txt (dram__bytes_read + dram__bytes_write)
 
 
 def peaks():

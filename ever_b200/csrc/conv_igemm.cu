@@ -40,147 +40,6 @@ struct IgemmParams {
   float* stats;   // STATS kernels: BN partial sums [2][Cout][kNbPad], column = blockIdx / tiles_c
 };
 
-template <int NT>
-struct IgemmCfg {
-  static constexpr int A_BYTES = 128 * 128;
-  static constexpr int B_BYTES = NT * 128;
-  static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (NT == 256) ? 4 : (NT == 128) ? 6 : 8;
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
-};
-
-template <int NT>
-__global__ void __launch_bounds__(192, 1)
-igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ IgemmParams p) {
-  using Cfg = IgemmCfg<NT>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE);
-  uint64_t* empty = full + Cfg::STAGES;
-  uint64_t* tfull = empty + Cfg::STAGES;
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(tfull + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int t = blockIdx.x;
-  const int tc = t % p.tiles_c; t /= p.tiles_c;
-  const int tw = t % p.tiles_w; t /= p.tiles_w;
-  const int th = t % p.tiles_h;
-  const int tn = t / p.tiles_h;
-  const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, cout0 = tc * NT;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int i = 0; i < Cfg::STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
-    mbar_init(tfull, 1);
-    fence_barrier_init();
-    fence_proxy_async();
-  }
-  if (warp == 1) tmem_alloc(tslot, Cfg::TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t taddr = *tslot;
-  const int niter = p.ntaps * p.kblocks;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tap = 0; tap < p.ntaps; ++tap) {
-        const ConvTap tp = p.taps[tap];
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1, 0x100 + stage);
-          uint8_t* a_dst = smem + stage * Cfg::STAGE;
-          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE);
-          tma_load_5d(a_dst, &tmA, &full[stage], tp.coff + kb * 64, w0 + tp.dw, h0 + tp.dh, n0, tp.phase);
-          tma_load_3d(a_dst + Cfg::A_BYTES, &tmB, &full[stage], kb * 64, cout0, tp.slab);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, NT, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < niter; ++it) {
-        mbar_wait(&full[stage], phase, 0x200 + stage);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE);
-        const uint32_t b_base = a_base + Cfg::A_BYTES;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          umma_bf16(taddr, make_smem_desc(a_base + k * 32, 0, 1024), make_smem_desc(b_base + k * 32, 0, 1024), idesc,
-                    (it | k) != 0);
-        }
-        umma_commit(&empty[stage]);
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-      }
-      umma_commit(tfull);
-    }
-  } else {
-    // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int wl = r % p.bw, hl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
-    const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
-    const bool valid = (n < p.No) && (h < p.Ho) && (w < p.Wo);
-    __nv_bfloat16* orow = p.out + n * p.o_sn + h * p.o_sh + w * p.o_sw;
-    const __nv_bfloat16* arow = nullptr;
-    if (p.add_mode) arow = p.add + n * p.a_sn + (h >> p.add_shift) * p.a_sh + (w >> p.add_shift) * p.a_sw;
-    mbar_wait(tfull, 0, 0x300);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < NT / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(taddr + (uint32_t(q * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-      if (valid) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int ch = cout0 + c * 32 + g * 8;
-          if (ch < p.Cout) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-            if (p.bias) {
-              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + ch);
-              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + ch + 4);
-              // torch's bf16 convolution adds the bias as a separate bf16 op (cudnn_convolution, then output.add_(bias) with
-              // the autocast-cast bf16 bias): y = bf16(bf16(acc) + bf16(b)).  Mirrored bit for bit (99.997 % identical
-              // outputs on B200, tools/diag_tf.py); a single rounding of acc + b differs on 37 % of the elements.
-              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j]) + bf16_round(bb[j]);
-            }
-            if (p.add_mode) {
-              // reference adds two bf16 tensors: round the conv result first, then add, then round
-              float a[8];
-              unpack8(*reinterpret_cast<const bf16x8*>(arow + ch), a);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j]) + a[j];
-            }
-            *reinterpret_cast<bf16x8*>(orow + ch) = pack8(f);
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc(taddr, Cfg::TMEM_COLS);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // Persistent variant: one CTA per SM loops over output tiles.  The fp32 accumulator is double-buffered in TMEM
 // (2 x NT columns) so the epilogue of tile i (tcgen05.ld -> bias/add -> bf16 -> 128B-swizzled smem -> TMA store)
@@ -450,7 +309,6 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
 }
 
-static int g_igemm_variant = 2;   // 2 = persistent + TMA store (default), 1 = one tile per CTA, direct stores
 static int g_num_sms = 0;
 
 static int pow2_le(int x, int cap) {
@@ -478,20 +336,6 @@ static int make_a_map(CUtensorMap* m, const ADesc& a, int stride, int bw, int bh
     strides[2] = (uint64_t)a.H * a.W * a.C * 2; strides[3] = (uint64_t)a.W * a.C * 2;
   }
   return evb_make_tmap_bf16(m, a.ptr, 5, dims, strides, box);
-}
-
-template <int NT>
-static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t st) {
-  using Cfg = IgemmCfg<NT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(igemm_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
-      return EVB_ERR_CUDA;
-    attr_set = true;
-  }
-  const int grid = p.tiles_c * p.tiles_w * p.tiles_h * p.tiles_n;
-  igemm_kernel<NT><<<grid, 192, Cfg::SMEM, st>>>(tmA, tmB, p);
-  return cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
 }
 
 template <int NT, bool EPI, bool STATS>
@@ -570,8 +414,7 @@ static int run_igemm(const ADesc& a, int a_stride, const void* wpk, int w_rows, 
   uint32_t wb[3] = {64, (uint32_t)nt, 1};
   rc = evb_make_tmap_bf16(&tmB, wpk, 3, wd, ws, wb);
   if (rc) return rc;
-  if (p.stats && g_igemm_variant != 2) return EVB_ERR_ARG;
-  if (g_igemm_variant == 2) {
+  {
     // output tensor map for the TMA-store epilogue: (channel, w, h, n, 1) with the caller's strides (covers the strided
     // per-phase outputs of the stride-2 dgrad); channels >= Cout and pixels outside the image are clipped by the TMA.
     CUtensorMap tmC;
@@ -587,24 +430,12 @@ static int run_igemm(const ADesc& a, int a_stride, const void* wpk, int w_rows, 
     }
     return EVB_ERR_ARG;
   }
-  switch (nt) {
-    case 256: return launch_igemm<256>(tmA, tmB, p, st);
-    case 128: return launch_igemm<128>(tmA, tmB, p, st);
-    case 64: return launch_igemm<64>(tmA, tmB, p, st);
-  }
   return EVB_ERR_ARG;
 }
 
 }  // namespace evb
 
 using namespace evb;
-
-// 2 = persistent kernel with TMA-store epilogue (default), 1 = one tile per CTA with direct stores (kept for A/B tests)
-extern "C" int evb_set_igemm_variant(int v) {
-  if (v != 1 && v != 2) return EVB_ERR_ARG;
-  g_igemm_variant = v;
-  return EVB_OK;
-}
 
 // y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w) (+bias) (+add).  ksize in {1,3}, pad = ksize/2, stride in {1,2}.
 // wpk: bf16 [ksize*ksize][w_rows][Cin], w_rows >= Cout.  add_mode: 0 none, 1 same-shape bf16 tensor,

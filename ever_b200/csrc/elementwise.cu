@@ -187,52 +187,6 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
   if (dbeta) { if (accumulate) dbeta[c] += (float)s; else dbeta[c] = (float)s; }
 }
 
-// y = act( bf16(x*scale+shift) [+ res] ).  blockDim is a multiple of C/8, so a thread's channel group is fixed and
-// the per-channel constants are hoisted; UN vectors are kept in flight per thread.
-__global__ void __launch_bounds__(kEwThreads)
-bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-                const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, long long nvec, int C, int relu) {
-  constexpr int UN = 4;
-  const int cg = C / 8;
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const int c0 = (int)(tid % cg) * 8;
-  float a[8], b[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { a[j] = scale[c0 + j]; b[j] = shift[c0 + j]; }
-  for (long long i0 = tid; i0 < nvec; i0 += stride * UN) {
-    bf16x8 xv[UN], rv[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < nvec) {
-        xv[u] = reinterpret_cast<const bf16x8*>(x)[i];
-        if (res) rv[u] = reinterpret_cast<const bf16x8*>(res)[i];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < nvec) {
-        float v[8];
-        unpack8(xv[u], v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = v[j] * a[j] + b[j];
-        if (res) {
-          float r[8];
-          unpack8(rv[u], r);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = bf16_round(v[j]) + r[j];
-        }
-        if (relu) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        reinterpret_cast<bf16x8*>(y)[i] = pack8(v);
-      }
-    }
-  }
-}
 
 // dx = scale * (g - (dbeta + xhat * dgamma) / M) = a*g + k0 - c2*x,  g = dy * mask ;  optional dres (+)= g
 //   c2 = a * rstd * dgamma / M,  k0 = c2 * mean - a * dbeta / M   (hoisted per channel); kernels below
@@ -242,94 +196,9 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s
 // twice as many CTAs fit per SM and twice the bytes are in flight per SM (measured on B200: the V = 8 backward kernels
 // ran at 46 % of the copy bandwidth, in-flight-limited).  MASK is a template parameter so unused constants are pruned.
 // ------------------------------------------------------------------------------------------------
-template <int V> struct bvec;
-template <> struct alignas(8) bvec<4> { uint32_t u[2]; };
-template <> struct alignas(16) bvec<8> { uint32_t u[4]; };
-template <int V>
-__device__ __forceinline__ void unpackv(const bvec<V>& v, float (&f)[V]) {
-#pragma unroll
-  for (int i = 0; i < V / 2; ++i) {
-    float2 t = unpack_bf16x2(v.u[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-template <int V>
-__device__ __forceinline__ bvec<V> packv(const float (&f)[V]) {
-  bvec<V> v;
-#pragma unroll
-  for (int i = 0; i < V / 2; ++i) v.u[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-  return v;
-}
-
 // BN backward reduction: per-channel sums of g = dy * mask and g * (x - mean) over M rows (rstd is applied by the finalize
 // kernel).  MASK 0: none; 1: ymask > 0; 2: recomputed bf16(x*scale+shift) > 0.  partial[which][C][kNbPadBwd], column = block.
 constexpr int kNbPadBwd = 640;   // up to 4 reduce blocks per SM
-template <int V, int MASK, int UN>
-__global__ void __launch_bounds__(kEwThreads)
-bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                     const __nv_bfloat16* __restrict__ ymask, const float* __restrict__ mean,
-                     const float* __restrict__ scale, const float* __restrict__ shift, long long M, int C,
-                     float* __restrict__ partial) {
-  extern __shared__ float sm[];  // [thread][2 * V]
-  const int cg = C / V;
-  const int rows_par = blockDim.x / cg;
-  const int t = threadIdx.x;
-  const int g = t % cg, rsub = t / cg;
-  const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
-  float s0[V], s1[V], mu[V], sc[V], sh[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    s0[j] = s1[j] = 0.f;
-    mu[j] = mean[g * V + j];
-    if (MASK == 2) { sc[j] = scale[g * V + j]; sh[j] = shift[g * V + j]; }
-  }
-  const size_t col = (size_t)g * V;
-  for (long long rb = r0 + rsub; rb < r1; rb += (long long)rows_par * UN) {
-    bvec<V> xq[UN], gq[UN], yq[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const long long r = rb + (long long)u * rows_par;
-      if (r < r1) {
-        xq[u] = *reinterpret_cast<const bvec<V>*>(x + r * C + col);
-        gq[u] = *reinterpret_cast<const bvec<V>*>(dy + r * C + col);
-        if (MASK == 1) yq[u] = *reinterpret_cast<const bvec<V>*>(ymask + r * C + col);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const long long r = rb + (long long)u * rows_par;
-      if (r >= r1) continue;
-      float xv[V], gv[V];
-      unpackv<V>(xq[u], xv);
-      unpackv<V>(gq[u], gv);
-      if (MASK == 1) {
-        float yv[V];
-        unpackv<V>(yq[u], yv);
-#pragma unroll
-        for (int j = 0; j < V; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
-      } else if (MASK == 2) {
-#pragma unroll
-        for (int j = 0; j < V; ++j) gv[j] = bf16_round(xv[j] * sc[j] + sh[j]) > 0.f ? gv[j] : 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < V; ++j) { s0[j] += gv[j]; s1[j] += gv[j] * (xv[j] - mu[j]); }
-    }
-  }
-  float* my = sm + (size_t)t * 2 * V;
-#pragma unroll
-  for (int j = 0; j < V; ++j) { my[j] = s0[j]; my[V + j] = s1[j]; }
-  __syncthreads();
-  for (int o = t; o < 2 * C; o += blockDim.x) {
-    const int which = o / C, c = o % C;
-    const int gg = c / V, j = c % V;
-    float acc = 0.f;
-    for (int rs_ = 0; rs_ < rows_par; ++rs_) acc += sm[((size_t)rs_ * cg + gg) * 2 * V + which * V + j];
-    partial[((size_t)which * C + c) * kNbPadBwd + blockIdx.x] = acc;
-  }
-}
 
 // finalize of bn_bwd_reduce_kernel: dbeta = sum g, dgamma = rstd * sum g (x - mean); fixed-order fp64 reduction
 __global__ void bn_bwd_finalize2_kernel(const float* __restrict__ partial, int nblk, int C, const float* __restrict__ rstd,
@@ -348,127 +217,7 @@ __global__ void bn_bwd_finalize2_kernel(const float* __restrict__ partial, int n
   if (dbeta) { if (accumulate) dbeta[c] += (float)s; else dbeta[c] = (float)s; }
 }
 
-// dx = a*g + k0 - c2*x (see bn_bwd_apply_kernel), V channels per thread, UN vectors in flight
-template <int V, int MASK, int UN>
-__global__ void __launch_bounds__(kEwThreads)
-bn_bwd_apply2_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
-                     const __nv_bfloat16* __restrict__ ymask, const float* __restrict__ mean,
-                     const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ shift,
-                     const float* __restrict__ dgamma, const float* __restrict__ dbeta, int frozen,
-                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres, int dres_acc, unsigned nvec, int C,
-                     float inv_m) {
-  const int cg = C / V;
-  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned stride = gridDim.x * blockDim.x;
-  const int c0 = (int)(tid % (unsigned)cg) * V;
-  float a[V], k0[V], c2[V], sh[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    const int c = c0 + j;
-    a[j] = scale[c];
-    if (MASK == 2) sh[j] = shift[c];
-    if (frozen) { c2[j] = 0.f; k0[j] = 0.f; }
-    else {
-      c2[j] = a[j] * rstd[c] * dgamma[c] * inv_m;
-      k0[j] = c2[j] * mean[c] - a[j] * dbeta[c] * inv_m;
-    }
-  }
-  typedef bvec<V> VT;
-  for (unsigned i0 = tid; i0 < nvec; i0 += stride * UN) {
-    VT gv[UN], xv[UN], yv[UN], dv[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const unsigned i = i0 + u * stride;
-      if (i < nvec) {
-        gv[u] = reinterpret_cast<const VT*>(dy)[i];
-        xv[u] = reinterpret_cast<const VT*>(x)[i];
-        if (MASK == 1) yv[u] = reinterpret_cast<const VT*>(ymask)[i];
-        if (dres && dres_acc) dv[u] = reinterpret_cast<const VT*>(dres)[i];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const unsigned i = i0 + u * stride;
-      if (i < nvec) {
-        float g[V], xf[V];
-        unpackv<V>(gv[u], g);
-        unpackv<V>(xv[u], xf);
-        if (MASK == 1) {
-          float yf[V];
-          unpackv<V>(yv[u], yf);
-#pragma unroll
-          for (int j = 0; j < V; ++j) g[j] = yf[j] > 0.f ? g[j] : 0.f;
-        } else if (MASK == 2) {
-#pragma unroll
-          for (int j = 0; j < V; ++j) g[j] = bf16_round(xf[j] * a[j] + sh[j]) > 0.f ? g[j] : 0.f;
-        }
-        if (dres) {
-          float d[V];
-          if (dres_acc) {
-            unpackv<V>(dv[u], d);
-#pragma unroll
-            for (int j = 0; j < V; ++j) d[j] += g[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < V; ++j) d[j] = g[j];
-          }
-          reinterpret_cast<VT*>(dres)[i] = packv<V>(d);
-        }
-        float o[V];
-#pragma unroll
-        for (int j = 0; j < V; ++j) o[j] = a[j] * g[j] + k0[j] - c2[j] * xf[j];
-        reinterpret_cast<VT*>(dx)[i] = packv<V>(o);
-      }
-    }
-  }
-}
 
-// y = act(bf16(x*scale+shift) [+ res]), V channels per thread
-template <int V, int UN>
-__global__ void __launch_bounds__(kEwThreads)
-bn_apply2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-                 const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, unsigned nvec, int C, int relu) {
-  const int cg = C / V;
-  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned stride = gridDim.x * blockDim.x;
-  const int c0 = (int)(tid % (unsigned)cg) * V;
-  float a[V], b[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) { a[j] = scale[c0 + j]; b[j] = shift[c0 + j]; }
-  typedef bvec<V> VT;
-  for (unsigned i0 = tid; i0 < nvec; i0 += stride * UN) {
-    VT xv[UN], rv[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const unsigned i = i0 + u * stride;
-      if (i < nvec) {
-        xv[u] = reinterpret_cast<const VT*>(x)[i];
-        if (res) rv[u] = reinterpret_cast<const VT*>(res)[i];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const unsigned i = i0 + u * stride;
-      if (i < nvec) {
-        float v[V];
-        unpackv<V>(xv[u], v);
-#pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = v[j] * a[j] + b[j];
-        if (res) {
-          float r[V];
-          unpackv<V>(rv[u], r);
-#pragma unroll
-          for (int j = 0; j < V; ++j) v[j] = bf16_round(v[j]) + r[j];
-        }
-        if (relu) {
-#pragma unroll
-          for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        reinterpret_cast<VT*>(y)[i] = packv<V>(v);
-      }
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // cp.async-staged BatchNorm backward.  The register-staged kernels above keep at most UN 16-byte loads per tensor in
@@ -1178,44 +927,6 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, 
   }
 }
 
-// All convolutions of the model in one launch.  desc[i] = {w, wf, wb, Co, Ci, kk, CoP, CiP, CiPb, CoPb, first_block, w_ld}
-// (w_ld = floats between consecutive output-channel rows of w, 0 -> Ci*kk; lets a conv use a Cin sub-range of a weight)
-// (12 x int64); block_map[b] = descriptor index of block b.  One block = a 32 co x 32 ci tile, all kk <= 9 taps, staged
-// through shared memory so that the OIHW read ((ci,tap) contiguous per co) and both packed writes
-// (wf[tap][co][ci]: ci contiguous; wb[tap][ci][co]: co contiguous) are coalesced.  Padding rows/columns of the packs are
-// never written (the pack arena is zero-initialised once).
-__global__ void __launch_bounds__(256)
-pack_weights_batched_kernel(const long long* __restrict__ desc, const int* __restrict__ block_map, int block0) {
-  __shared__ float tile[9][32][33];  // [tap][co][ci]
-  const int bid = blockIdx.x + block0;
-  const long long* d = desc + (long long)block_map[bid] * 12;
-  const float* w = reinterpret_cast<const float*>(d[0]);
-  __nv_bfloat16* wf = reinterpret_cast<__nv_bfloat16*>(d[1]);
-  __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(d[2]);
-  const int Co = (int)d[3], Ci = (int)d[4], kk = (int)d[5], CoP = (int)d[6], CiP = (int)d[7], CiPb = (int)d[8],
-            CoPb = (int)d[9];
-  const int t = bid - (int)d[10];
-  const long long w_ld = d[11] ? d[11] : (long long)Ci * kk;
-  const int tiles_ci = (Ci + 31) / 32;
-  const int co0 = (t / tiles_ci) * 32, ci0 = (t % tiles_ci) * 32;
-  const int nci = min(32, Ci - ci0);
-  const int run = nci * kk;  // contiguous floats per co
-  for (int idx = threadIdx.x; idx < 32 * run; idx += 256) {
-    const int c = idx / run, e = idx % run;
-    const int cil = e / kk, tap = e % kk;
-    if (co0 + c < Co) tile[tap][c][cil] = w[(long long)(co0 + c) * w_ld + (long long)ci0 * kk + e];
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < kk * 32 * 32; idx += 256) {
-    const int tap = idx / 1024, r = (idx / 32) % 32, q = idx % 32;
-    // wf: row = co (r), fastest = ci (q)
-    if (co0 + r < Co && ci0 + q < Ci)
-      wf[((long long)tap * CoP + co0 + r) * CiP + ci0 + q] = __float2bfloat16_rn(tile[tap][r][q]);
-    // wb: row = ci (r), fastest = co (q)
-    if (wb && ci0 + r < Ci && co0 + q < Co)
-      wb[((long long)tap * CiPb + ci0 + r) * CoPb + co0 + q] = __float2bfloat16_rn(tile[tap][q][r]);
-  }
-}
 
 // 64 x 64 (co, ci) tiles, bf16 staging, 16-byte stores: the 32 x 32 kernel above issues one 2-byte store per element and is
 // instruction-bound (190 us for 135 MB of packs; 0.48 ms in situ right after the optimizer's writes).  Here a warp reads
@@ -1346,29 +1057,12 @@ extern "C" int evb_set_bn_reduce_blocks(int per_sm) {
   g_bn_blocks_per_sm = per_sm;
   return EVB_OK;
 }
-static int g_bn_variant = 2;   // BN backward kernels: 2 = cp.async-staged (default), 1 = register-staged
-extern "C" int evb_set_bn_variant(int v) {
-  if (v != 1 && v != 2) return EVB_ERR_ARG;
-  g_bn_variant = v;
-  return EVB_OK;
-}
-static int g_bn_vec = 0;   // 0 = auto (4 channels per thread when C <= 1024), 4 / 8 forced (A/B measurements)
-extern "C" int evb_set_bn_vec(int v) {
-  if (v != 0 && v != 4 && v != 8) return EVB_ERR_ARG;
-  g_bn_vec = v;
-  return EVB_OK;
-}
-static inline int bn_vec_for(int C) {
-  int v = g_bn_vec ? g_bn_vec : 4;
-  if (v == 4 && (C % 4 || C / 4 > kEwThreads)) v = 8;
-  return v;
-}
-
 extern "C" int evb_bn_apply(const void* x, const float* scale, const float* shift, const void* res, void* y, long long M,
                             int C, int relu, void* stream) {
   if (C % 8) return EVB_ERR_ARG;
   if (C / 8 > kEwThreads) return EVB_ERR_ARG;
-  if (g_bn_variant == 2 && M * C / 8 < (1LL << 31) - (1LL << 24)) {   // cp.async rings, 16-byte vectors
+  if (M * C / 8 >= (1LL << 31) - (1LL << 24)) return EVB_ERR_ARG;   // vectors are indexed with 32 bits
+  {   // cp.async rings, 16-byte vectors
     const long long nvec = M * C / 8;
     const int cg_ = C / 8;
     const int bt = (kEwThreads / cg_) * cg_;
@@ -1391,20 +1085,7 @@ extern "C" int evb_bn_apply(const void* x, const float* scale, const float* shif
     if (e != cudaSuccess) return EVB_ERR_CUDA;
     return LAUNCH_OK();
   }
-  int V = g_bn_vec == 4 ? 4 : 8;   // register-staged: 8 channels per thread unless forced (V = 4 measured no faster here)
-  if (V == 4 && (C % 4 || C / 4 > kEwThreads)) V = 8;
-  if (M * C / 4 >= (1LL << 31) - (1LL << 24)) V = 8;   // the narrow kernels index vectors with 32 bits
-  const long long nvec = M * C / V;
-  const int cg_ = C / V;
-  const int bt = (kEwThreads / cg_) * cg_;
-  if (V == 4)
-    bn_apply2_kernel<4, 8><<<ew_blocks(nvec, bt * 8), bt, 0, ST>>>((const __nv_bfloat16*)x, scale, shift,
-                                                                  (const __nv_bfloat16*)res, (__nv_bfloat16*)y,
-                                                                  (unsigned)nvec, C, relu);
-  else
-    bn_apply_kernel<<<ew_blocks(nvec, bt * 4), bt, 0, ST>>>((const __nv_bfloat16*)x, scale, shift,
-                                                           (const __nv_bfloat16*)res, (__nv_bfloat16*)y, nvec, C, relu);
-  return LAUNCH_OK();
+  return EVB_ERR_ARG;
 }
 
 template <int MASK>
@@ -1446,52 +1127,17 @@ static int launch_bn_bwd_ca(const void* dy, const void* x, const void* ymask, co
   return EVB_OK;
 }
 
-template <int V, int MASK>
-static void launch_bn_bwd(const void* dy, const void* x, const void* ymask, const float* mean, const float* rstd,
-                          const float* scale, const float* shift, int frozen, void* dx, void* dres, int dres_acc,
-                          float* dgamma, float* dbeta, int param_acc, long long M, int C, void* ws, cudaStream_t st) {
-  constexpr int UNR = V == 4 ? 4 : 2, UNA = V == 4 ? 4 : 2;
-  const int cg = C / V;
-  const int bt = (kEwThreads / cg) * cg;
-  const int rows_par = bt / cg;
-  long long nb = (M + (long long)rows_par * UNR * 2 - 1) / ((long long)rows_par * UNR * 2);
-  const int cap = g_bn_blocks_per_sm * 148;
-  if (nb > cap) nb = cap;
-  if (nb < 1) nb = 1;
-  bn_bwd_reduce_kernel<V, MASK, UNR><<<(int)nb, bt, bt * 2 * V * sizeof(float), st>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)ymask, mean, scale, shift, M, C, (float*)ws);
-  float* fresh = (float*)ws + (size_t)kNbPadBwd * 2 * C;
-  bn_bwd_finalize2_kernel<<<(C + 7) / 8, 256, 0, st>>>((const float*)ws, (int)nb, C, rstd, dgamma, dbeta, param_acc, fresh);
-  const long long nvec = M * C / V;
-  bn_bwd_apply2_kernel<V, MASK, UNA><<<ew_blocks(nvec, bt * UNA), bt, 0, st>>>(
-      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ymask, mean, rstd, scale, shift, fresh + C,
-      fresh, frozen, (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, dres_acc, (unsigned)nvec, C, 1.0f / (float)M);
-}
-
 extern "C" int evb_bn_bwd(const void* dy, const void* x, const void* ymask, const float* mean, const float* rstd,
                           const float* scale, const float* shift, int mask_mode, int frozen, void* dx, void* dres,
                           int dres_acc, float* dgamma, float* dbeta, int param_acc, long long M, int C, void* ws,
                           void* stream) {
   if (C % 8 || C > 2048 || mask_mode < 0 || mask_mode > 2) return EVB_ERR_ARG;
   if (M * C / 8 >= (1LL << 31) - (1LL << 24)) return EVB_ERR_ARG;
-  int V = bn_vec_for(C);
-  if (M * C / 4 >= (1LL << 31) - (1LL << 24)) V = 8;
-  if (g_bn_variant == 2) {
-    int rc;
-    if (mask_mode == 0) rc = launch_bn_bwd_ca<0>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
-    else if (mask_mode == 1) rc = launch_bn_bwd_ca<1>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
-    else rc = launch_bn_bwd_ca<2>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
-    if (rc) return rc;
-    return LAUNCH_OK();
-  }
-#define EVB_BN_BWD(V_, MK_) launch_bn_bwd<V_, MK_>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, \
-                                                   dbeta, param_acc, M, C, ws, ST)
-  if (V == 4) {
-    if (mask_mode == 0) EVB_BN_BWD(4, 0); else if (mask_mode == 1) EVB_BN_BWD(4, 1); else EVB_BN_BWD(4, 2);
-  } else {
-    if (mask_mode == 0) EVB_BN_BWD(8, 0); else if (mask_mode == 1) EVB_BN_BWD(8, 1); else EVB_BN_BWD(8, 2);
-  }
-#undef EVB_BN_BWD
+  int rc;
+  if (mask_mode == 0) rc = launch_bn_bwd_ca<0>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
+  else if (mask_mode == 1) rc = launch_bn_bwd_ca<1>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
+  else rc = launch_bn_bwd_ca<2>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
+  if (rc) return rc;
   return LAUNCH_OK();
 }
 
@@ -1728,12 +1374,6 @@ extern "C" int evb_pack_weight(const float* w, int Co, int Ci, int kk, void* wf,
   return LAUNCH_OK();
 }
 
-extern "C" int evb_pack_weights_batched(const void* desc, const void* block_map, int nblocks, void* stream) {
-  pack_weights_batched_kernel<<<nblocks, 256, 0, ST>>>((const long long*)desc, (const int*)block_map, 0);
-  return LAUNCH_OK();
-}
-// 64 x 64 tile variant (block_map counts ceil(Co/64) * ceil(Ci/64) blocks per convolution); blocks [block0, block0+nblocks).
-// Requires CiP, CoPb multiples of 8 and 16-byte aligned pack bases (the engine's arena guarantees 128 bytes).
 extern "C" int evb_pack_weights_tiled(const void* desc, const void* block_map, int block0, int nblocks, void* stream) {
   if (nblocks <= 0) return EVB_OK;
   constexpr int T = 64;
@@ -1749,12 +1389,6 @@ extern "C" int evb_pack_weights_tiled(const void* desc, const void* block_map, i
 }
 // blocks [block0, block0 + nblocks) of the same table: lets the caller pack the first layers' weights on the main stream
 // and the rest on a second stream that overlaps the start of the forward pass
-extern "C" int evb_pack_weights_range(const void* desc, const void* block_map, int block0, int nblocks, void* stream) {
-  if (nblocks <= 0) return EVB_OK;
-  pack_weights_batched_kernel<<<nblocks, 256, 0, ST>>>((const long long*)desc, (const int*)block_map, block0);
-  return LAUNCH_OK();
-}
-
 extern "C" int evb_copy2d_f32(const float* src, int lds, float* dst, int ldd, int rows, int cols, int accumulate,
                               void* stream) {
   copy2d_kernel<<<ew_blocks((long long)rows * cols, kEwThreads), kEwThreads, 0, ST>>>(src, lds, dst, ldd, rows, cols,

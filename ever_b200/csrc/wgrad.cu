@@ -27,7 +27,6 @@ struct WgradParams {
   int nchunks, chunks_per_split, nsplit;
   int tiles_ci, tiles_co;
   float* ws;   // deterministic mode: [split][tap][CinP][CoutP] partials, reduced by a second kernel
-  float* acc;  // atomic mode (ws == nullptr): [tap][CinP][CoutP] fp32 accumulated with red.global.add.v4.f32
   int CinP, CoutP, Cin, Cout;
 };
 
@@ -140,7 +139,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     for (int m = 0; m < MT; ++m) {
       const int ci = ci0 + m * 128 + r;
       const uint32_t tm = taddr + (uint32_t(q * 32) << 16) + m * NT;
-      if (p.ws) {
+      {
         float* orow = p.ws + (((long long)split * p.ntaps + tap) * p.CinP + ci) * p.CoutP + co0;
 #pragma unroll 1
         for (int c = 0; c < NT / 32; ++c) {
@@ -155,22 +154,6 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             *reinterpret_cast<uint4*>(orow + c * 32 + g * 4) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-        }
-      } else if (niter > 0) {
-        float* orow = p.acc + (((long long)tap) * p.CinP + ci) * p.CoutP + co0;
-        const bool row_ok = ci < p.Cin;
-#pragma unroll 1
-        for (int c = 0; c < NT / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tm + c * 32, v);   // warp-collective: outside the row predicate
-          tmem_ld_wait();
-          if (row_ok && co0 + c * 32 < p.Cout) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              atomicAdd(reinterpret_cast<float4*>(orow + c * 32 + g * 4),
-                        make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
-                                    __uint_as_float(v[g * 4 + 3])));
-          }
         }
       }
     }
@@ -296,42 +279,6 @@ __global__ void wgrad_reduce_splitpar_kernel(const float* __restrict__ ws, float
   }
 }
 
-// All convolutions in one launch: dw[co][ci][tap] (+)= acc[tap][ci][co]; acc = 0.
-// desc[i] = {acc, dw, Co, Ci, kk, CinP, CoutP, first_block, accumulate, -,-,-} (12 x int64); 32x32 (ci,co) tiles per block.
-__global__ void __launch_bounds__(256)
-wgrad_unstage_batched_kernel(const long long* __restrict__ desc, const int* __restrict__ block_map) {
-  __shared__ float tile[32][33];
-  const long long* d = desc + (long long)block_map[blockIdx.x] * 12;
-  float* acc = reinterpret_cast<float*>(d[0]);
-  float* dw = reinterpret_cast<float*>(d[1]);
-  const int Co = (int)d[2], Ci = (int)d[3], kk = (int)d[4], CinP = (int)d[5], CoutP = (int)d[6], accumulate = (int)d[8];
-  int t = blockIdx.x - (int)d[7];
-  const int tco = (Co + 31) / 32, tci = (Ci + 31) / 32;
-  const int bco = t % tco; t /= tco;
-  const int bci = t % tci;
-  const int tap = t / tci;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (int i = ty; i < 32; i += 8) {
-    const int ci = bci * 32 + i, co = bco * 32 + tx;
-    float v = 0.f;
-    if (ci < Ci && co < Co) {
-      float* src = acc + ((long long)tap * CinP + ci) * CoutP + co;
-      v = *src;
-      *src = 0.f;
-    }
-    tile[i][tx] = v;
-  }
-  __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int co = bco * 32 + i, ci = bci * 32 + tx;
-    if (ci < Ci && co < Co) {
-      float* dst = dw + ((long long)co * Ci + ci) * kk + tap;
-      const float v = tile[tx][i];
-      *dst = accumulate ? (*dst + v) : v;
-    }
-  }
-}
-
 static int pow2_le(int x, int cap) {
   int r = 1;
   while (r * 2 <= x && r * 2 <= cap) r *= 2;
@@ -423,14 +370,13 @@ extern "C" long long evb_conv2d_wgrad_workspace(int N, int Ho, int Wo, int Cin, 
 
 // dw[Cout][Cin][k][k] fp32 (+)= sum_pixels x (*) dy.  x: [N,H,W,Cin] bf16 (the conv input), dy: [N,Ho,Wo,Cout] bf16.
 static int wgrad_impl(const void* x, int N, int H, int W, int Cin, const void* dy, int Cout, int ksize, int stride,
-                      float* dw, int accumulate, void* ws, long long ws_bytes, float* acc, int cin_valid, int cout_valid,
-                      int force_nt, int force_split, void* stream) {
+                      float* dw, int accumulate, void* ws, long long ws_bytes, int force_nt, int force_split, void* stream) {
   if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return EVB_ERR_ARG;
   if (Cin % 64 || Cout % 64) return EVB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int Ho = H / stride, Wo = W / stride, ntaps = ksize * ksize;
-  const WgradPlan pl = plan_wgrad(N, Ho, Wo, Cin, Cout, ntaps, force_nt, force_split, acc ? 0 : 1);
-  if (!acc && (size_t)ws_bytes < pl.ws_bytes) return EVB_ERR_ARG;
+  const WgradPlan pl = plan_wgrad(N, Ho, Wo, Cin, Cout, ntaps, force_nt, force_split, 1);
+  if ((size_t)ws_bytes < pl.ws_bytes) return EVB_ERR_ARG;
   WgradParams p{};
   p.ntaps = ntaps;
   for (int r = 0; r < ksize; ++r)
@@ -449,8 +395,8 @@ static int wgrad_impl(const void* x, int N, int H, int W, int Cin, const void* d
   p.tiles_w = pl.tw; p.tiles_h = pl.th; p.tiles_n = pl.tn;
   p.nchunks = pl.nchunks; p.chunks_per_split = pl.cps; p.nsplit = pl.nsplit;
   p.tiles_ci = pl.tiles_ci; p.tiles_co = pl.tiles_co;
-  p.ws = acc ? nullptr : (float*)ws; p.acc = acc; p.CinP = pl.CinP; p.CoutP = pl.CoutP;
-  p.Cin = cin_valid; p.Cout = cout_valid;
+  p.ws = (float*)ws; p.CinP = pl.CinP; p.CoutP = pl.CoutP;
+  p.Cin = Cin; p.Cout = Cout;
   CUtensorMap tmX, tmDY;
   int rc = make_act_map(&tmX, x, N, H, W, Cin, stride, pl.bw, pl.bh, pl.bn);
   if (rc) return rc;
@@ -465,7 +411,6 @@ static int wgrad_impl(const void* x, int N, int H, int W, int Cin, const void* d
     default: rc = EVB_ERR_ARG;
   }
   if (rc) return rc;
-  if (acc) return EVB_OK;
   if (pl.nsplit > 16 && (long long)Cin * Cout * ntaps <= 65536) {   // few outputs, many splits
     dim3 grid((Cout + 31) / 32, Cin, ntaps), block(32, 8);
     wgrad_reduce_splitpar_kernel<<<grid, block, 0, st>>>((const float*)ws, dw, pl.nsplit, ntaps, Cin, Cout, pl.CinP,
@@ -488,29 +433,5 @@ static int wgrad_impl(const void* x, int N, int H, int W, int Cin, const void* d
 extern "C" int evb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, const void* dy, int Cout, int ksize,
                                 int stride, float* dw, int accumulate, void* ws, long long ws_bytes, int force_nt,
                                 int force_split, void* stream) {
-  return wgrad_impl(x, N, H, W, Cin, dy, Cout, ksize, stride, dw, accumulate, ws, ws_bytes, nullptr, Cin, Cout, force_nt,
-                    force_split, stream);
-}
-
-// Padded staging layout used by evb_conv2d_wgrad_acc: acc is fp32 [k*k][CinP][CoutP].
-extern "C" int evb_conv2d_wgrad_layout(int Cin, int Cout, int* CinP, int* CoutP) {
-  const WgradPlan pl = plan_wgrad(1, 64, 64, Cin, Cout, 1, 0, 1, 0);
-  *CinP = pl.CinP;
-  *CoutP = pl.CoutP;
-  return EVB_OK;
-}
-
-// Fast path: every split adds its tile into acc[tap][ci][co] with red.global.add.v4.f32 (no workspace, no reduce
-// launch; summation order is not fixed).  Rows >= cin_valid / columns >= cout_valid (zero padding) are skipped.
-// evb_wgrad_unstage_batched later moves acc into the OIHW gradients and re-zeroes it.
-extern "C" int evb_conv2d_wgrad_acc(const void* x, int N, int H, int W, int Cin, const void* dy, int Cout, int ksize,
-                                    int stride, float* acc, int cin_valid, int cout_valid, void* stream) {
-  if (!acc) return EVB_ERR_ARG;
-  return wgrad_impl(x, N, H, W, Cin, dy, Cout, ksize, stride, nullptr, 0, nullptr, 0, acc, cin_valid, cout_valid, 0, 0,
-                    stream);
-}
-
-extern "C" int evb_wgrad_unstage_batched(const void* desc, const void* block_map, int nblocks, void* stream) {
-  wgrad_unstage_batched_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>((const long long*)desc, (const int*)block_map);
-  return cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
+  return wgrad_impl(x, N, H, W, Cin, dy, Cout, ksize, stride, dw, accumulate, ws, ws_bytes, force_nt, force_split, stream);
 }

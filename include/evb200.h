@@ -47,9 +47,6 @@ int evb_conv2d_fwd_stats(const void* x, int N, int H, int W, int Cin, const void
 /* same, with a per-channel fp32 bias added before the bf16 rounding (conv+bias -> BN, ever/module/fs_relation.py:41-52) */
 int evb_conv2d_fwd_bias_stats(const void* x, int N, int H, int W, int Cin, const void* wpk, int w_rows, int ksize, int stride,
                               void* y, int Cout, const float* bias, float* partial, int* nblk_out, void* stream);
-/* kernel variant for evb_conv2d_fwd/dgrad: 2 = persistent, TMEM double-buffered, TMA-store epilogue (default);
- * 1 = one tile per CTA with direct global stores (kept for A/B measurements). */
-int evb_set_igemm_variant(int v);
 /* dx[N,H,W,Cin] (+)= conv_transpose(dy[N,Ho,Wo,Cout]).  wpk_t: bf16 [ksize*ksize][w_rows>=Cin][Cout]. */
 int evb_conv2d_dgrad(const void* dy, int N, int Ho, int Wo, int Cout, const void* wpk_t, int w_rows, int ksize,
                      int stride, void* dx, int H, int W, int Cin, int accumulate, int force_nt, void* stream);
@@ -57,25 +54,12 @@ int evb_conv2d_dgrad(const void* dy, int N, int Ho, int Wo, int Cout, const void
 long long evb_conv2d_wgrad_workspace(int N, int Ho, int Wo, int Cin, int Cout, int ksize, int force_nt, int force_split);
 int evb_conv2d_wgrad(const void* x, int N, int H, int W, int Cin, const void* dy, int Cout, int ksize, int stride,
                      float* dw, int accumulate, void* ws, long long ws_bytes, int force_nt, int force_split, void* stream);
-/* Fast path: split-K tiles are accumulated into acc (fp32 [k*k][CinP][CoutP], evb_conv2d_wgrad_layout gives the padded
- * sizes) with red.global.add.v4.f32 -- no workspace, no reduce launch, summation order not fixed.  Rows >= cin_valid and
- * columns >= cout_valid (zero padding) are skipped.  evb_wgrad_unstage_batched moves every conv's acc into its OIHW fp32
- * gradient (dw[co][ci][tap] (+)= acc[tap][ci][co]) and re-zeroes acc; desc: int64[n][12] =
- * {acc, dw, Co, Ci, kk, CinP, CoutP, first_block, accumulate, 0, 0, 0}, block_map: int32[nblocks] (32x32 tiles). */
-int evb_conv2d_wgrad_layout(int Cin, int Cout, int* CinP, int* CoutP);
-int evb_conv2d_wgrad_acc(const void* x, int N, int H, int W, int Cin, const void* dy, int Cout, int ksize, int stride,
-                         float* acc, int cin_valid, int cout_valid, void* stream);
-int evb_wgrad_unstage_batched(const void* desc, const void* block_map, int nblocks, void* stream);
 /* fp32 OIHW master weights -> bf16 packs [kk][CoP][CiP] (forward) and [kk][CiPb][CoPb] (dgrad), zero padded. */
 int evb_pack_weight(const float* w, int Co, int Ci, int kk, void* wf, int CoP, int CiP, void* wb, int CiPb, int CoPb,
                     void* stream);
-/* every convolution of a model in one launch; desc: int64[n][12], block_map: int32[nblocks] (see elementwise.cu) */
-int evb_pack_weights_batched(const void* desc, const void* block_map, int nblocks, void* stream);
-/* same table layout with 64 x 64 (co, ci) tiles per block (block_map counts ceil(Co/64)*ceil(Ci/64) blocks per conv), bf16
- * staging and 16-byte stores: the variant the engine uses */
+/* every convolution of a model in one launch: desc int64[n][12], block_map int32[nblocks] (one block per 64 x 64 (co, ci)
+ * tile, all taps; see elementwise.cu); bf16 staging, 16-byte stores of both layouts; blocks [block0, block0 + nblocks) */
 int evb_pack_weights_tiled(const void* desc, const void* block_map, int block0, int nblocks, void* stream);
-/* blocks [block0, block0 + nblocks) of the same table (first layers on the main stream, the rest on a second stream) */
-int evb_pack_weights_range(const void* desc, const void* block_map, int block0, int nblocks, void* stream);
 /* 7x7 stride-2 pad-3 stem lowered to a GEMM: x NCHW fp32 -> A[N*H/2*W/2][KP] bf16, k = c*49 + r*7 + s
  * (ResNet.stem_forward, ever/module/_resnets.py:205-212). */
 int evb_stem_im2col(const float* x, void* a, int N, int Cin, int H, int W, int KP, void* stream);
@@ -110,10 +94,6 @@ int evb_bn_fold(const float* gamma, const float* beta, const float* rm, const fl
 int evb_bn_apply(const void* x, const float* scale, const float* shift, const void* res, void* y, long long M, int C,
                  int relu, void* stream);
 /* backward of the above.  mask_mode 0 none | 1 (ymask>0) | 2 recomputed from x.  dres (+)= masked dy. */
-/* channels per thread of the BN streaming kernels: 0 auto (4 when C <= 1024), 4 or 8 forced (A/B measurements) */
-int evb_set_bn_vec(int v);
-/* BN backward kernels: 2 = cp.async-staged shared-memory rings (default), 1 = register-staged loads */
-int evb_set_bn_variant(int v);
 /* grid cap of the BN backward reduction, blocks per SM (1..4, default 4) */
 int evb_set_bn_reduce_blocks(int per_sm);
 int evb_bn_bwd(const void* dy, const void* x, const void* ymask, const float* mean, const float* rstd, const float* scale,

@@ -111,40 +111,6 @@ def test_conv_wgrad(case, split):
     _close(dw2, 2 * ref, tol=2e-3)
 
 
-@pytest.mark.parametrize('case', [(2, 32, 32, 64, 128, 3, 1), (8, 16, 16, 192, 64, 1, 1), (2, 32, 32, 128, 256, 3, 2),
-                                  (1, 64, 64, 256, 64, 1, 1)])
-def test_conv_wgrad_atomic_staging(case):
-    """evb_conv2d_wgrad_acc (vector-atomic split-K) + evb_wgrad_unstage_batched == the deterministic path."""
-    import ctypes
-    from ever_b200._lib import check, lib, ptr, stream
-    n, h, w, cin, cout, k, s = case
-    L = lib()
-    c_int = ctypes.c_int
-    g = torch.Generator(device='cuda').manual_seed(5)
-    x = torch.randn(n, h, w, cin, device='cuda', generator=g).to(torch.bfloat16)
-    dy = torch.randn(n, h // s, w // s, cout, device='cuda', generator=g).to(torch.bfloat16)
-    cinp, coutp = c_int(0), c_int(0)
-    L.evb_conv2d_wgrad_layout(c_int(cin), c_int(cout), ctypes.byref(cinp), ctypes.byref(coutp))
-    cin_valid, cout_valid = cin - 5, cout - 3     # padded operands: trailing channels are ignored
-    acc = torch.zeros(k * k * cinp.value * coutp.value, device='cuda')
-    check(L.evb_conv2d_wgrad_acc(ptr(x), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(dy), c_int(cout), c_int(k), c_int(s),
-                                 ptr(acc), c_int(cin_valid), c_int(cout_valid), stream()), 'acc')
-    dw = torch.full((cout_valid, cin_valid, k, k), 7.0, device='cuda')
-    nb = ((cout_valid + 31) // 32) * ((cin_valid + 31) // 32) * k * k
-    desc = torch.tensor([[acc.data_ptr(), dw.data_ptr(), cout_valid, cin_valid, k * k, cinp.value, coutp.value, 0, 0, 0, 0, 0]],
-                        dtype=torch.int64, device='cuda')
-    bmap = torch.zeros(nb, dtype=torch.int32, device='cuda')
-    check(L.evb_wgrad_unstage_batched(ptr(desc), ptr(bmap), c_int(nb), stream()), 'unstage')
-    torch.cuda.synchronize()
-    torch.backends.cudnn.allow_tf32 = False
-    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, k, k), dy.float().permute(0, 3, 1, 2),
-                                      stride=s, padding=k // 2)[:cout_valid, :cin_valid]
-    _close(dw, ref, tol=2e-3)
-    # the valid region of the staging buffer is zero again
-    view = acc.view(k * k, cinp.value, coutp.value)[:, :cin_valid, :cout_valid]
-    assert float(view.abs().max()) == 0.0
-
-
 @pytest.mark.parametrize('case', [(2, 16, 16, 64, 64, 1, 1), (1, 128, 128, 256, 256, 3, 1), (8, 16, 16, 256, 2048, 1, 1),
                                   (3, 24, 40, 64, 192, 3, 1), (2, 32, 32, 128, 512, 1, 2), (8, 64, 64, 128, 128, 3, 1)])
 def test_conv_fwd_fused_bn_stats(case):

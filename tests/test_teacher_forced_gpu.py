@@ -42,6 +42,31 @@ def _build(resnet, k, dec, **opts):
     return ora.cuda().train(), mine.cuda().train()
 
 
+def bn_truth(cap, params, bn_name):
+    """fp64 (d-gamma, d-beta) of the BatchNorm `bn_name` recomputed from the reference's captured tensors: x = output of the
+    conv in front of it, g = gradient arriving at the BN output (= the gradient of the ReLU output behind it masked by
+    output > 0; for the BN of a residual branch the block's last ReLU; a down-sample BN has no ReLU).  None if the layer
+    does not follow one of those patterns."""
+    head, idx = bn_name.rsplit('.', 1)
+    if idx in ('bn1', 'bn2', 'bn3'):                      # ResNet blocks and the plain stem
+        conv = head + '.conv' + idx[2]
+        relu = head + '.relu#%d' % (int(idx[2]) - 1)
+    elif idx.isdigit() and '.downsample' in head:         # Sequential(conv, BN)
+        conv, relu = '%s.%d' % (head, int(idx) - 1), None
+    elif idx.isdigit():                                   # Sequential(conv, BN, ReLU, ...): deep stem, decoder, FS-Relation
+        conv, relu = '%s.%d' % (head, int(idx) - 1), '%s.%d' % (head, int(idx) + 1)
+    else:
+        return None
+    if conv not in cap.fwd or (relu is not None and relu not in cap.bwd) or (relu is None and bn_name not in cap.bwd):
+        return None
+    x = cap.fwd[conv].double()
+    g = cap.bwd[bn_name].double() if relu is None else cap.bwd[relu].double() * (cap.fwd[relu] > 0)
+    dims = (0, 2, 3)
+    mean = x.mean(dims, keepdim=True)
+    xhat = (x - mean) / torch.sqrt(x.var(dims, unbiased=False, keepdim=True) + 1e-5)
+    return (g * xhat).sum(dims), g.sum(dims)
+
+
 def oracle_step_captured(ora, x, y, all_reduce=None):
     from oracle.farseg_oracle import bce_loss_oracle, dice_loss_oracle
     cap = RefCapture(ora)
@@ -125,25 +150,30 @@ def test_teacher_forced_step(case):
             assert float(p.grad.norm()) == 0.0, name
             continue
         grads[name] = rel_l2(p.grad, g_ref)
-    # The BN in front of the max-pool: its d-gamma / d-beta are sums of the SPARSE max-pool gradient with a cancellation
-    # factor of ~400 (sum|g| / |sum g|); torch's own bf16 batch-norm backward is 1-2 % away from the exact sums there
-    # (tools/diag_tf.py: oracle vs fp64 1.8e-2, engine vs fp64 2e-8).  For these two tensors the engine is held to the
-    # fp64 recomputation from the reference's own captured tensors (<= 1e-3) instead of to the reference's noise.
-    conv_nm, bn_nm, relu_nm = STEM_BN['v1c' if resnet.endswith('_v1c') else 'plain']
-    xs = cap.fwd[conv_nm].double().requires_grad_(True)
-    gam = pr[bn_nm + '.weight'].detach().double().requires_grad_(True)
-    bet = pr[bn_nm + '.bias'].detach().double().requires_grad_(True)
-    F.relu(F.batch_norm(xs, None, None, gam, bet, True, 0.1, 1e-5)).backward(cap.bwd[relu_nm].double())
-    truth = {bn_nm + '.weight': gam.grad, bn_nm + '.bias': bet.grad}
-    stem_rep = {}
-    for nm, t in truth.items():
-        stem_rep[nm] = dict(engine_vs_fp64=rel_l2(pm[nm].grad, t), reference_vs_fp64=rel_l2(pr[nm].grad, t),
-                            engine_vs_reference=grads[nm])
-        assert stem_rep[nm]['engine_vs_fp64'] <= 1e-3, stem_rep
-        if grads[nm] > GATE:
-            assert stem_rep[nm]['reference_vs_fp64'] > 0.5 * grads[nm], stem_rep   # the distance IS the reference's error
-            grads.pop(nm)
-    print(json.dumps(dict(stem_bn_vs_fp64=stem_rep)))
+    # BatchNorm d-gamma / d-beta are sums over all pixels; where the summands cancel (factor ~400 for the BN in front of the
+    # max-pool, whose input gradient is the SPARSE max-pool gradient; 10-50 elsewhere) torch's own bf16 batch-norm backward is
+    # 1-5 % away from the exact sums (tools/diag_tf.py: reference vs fp64 1.8e-2, engine vs fp64 2e-8).  A BN parameter
+    # gradient that misses the 1e-2 gate against the reference is therefore held to the fp64 recomputation from the
+    # reference's own captured tensors instead: engine within 1e-3 of fp64 AND the distance explained by the reference's error.
+    bn_rep = {}
+    for nm in [n_ for n_, e in grads.items() if e > GATE]:
+        mod_name, leaf = nm.rsplit('.', 1)
+        truth = bn_truth(cap, pr, mod_name) if leaf in ('weight', 'bias') else None
+        if truth is None:
+            continue
+        t = truth[0 if leaf == 'weight' else 1]
+        bn_rep[nm] = dict(engine_vs_fp64=rel_l2(pm[nm].grad, t), reference_vs_fp64=rel_l2(pr[nm].grad, t),
+                          engine_vs_reference=grads[nm])
+        assert bn_rep[nm]['engine_vs_fp64'] <= 1e-3, bn_rep
+        assert bn_rep[nm]['reference_vs_fp64'] > 0.5 * grads[nm], bn_rep
+        grads.pop(nm)
+    # the max-pool BN is always reported (the extreme case)
+    for leaf, idx in (('weight', 0), ('bias', 1)):
+        nm = STEM_BN['v1c' if resnet.endswith('_v1c') else 'plain'][1] + '.' + leaf
+        t = bn_truth(cap, pr, nm.rsplit('.', 1)[0])[idx]
+        bn_rep.setdefault(nm, dict(engine_vs_fp64=rel_l2(pm[nm].grad, t), reference_vs_fp64=rel_l2(pr[nm].grad, t)))
+        assert bn_rep[nm]['engine_vs_fp64'] <= 1e-3, bn_rep
+    print(json.dumps(dict(bn_param_grads_vs_fp64=bn_rep)))
     tag = '%s_k%d_%dx%dx%d' % (resnet, k, n, h, w)
     s = summarize(tf, grads, tag)
     assert not tf.missing, tf.missing[:5]

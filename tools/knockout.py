@@ -7,7 +7,9 @@ import sys
 
 sys.path.insert(0, '.')
 import torch  # noqa: E402
-from bench import PER_GPU_BATCH, farseg_config, synthetic  # noqa: E402
+from bench import CONFIGS, model_config, synthetic, units_per_gpu  # noqa: E402
+
+CFG = CONFIGS['c2']
 from ever_b200._lib import lib  # noqa: E402
 from ever_b200.module import FarSegB200  # noqa: E402
 
@@ -19,12 +21,12 @@ CLASSES = {
     'bilinear_up': ['evb_bilinear_up'],
     'bilinear_bwd': ['evb_bilinear_up_bwd_sep'],
     'loss': ['evb_loss_stats', 'evb_loss_grad'],
-    'stem_im2col': ['evb_stem_im2col'],
+    'stem_im2col': ['evb_im2col_nchw'],
     'maxpool': ['evb_maxpool3x3s2_fwd', 'evb_maxpool3x3s2_bwd'],
     'relation': ['evb_relation_fwd', 'evb_relation_bwd'],
     'pack_weights': ['evb_pack_weights_tiled'],
     'wgrad': ['evb_conv2d_wgrad'],
-    'conv_fwd': ['evb_conv2d_fwd', 'evb_conv2d_fwd_stats'],
+    'conv_fwd': ['evb_conv2d_fwd', 'evb_conv2d_fwd_stats', 'evb_conv2d_fwd_bias_stats'],
     'dgrad': ['evb_conv2d_dgrad'],
     'merge/scale_add/sumpool': ['evb_merge4', 'evb_scale_add', 'evb_sumpool2'],
     'gap+linear': ['evb_gap_fwd', 'evb_gap_bwd', 'evb_linear_fwd', 'evb_linear_bwd'],
@@ -38,19 +40,19 @@ def run(names, iters=20):
     saved = {}
     for n in names:
         saved[n] = getattr(L, n)
-        if n == 'evb_conv2d_fwd_stats':
-            def fake(*a):
-                a[12]._obj.value = 1
+        if n in ('evb_conv2d_fwd_stats', 'evb_conv2d_fwd_bias_stats'):
+            def fake(*a, _i=12 if n == 'evb_conv2d_fwd_stats' else 13):
+                a[_i]._obj.value = 1
                 return 0
             setattr(L, n, fake)
         else:
             setattr(L, n, lambda *a: 0)
     try:
         torch.manual_seed(0)
-        m = FarSegB200(farseg_config()).cuda().train()
+        m = FarSegB200(model_config(CFG)).cuda().train()
         eng = m._engine()
-        x, y = synthetic(PER_GPU_BATCH)
-        replay, out = eng.capture_step(x.cuda(), y.cuda())
+        x, y = synthetic(CFG, units_per_gpu(CFG, 1))
+        replay, out = eng.capture_step(x.cuda(), y['cls'].cuda())
         for _ in range(3):
             replay(); eng.sgd_step(0.007)
         torch.cuda.synchronize()

@@ -11,6 +11,7 @@
 //
 // Replaces (reference): the weight-gradient half of every nn.Conv2d backward on the FarSeg path
 // (aten::convolution_backward -> cuDNN wgrad), ever/module/_resnets.py:21-29, fpn.py:165,179 etc.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace evb {
@@ -320,9 +321,24 @@ struct WgradPlan {
   size_t ws_bytes;
 };
 
+// CTAs a weight-gradient launch aims for.  A full wave (148) is best for the kernel alone, but the weight gradients run on a
+// side stream NEXT TO the dgrad / BatchNorm chain: half a wave means half as many split-K partials to write and re-read (the
+// kernel is L2-fed) and leaves the other SMs to the critical path.  Measured in situ on the C2 step (bench.py, 200 steps,
+// same box): 148 -> 9.08 / 9.13 ms, 111 -> 8.89, 96 -> 8.87 / 9.00, 84 -> 8.97, 74 -> 8.83 / 8.87, 64 -> 9.04, 56 -> 9.01.
+static int wgrad_wave() {
+  static int wave = 0;
+  if (!wave) {
+    const char* e = getenv("EVB_WGRAD_WAVE");
+    wave = e ? atoi(e) : 74;
+    if (wave < 16 || wave > 592) wave = 74;
+  }
+  return wave;
+}
+
 static WgradPlan plan_wgrad(int N, int Ho, int Wo, int Cin, int Cout, int ntaps, int force_nt, int force_split,
                             int allow_mt2 = 1) {
   WgradPlan pl{};
+  const int wave = wgrad_wave();
   pl.nt = force_nt ? force_nt : (Cout >= 256 ? 256 : (Cout >= 128 ? 128 : 64));
   pl.tiles_co = (Cout + pl.nt - 1) / pl.nt;
   pl.CoutP = pl.tiles_co * pl.nt;
@@ -337,18 +353,18 @@ static WgradPlan plan_wgrad(int N, int Ho, int Wo, int Cin, int Cout, int ntaps,
   pl.mt = 1;
   if (allow_mt2 && pl.nt >= 128 && Cin >= 256) {
     const int base2 = ntaps * ((Cin + 255) / 256) * pl.tiles_co;
-    int sp = 148 / base2 > 0 ? 148 / base2 : 1;
+    int sp = wave / base2 > 0 ? wave / base2 : 1;
     if (sp > (pl.nchunks + 7) / 8) sp = (pl.nchunks + 7) / 8;
-    if (base2 * sp >= 110) pl.mt = 2;
+    if (base2 * sp >= wave * 3 / 4) pl.mt = 2;
   }
   pl.tiles_ci = (Cin + 128 * pl.mt - 1) / (128 * pl.mt);
   pl.CinP = pl.tiles_ci * 128 * pl.mt;
   const int base = ntaps * pl.tiles_ci * pl.tiles_co;
-  int split = force_split ? force_split : 148 / base;  // round down: one full wave of CTAs (measured best, tools/exp_wgrad.py)
+  int split = force_split ? force_split : wave / base;  // round down: at most one wave of CTAs
   if (split > pl.nchunks) split = pl.nchunks;
   if (!force_split && split > 74) split = 74;   // bounds the reduction depth (and workspace) of small-channel convs
   if (!force_split) {
-    const int max_by_work = (pl.nchunks + 7) / 8;  // at least ~8 chunks (512 pixels) per CTA
+    const int max_by_work = (pl.nchunks + 7) / 8;  // at least ~8 chunks (512 pixels) per CTA (16 / 32 measured no better)
     if (split > max_by_work) split = max_by_work;
   }
   if (split < 1) split = 1;

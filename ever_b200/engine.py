@@ -114,6 +114,8 @@ class FarSegEngine:
             pass
         self._flatten_params()
         self._collect()
+        if os.environ.get('EVB_BN_REDUCE_BLOCKS'):   # grid cap of the BatchNorm backward reduction, blocks per SM (1..4)
+            self.L.evb_set_bn_reduce_blocks(c_int(int(os.environ['EVB_BN_REDUCE_BLOCKS'])))
         self.tape = []
         self.ws = None
         self.ws_bytes = 0

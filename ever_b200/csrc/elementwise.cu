@@ -337,7 +337,8 @@ bn_bwd_apply_ca_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
     const int c = c0 + j;
     a[j] = scale[c];
     if (MASK == 2) sh[j] = shift[c];
-    if (frozen) { c2[j] = 0.f; k0[j] = 0.f; }
+    if (frozen == 2) { c2[j] = dgamma[c]; k0[j] = dbeta[c]; }   // explicit constants (evb_norm_bwd_apply: GroupNorm, plain ReLU)
+    else if (frozen) { c2[j] = 0.f; k0[j] = 0.f; }
     else {
       c2[j] = a[j] * rstd[c] * dgamma[c] * inv_m;
       k0[j] = c2[j] * mean[c] - a[j] * dbeta[c] * inv_m;
@@ -1091,7 +1092,10 @@ extern "C" int evb_bn_apply(const void* x, const float* scale, const float* shif
 template <int MASK>
 static int launch_bn_bwd_ca(const void* dy, const void* x, const void* ymask, const float* mean, const float* rstd,
                             const float* scale, const float* shift, int frozen, void* dx, void* dres, int dres_acc,
-                            float* dgamma, float* dbeta, int param_acc, long long M, int C, void* ws, cudaStream_t st) {
+                            float* dgamma, float* dbeta, int param_acc, long long M, int C, void* ws, cudaStream_t st,
+                            int phase = 0) {
+  // phase 0: reduce + finalize + apply (BatchNorm).  1: reduce + finalize only (per-channel sums -> dgamma / dbeta).
+  // 2: apply only, with explicit per-channel constants c2 = dgamma[], k0 = dbeta[] (frozen must be 2).
   constexpr int NT = MASK == 1 ? 3 : 2;
   const int cg = C / 8;
   const int bt = (kEwThreads / cg) * cg;
@@ -1112,16 +1116,21 @@ static int launch_bn_bwd_ca(const void* dy, const void* x, const void* ymask, co
   const int cap = per_sm * 148;
   if (nb > cap) nb = cap;
   if (nb < 1) nb = 1;
-  bn_bwd_reduce_ca_kernel<MASK><<<(int)nb, bt, smem, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
-                                                         (const __nv_bfloat16*)ymask, mean, scale, shift, M, C, (float*)ws);
-  float* fresh = (float*)ws + (size_t)kNbPadBwd * 2 * C;
-  if (evb_launch_pdl_small(bn_bwd_finalize2_kernel, dim3((C + 7) / 8), dim3(256), 0, st, (const float*)ws, (int)nb, C, rstd,
-                           dgamma, dbeta, param_acc, fresh) != cudaSuccess)
-    return EVB_ERR_CUDA;
+  float* fresh = ws ? (float*)ws + (size_t)kNbPadBwd * 2 * C : nullptr;
+  if (phase != 2) {
+    bn_bwd_reduce_ca_kernel<MASK><<<(int)nb, bt, smem, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
+                                                           (const __nv_bfloat16*)ymask, mean, scale, shift, M, C, (float*)ws);
+    if (evb_launch_pdl_small(bn_bwd_finalize2_kernel, dim3((C + 7) / 8), dim3(256), 0, st, (const float*)ws, (int)nb, C, rstd,
+                             dgamma, dbeta, param_acc, fresh) != cudaSuccess)
+      return EVB_ERR_CUDA;
+    if (phase == 1) return EVB_OK;
+  }
   const long long nvec = M * C / 8;
+  const float* c_dgamma = phase == 2 ? dgamma : (const float*)(fresh + C);
+  const float* c_dbeta = phase == 2 ? dbeta : (const float*)fresh;
   if (evb_launch_pdl_small(bn_bwd_apply_ca_kernel<MASK>, dim3(ew_blocks(nvec, bt * 8, 148 * (NT == 3 ? 2 : 3))), dim3(bt), smem,
                            st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)ymask, mean, rstd,
-                           scale, shift, (const float*)(fresh + C), (const float*)fresh, frozen, (__nv_bfloat16*)dx,
+                           scale, shift, c_dgamma, c_dbeta, frozen, (__nv_bfloat16*)dx,
                            (__nv_bfloat16*)dres, dres_acc, (unsigned)nvec, C, 1.0f / (float)M) != cudaSuccess)
     return EVB_ERR_CUDA;
   return EVB_OK;
@@ -1137,6 +1146,38 @@ extern "C" int evb_bn_bwd(const void* dy, const void* x, const void* ymask, cons
   if (mask_mode == 0) rc = launch_bn_bwd_ca<0>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
   else if (mask_mode == 1) rc = launch_bn_bwd_ca<1>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
   else rc = launch_bn_bwd_ca<2>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
+  if (rc) return rc;
+  return LAUNCH_OK();
+}
+
+// The two halves of evb_bn_bwd as separate calls, for normalisations whose statistics are not per-channel batch statistics
+// (GroupNorm: ever_b200 FreeNet path) and for element-wise gates (plain ReLU, squeeze-excitation):
+// evb_norm_bwd_reduce: dbeta[c] (+)= sum_rows g, dgamma[c] (+)= rstd[c] * sum_rows g * (x - mean[c]), g = dy * mask.
+extern "C" int evb_norm_bwd_reduce(const void* dy, const void* x, const void* ymask, const float* mean, const float* rstd,
+                                   const float* scale, const float* shift, int mask_mode, float* dgamma, float* dbeta,
+                                   int param_acc, long long M, int C, void* ws, void* stream) {
+  if (C % 8 || C > 2048 || mask_mode < 0 || mask_mode > 2 || !dgamma || !dbeta) return EVB_ERR_ARG;
+  if (M * C / 8 >= (1LL << 31) - (1LL << 24)) return EVB_ERR_ARG;
+  int rc;
+  if (mask_mode == 0) rc = launch_bn_bwd_ca<0>(dy, x, ymask, mean, rstd, scale, shift, 0, nullptr, nullptr, 0, dgamma, dbeta, param_acc, M, C, ws, ST, 1);
+  else if (mask_mode == 1) rc = launch_bn_bwd_ca<1>(dy, x, ymask, mean, rstd, scale, shift, 0, nullptr, nullptr, 0, dgamma, dbeta, param_acc, M, C, ws, ST, 1);
+  else rc = launch_bn_bwd_ca<2>(dy, x, ymask, mean, rstd, scale, shift, 0, nullptr, nullptr, 0, dgamma, dbeta, param_acc, M, C, ws, ST, 1);
+  if (rc) return rc;
+  return LAUNCH_OK();
+}
+// evb_norm_bwd_apply: dx = a[c] * (dy * mask) + k0[c] - c2[c] * x with explicit per-channel constants (a = the forward scale);
+// dres (+)= dy * mask as in evb_bn_bwd.  A plain ReLU backward is a = 1, k0 = c2 = 0, mask_mode 1.
+extern "C" int evb_norm_bwd_apply(const void* dy, const void* x, const void* ymask, const float* a, const float* shift,
+                                  const float* c2, const float* k0, int mask_mode, void* dx, void* dres, int dres_acc,
+                                  long long M, int C, void* stream) {
+  if (C % 8 || C > 2048 || mask_mode < 0 || mask_mode > 2 || !a || !c2 || !k0) return EVB_ERR_ARG;
+  if (M * C / 8 >= (1LL << 31) - (1LL << 24)) return EVB_ERR_ARG;
+  int rc;
+  float* c2_ = const_cast<float*>(c2);
+  float* k0_ = const_cast<float*>(k0);
+  if (mask_mode == 0) rc = launch_bn_bwd_ca<0>(dy, x, ymask, a, a, a, shift, 2, dx, dres, dres_acc, c2_, k0_, 0, M, C, nullptr, ST, 2);
+  else if (mask_mode == 1) rc = launch_bn_bwd_ca<1>(dy, x, ymask, a, a, a, shift, 2, dx, dres, dres_acc, c2_, k0_, 0, M, C, nullptr, ST, 2);
+  else rc = launch_bn_bwd_ca<2>(dy, x, ymask, a, a, a, shift, 2, dx, dres, dres_acc, c2_, k0_, 0, M, C, nullptr, ST, 2);
   if (rc) return rc;
   return LAUNCH_OK();
 }

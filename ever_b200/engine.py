@@ -147,6 +147,9 @@ class FarSegEngine:
         self._graphs = {}
         self.debug = None            # dict -> named activations are recorded (tests / diagnostics)
         self.tf = None               # callable(kind, name, tensor) -> teacher forcing hook (tests; see _tf_fwd)
+        self._read_config(module)
+
+    def _read_config(self, module):
         cfg = module.config
         self.ignore_index = int(cfg.loss.ignore_index)
         self.ce_w = float(cfg.loss.ce.weight)
@@ -358,7 +361,8 @@ class FarSegEngine:
         # optional (EVB_PACK_OVERLAP=1; measured neutral on B200, off by default): blocks of the convolutions the forward
         # pass needs first (stem, layer1, layer2) are packed on the main stream, the rest (layer3, layer4, head: ~95 % of
         # the parameters) on the side stream while those layers run
-        first_late = self.stages[2][0]['c1'] if len(self.stages) > 2 else None
+        stages = getattr(self, 'stages', ())
+        first_late = stages[2][0]['c1'] if len(stages) > 2 else None
         self._pack_split = nblk
         if first_late is not None and self.side is not None and os.environ.get('EVB_PACK_OVERLAP', '0') == '1':
             self._pack_split = rows[self.convs.index(first_late)][10]
@@ -1119,9 +1123,13 @@ class FarSegEngine:
         n, h4, w4, _ = cls.data.shape
         ld = self.ld if cp is self.cls else 16
         logits = self._new(n, h4 * f, w4 * f, ld)
-        check(L.evb_bilinear_up(ptr(cls.data), None, None, ptr(logits), c_int(n), c_int(h4), c_int(w4), c_int(ld),
-                                c_int(64), c_int(ld), c_int(f), stream()), 'evb_bilinear_up(logits)')
-        if self.tf is not None and cp.name:
+        if f == 1:   # classifier at the output resolution (no up-sampling): the first ld channels of the padded conv output
+            check(L.evb_copy2d_bf16(ptr(cls.data), c_int(64), ptr(logits), c_int(ld), c_ll(n * h4 * w4), c_int(ld), c_int(0),
+                                    stream()), 'evb_copy2d_bf16')
+        else:
+            check(L.evb_bilinear_up(ptr(cls.data), None, None, ptr(logits), c_int(n), c_int(h4), c_int(w4), c_int(ld),
+                                    c_int(64), c_int(ld), c_int(f), stream()), 'evb_bilinear_up(logits)')
+        if self.tf is not None and cp.name and f != 1:
             self.tf('fwd', cp.name.rsplit('.', 1)[0] + '.1', logits)
         self._dbg('cls' if name == 'logits' else name + '_cls', cls)
         self._dbg(name, logits)
@@ -1141,7 +1149,7 @@ class FarSegEngine:
         check(L.evb_loss_stats(ptr(logits), ptr(labels), c_ll(npx), c_int(k), c_int(logits.shape[-1]), c_int(self.ignore_index),
                                ptr(stats), ptr(ws), stream()), 'evb_loss_stats')
         g = dict(cls=cls, logits=logits, labels=labels, stats=stats, npx=npx, k=k, f=f, names=names, weight=weight,
-                 name=cls.name.rsplit('.', 1)[0] + '.1' if cls.name else None)
+                 name=cls.name.rsplit('.', 1)[0] + '.1' if (cls.name and f != 1) else None)
         self._groups.append(g)
         return g
 
@@ -1256,6 +1264,10 @@ class FarSegEngine:
                 self.tf('bwd', g['name'], dlogits)
             cls.grad = torch.zeros_like(cls.data)   # padding channels 16..63 stay zero
             cls.has_grad = True
+            if f == 1:
+                check(L.evb_copy2d_bf16(ptr(dlogits), c_int(ld), ptr(cls.grad), c_int(64), c_ll(n * hh * ww), c_int(ld),
+                                        c_int(0), stream()), 'evb_copy2d_bf16')
+                continue
             ws = self._ws(L.evb_bilinear_up_bwd_workspace(c_int(n), c_int(hh // f), c_int(ww // f), c_int(ld), c_int(f)))
             check(L.evb_bilinear_up_bwd_sep(ptr(dlogits), ptr(cls.grad), c_int(n), c_int(hh // f), c_int(ww // f), c_int(ld),
                                             c_int(ld), c_int(64), c_int(f), ptr(ws), c_ll(self._ws_cap()), stream()),

@@ -233,8 +233,55 @@ class _StepFn(torch.autograd.Function):
         return (None, None, None) + grads
 
 
+class NativeStepMixin:
+    """forward / backward plumbing shared by the plugin models: the training forward is one autograd node (_StepFn) and
+    ``backward`` takes the native or the autograd path (see FarSegB200.backward)"""
+
+    def _train_forward(self, eng, x, labels):
+        if torch.is_grad_enabled():
+            tp = [p for p in eng.params if p.requires_grad]
+            keys_vals = _StepFn.apply(self, x, labels, *tp)
+            out = dict(zip(eng._last_keys, keys_vals))
+        elif bool(self.config.cuda_graph):
+            out = eng.graph_forward(x, labels)
+        else:
+            out = eng.forward_train(x, labels)
+        object.__setattr__(self, '_last_out', out)
+        return out
+
+    def backward(self, loss_dict=None, amp=None, scaler=None, **kwargs):
+        """ERModule.backward hook (ever/interface/module.py:76-81).
+
+        Native path: ``loss_dict`` is None or the very dict values the last training forward returned -> the engine's
+        backward runs with unit loss weights, the gradient all-reduce follows (world > 1) and every ``p.grad`` aliases its
+        slot of the flat arena (StepLoop, bench, and any caller that wants the fused optimizer).
+        Autograd path: anything else (Launcher hands over ``v / forward_times``; a GradScaler may scale) -> the reference's
+        own ``sum(loss_dict.values()).backward()``, which reaches the engine through ``_StepFn.backward`` with the upstream
+        factors; gradients accumulate into ordinary ``p.grad`` tensors and a DDP wrapper does its own all-reduce."""
+        eng = self._engine()
+        last = getattr(self, '_last_out', None)
+        native = loss_dict is None or (last is not None and len(loss_dict) == len(last)
+                                       and all(loss_dict.get(k) is v for k, v in last.items()))
+        if native:
+            eng.backward()
+            return
+        total_loss = sum([e for e in loss_dict.values()])
+        if amp and scaler is not None:
+            scaler.scale(total_loss).backward()
+        else:
+            total_loss.backward()
+
+    def clip_grad_info(self):
+        return dict()
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        object.__setattr__(self, 'engine', None)  # parameter storage moved: rebuild arenas lazily
+        return r
+
+
 @MODEL.register('FarSegB200')
-class FarSegB200(ERModule):
+class FarSegB200(NativeStepMixin, ERModule):
     """FarSeg (ResNetEncoder -> FarSegHead -> CE + Dice), glue model of SURVEY.md Appendix E, computed by the
     sm_100a engine.  forward(x, y): training -> {'ce_loss','dice_loss'}; eval -> softmax probabilities."""
 
@@ -360,48 +407,6 @@ class FarSegB200(ERModule):
             return self._train_forward(eng, x, self._labels(y))
         return eng.forward_eval(x)
 
-    def _train_forward(self, eng, x, labels):
-        if torch.is_grad_enabled():
-            tp = [p for p in eng.params if p.requires_grad]
-            keys_vals = _StepFn.apply(self, x, labels, *tp)
-            out = dict(zip(eng._last_keys, keys_vals))
-        elif bool(self.config.cuda_graph):
-            out = eng.graph_forward(x, labels)
-        else:
-            out = eng.forward_train(x, labels)
-        object.__setattr__(self, '_last_out', out)
-        return out
-
-    def backward(self, loss_dict=None, amp=None, scaler=None, **kwargs):
-        """ERModule.backward hook (ever/interface/module.py:76-81).
-
-        Native path: ``loss_dict`` is None or the very dict values the last training forward returned -> the engine's
-        backward runs with unit loss weights, the gradient all-reduce follows (world > 1) and every ``p.grad`` aliases its
-        slot of the flat arena (StepLoop, bench, and any caller that wants the fused optimizer).
-        Autograd path: anything else (Launcher hands over ``v / forward_times``; a GradScaler may scale) -> the reference's
-        own ``sum(loss_dict.values()).backward()``, which reaches the engine through ``_StepFn.backward`` with the upstream
-        factors; gradients accumulate into ordinary ``p.grad`` tensors and a DDP wrapper does its own all-reduce."""
-        eng = self._engine()
-        last = getattr(self, '_last_out', None)
-        native = loss_dict is None or (last is not None and len(loss_dict) == len(last)
-                                       and all(loss_dict.get(k) is v for k, v in last.items()))
-        if native:
-            eng.backward()
-            return
-        total_loss = sum([e for e in loss_dict.values()])
-        if amp and scaler is not None:
-            scaler.scale(total_loss).backward()
-        else:
-            total_loss.backward()
-
-    def clip_grad_info(self):
-        return dict()
-
-    def _apply(self, fn, *a, **k):
-        r = super()._apply(fn, *a, **k)
-        object.__setattr__(self, 'engine', None)  # parameter storage moved: rebuild arenas lazily
-        return r
-
 
 MODEL.register('FarSeg', FarSegB200, override=True) if hasattr(MODEL, 'register') else None
 
@@ -453,3 +458,6 @@ class ChangeStarB200(FarSegB200):
 
 
 MODEL.register('ChangeStar', ChangeStarB200, override=True) if hasattr(MODEL, 'register') else None
+
+
+from . import freenet  # noqa: E402,F401  (registers 'FreeNetB200' / 'FreeNet'; imports NativeStepMixin from this module)

@@ -99,6 +99,26 @@ int evb_set_bn_reduce_blocks(int per_sm);
 int evb_bn_bwd(const void* dy, const void* x, const void* ymask, const float* mean, const float* rstd, const float* scale,
                const float* shift, int mask_mode, int frozen, void* dx, void* dres, int dres_acc, float* dgamma,
                float* dbeta, int param_acc, long long M, int C, void* ws, void* stream);
+/* the two halves of evb_bn_bwd on their own (GroupNorm, squeeze-excitation and plain-ReLU backward are built from them):
+ * reduce: dbeta[c] (+)= sum_rows g, dgamma[c] (+)= rstd[c] * sum_rows g * (x - mean[c]), g = dy * mask;
+ * apply:  dx = a[c] * g + k0[c] - c2[c] * x with explicit per-channel constants, dres (+)= g */
+int evb_norm_bwd_reduce(const void* dy, const void* x, const void* ymask, const float* mean, const float* rstd,
+                        const float* scale, const float* shift, int mask_mode, float* dgamma, float* dbeta, int param_acc,
+                        long long M, int C, void* ws, void* stream);
+int evb_norm_bwd_apply(const void* dy, const void* x, const void* ymask, const float* a, const float* shift, const float* c2,
+                       const float* k0, int mask_mode, void* dx, void* dres, int dres_acc, long long M, int C, void* stream);
+/* nn.GroupNorm(G, Creal) on an NHWC tensor of ONE sample (FreeNet's conv3x3_gn_relu blocks): evb_bn_stats gives the per-channel
+ * mean / rstd (with eps_bn); evb_gn_fold combines the channels of each group into GroupNorm's statistics and emits the
+ * per-channel affine map (scale, shift) for evb_bn_apply plus (gmean, grstd) for the backward; channels >= Creal (zero padding)
+ * get the identity.  evb_gn_bwd_consts turns the per-channel sums of evb_norm_bwd_reduce (called with mean = gmean,
+ * rstd = grstd) into the constants of evb_norm_bwd_apply; inv_m = 1 / (pixels * Creal / G). */
+int evb_gn_fold(const float* mean_c, const float* rstd_c, float eps_bn, const float* gamma, const float* beta, int C, int Creal,
+                int G, float eps, float* scale, float* shift, float* gmean, float* grstd, void* stream);
+int evb_gn_bwd_consts(const float* dgamma_c, const float* dbeta_c, const float* gamma, const float* gmean, const float* grstd,
+                      int C, int Creal, int G, float inv_m, float* c2, float* k0, void* stream);
+/* squeeze-excitation gate (ever/module/se_block.py:9-24): sig = bf16(sigmoid(s)); ds = bf16(dsig * sig * (1 - sig)) */
+int evb_sigmoid_fwd(const float* s, float* sig, int n, void* stream);
+int evb_sigmoid_bwd(const float* dsig, const float* sig, float* ds, int n, void* stream);
 /* db[C] (+)= column sums of dy[M,C]  (conv bias gradient) */
 int evb_bias_grad(const void* dy, long long M, int C, float* db, float* unused, int accumulate, void* ws, void* stream);
 

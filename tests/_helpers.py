@@ -35,7 +35,7 @@ class RefCapture:
         self.fwd, self.bwd, self.handles, self._calls = {}, {}, [], {}
         for name, mod in model.named_modules():
             leafish = isinstance(mod, (nn.Conv2d, nn.ReLU, nn.MaxPool2d, nn.Identity, nn.Dropout2d)) or \
-                type(mod).__name__ in ('_Fp32Around', 'Bf16compatible') or \
+                type(mod).__name__ in ('_Fp32Around', 'Bf16compatible', 'SEBlock', 'SEBlockOracle') or \
                 (isinstance(mod, nn.BatchNorm2d) and '.downsample.' in name)
             if not leafish:
                 continue

@@ -39,9 +39,10 @@ CONFIGS = {
     'c4': dict(model='FarSeg', resnet='resnet101', k=7, dec=256, hw=(1024, 1024), per_gpu=4, scaling='weak', cin=3,
                workload='FarSeg-R101 7-class, 4x3x1024x1024 synthetic tiles per GPU (BASELINE configs[3])',
                gflop_per_tile=1837.0),
-    'c5': dict(model='FarSeg', resnet='resnet50', k=9, dec=256, hw=(640, 352), per_gpu=1, scaling='weak', cin=200,
-               workload='hyperspectral cube 1x200x610x340 padded to 640x352 through ResNetEncoder(in_channels=200) + FarSegHead '
-                        '(shape class of BASELINE configs[4]; FreeNet itself is not in the reference tree)', gflop_per_tile=None),
+    'c5': dict(model='FreeNet', resnet='freenet', k=9, dec=128, hw=(624, 352), per_gpu=1, scaling='weak', cin=200,
+               workload='FreeNet (patch-free hyperspectral classification: conv3x3+GroupNorm+ReLU blocks with squeeze-excitation, '
+                        'top-down fusion), one 200-band 610x340 cube zero-padded to 624x352 per GPU (BASELINE configs[4]), masked '
+                        'CE on the labelled pixels', gflop_per_tile=None),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the ncu --set full capture
 # summarised in profiles/ (None until captured)
@@ -96,6 +97,8 @@ class ClockSampler:
 
 
 def model_config(cfg):
+    if cfg['model'] == 'FreeNet':
+        return dict(in_channels=cfg['cin'], num_classes=cfg['k'])
     return dict(encoder=dict(resnet_type=cfg['resnet'], in_channels=cfg['cin']),
                 head=dict(fpn_decoder=dict(out_channels=cfg['dec'], classifier_config=dict(num_classes=cfg['k']))))
 
@@ -113,6 +116,11 @@ def synthetic(cfg, n, seed=0):
     kk = max(cfg['k'], 2)
     g = torch.Generator().manual_seed(1234 + seed)
     x = torch.randn(n, cfg['cin'], h, w, generator=g)
+    if cfg['model'] == 'FreeNet':   # labels 1..K on 5 % of the pixels (0 = unlabelled) + the training mask that selects them
+        g = torch.Generator().manual_seed(4321 + seed)
+        y = torch.randint(1, kk + 1, (n, h, w), generator=g)
+        wm = (torch.rand(n, h, w, generator=g) < 0.05).float()
+        return x, dict(cls=y * (wm > 0).long(), w=wm)
     g = torch.Generator().manual_seed(4321 + seed)
     y = torch.randint(0, kk, (n, h, w), generator=g)
     g = torch.Generator().manual_seed(99 + seed)
@@ -131,6 +139,8 @@ def tiles_of(cfg, n):
 
 def metric_name(cfg):
     h, w = cfg['hw']
+    if cfg['model'] == 'FreeNet':
+        return 'FreeNet %dx%dx%d cubes/s fwd+bwd' % (cfg['cin'], h, w)
     return '%s-%s %dx%d tiles/s fwd+bwd' % (cfg['model'], cfg['resnet'].replace('resnet', 'R'), h, w)
 
 
@@ -142,6 +152,9 @@ def reference_model(cfg):
     if cfg['model'] == 'ChangeStar':
         from oracle.changestar_oracle import ChangeStarOracle
         return ChangeStarOracle(cfg['resnet'], cfg['k'], cfg['dec']), 'port'
+    if cfg['model'] == 'FreeNet':   # not in the reference tree either: the restated network (its SEBlock is the in-tree one)
+        from oracle.freenet_oracle import FreeNetOracle
+        return FreeNetOracle(cfg['cin'], cfg['k']), 'port'
     try:
         from oracle.ref_glue import make_reference_farseg, reference_available
         if reference_available():
@@ -332,7 +345,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.manual_seed(0)
-    cls = ChangeStarB200 if cfg['model'] == 'ChangeStar' else FarSegB200
+    from ever_b200.freenet import FreeNetB200
+    cls = dict(ChangeStar=ChangeStarB200, FreeNet=FreeNetB200).get(cfg['model'], FarSegB200)
     model = cls(model_config(cfg)).cuda().train()
     eng = model._engine()
     eng.set_distributed(rank, world)
@@ -349,7 +363,7 @@ def run_b200(args):
     yh = {k_: v.pin_memory() for k_, v in yh.items()}
     x = xh.cuda()
     y = {k_: v.cuda() for k_, v in yh.items()}
-    labels = y if cfg['model'] == 'ChangeStar' else y['cls']
+    labels = y['cls'] if cfg['model'] == 'FarSeg' else y
     lr = 0.007
 
     def barrier():
@@ -481,7 +495,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms2 = float(t)
-    h2d = int(xh.numel() * 4 + sum(v.numel() * 8 for v in yh.values()))
+    h2d = int(xh.numel() * xh.element_size() + sum(v.numel() * v.element_size() for v in yh.values()))
     e2e = dict(value=world * n_tiles / (ms2 * 1e-3), unit='tiles/s', h2d_bytes_per_step=h2d,
                d2h_bytes_per_step=4 * len(out), ms_per_step=ms2, steps=e2e_steps,
                api='%s.forward(x, y) + .backward() via libevb200.so C ABI; pinned host inputs, double-buffered H2D on a copy '

@@ -209,7 +209,13 @@ class FreeNetEngine(FarSegEngine):
         cr, hid, hw = l1.in_features, l1.out_features, h * w
         f32 = torch.float32
         v = self._new(n, c, dtype=f32)
-        check(L.evb_gap_fwd(ptr(x.data), ptr(v), c_int(n), c_int(hw), c_int(c), stream()), 'evb_gap_fwd')
+        one, zero = self._const(c)
+        scr3 = self._new(3, c, dtype=f32)
+        for s in range(n):   # global average pool = the per-channel mean of the BatchNorm statistics kernel (full-grid column
+            ws = self._ws(L.evb_bn_workspace(c_ll(hw), c_int(c)))   # sums; evb_gap_fwd is written for the 16 x 16 scene map)
+            check(L.evb_bn_stats(ptr(x.data[s]), c_ll(hw), c_int(c), ptr(one), ptr(zero), None, None, c_float(0.0),
+                                 c_float(1e-5), ptr(v[s]), ptr(scr3[0]), ptr(scr3[1]), ptr(scr3[2]), ptr(ws), stream()),
+                  'evb_bn_stats')
         vc = self._new(n, cr, dtype=f32)      # the real channels, compact rows for the linears
         check(L.evb_copy2d_f32(ptr(v), c_int(c), ptr(vc), c_int(cr), c_int(n), c_int(cr), c_int(0), stream()), 'evb_copy2d_f32')
         h1, s2 = self._new(n, hid, dtype=f32), self._new(n, cr, dtype=f32)

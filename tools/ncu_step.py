@@ -6,11 +6,12 @@ sys.path.insert(0, '.')
 import torch
 from bench import CONFIGS, model_config, synthetic, units_per_gpu
 from ever_b200 import _lib
+from ever_b200.freenet import FreeNetB200
 from ever_b200.module import ChangeStarB200, FarSegB200
 nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 cfg = CONFIGS[sys.argv[2] if len(sys.argv) > 2 else 'c2']
 torch.manual_seed(0)
-m = (ChangeStarB200 if cfg['model'] == 'ChangeStar' else FarSegB200)(model_config(cfg)).cuda().train()
+m = dict(ChangeStar=ChangeStarB200, FreeNet=FreeNetB200).get(cfg['model'], FarSegB200)(model_config(cfg)).cuda().train()
 x, y = synthetic(cfg, units_per_gpu(cfg, 1))
 x, y = x.cuda(), {k: v.cuda() for k, v in y.items()}
 for i in range(nsteps):

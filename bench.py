@@ -33,6 +33,9 @@ CONFIGS = {
     'c2': dict(model='FarSeg', resnet='resnet50', k=15, dec=256, hw=(512, 512), per_gpu=8, scaling='weak', cin=3,
                workload='FarSeg-R50 (ResNet-50 + FPN + FS-Relation + asymmetric decoder, 256-ch), 15-class, 8x3x512x512 '
                         'synthetic tiles per GPU (BASELINE configs[1])', gflop_per_tile=343.1),
+    'c2s': dict(model='FarSeg', resnet='resnet50', k=15, dec=256, hw=(512, 512), total=8, scaling='strong', cin=3,
+                workload='FarSeg-R50 15-class, 8x3x512x512 synthetic tiles in TOTAL split over the GPUs (strong scaling of '
+                         'BASELINE configs[1]: 1 tile per GPU at 8 GPUs)', gflop_per_tile=343.1),
     'c3': dict(model='ChangeStar', resnet='resnet50', k=1, dec=256, hw=(512, 512), total=8, scaling='strong', cin=3,
                workload='ChangeStar (FarSeg-R50 + ChangeMixin), 8 bitemporal pairs of 3x512x512 sharded by batch over the '
                         'GPUs (BASELINE configs[2]); a pair counts as 2 tiles', gflop_per_tile=None),
@@ -186,7 +189,7 @@ def cpu_reference(cfg, n_units, iters, warmup):
     return tiles_of(cfg, n_units) / sec, sec, cores, kind, len(ts)
 
 
-CPU_SAMPLE = dict(c1=2, c2=4, c3=1, c4=1, c5=1)   # units per CPU step (bounded sample of the per-GPU batch)
+CPU_SAMPLE = dict(c1=2, c2=4, c2s=4, c3=1, c4=1, c5=1)   # units per CPU step (bounded sample of the per-GPU batch)
 
 
 def run_reference(args):

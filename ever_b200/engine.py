@@ -77,6 +77,12 @@ class BNP:
     """BatchNorm parameters; cpad > C gives zero-padded shadow buffers (padded channels: gamma 1, beta 0 -> stay 0)."""
 
     def __init__(self, bn, cpad=None):
+        if isinstance(bn, torch.nn.SyncBatchNorm):
+            # train.sync_bn (ever/trainer/th_ddp_trainer.py:21-22) converts every BatchNorm2d: statistics over the GLOBAL batch
+            # need two collectives per layer, which this engine does not issue -- refuse instead of silently normalising with
+            # per-GPU statistics
+            raise NotImplementedError('SyncBatchNorm (train.sync_bn=True) is not supported by the B200 engine: BatchNorm '
+                                      'statistics are per GPU (the reference default); set sync_bn=False')
         self.bn = bn
         self.c_real = bn.num_features
         self.c = cpad or bn.num_features

@@ -163,6 +163,51 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, 
   }
 }
 
+// SyncBatchNorm support: the per-CTA partial columns of a rank are summed (fixed order) into sums[2][C]; the caller
+// all-reduces sums over the ranks and finalizes with the global row count.
+__global__ void bn_partial_sums_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ sums) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= C) return;
+  double s, ss;
+  reduce_partials(partial, nblk, C, c, s, ss);
+  if ((threadIdx.x & 31) != 0) return;
+  sums[c] = (float)s;
+  sums[C + c] = (float)ss;
+}
+__global__ void bn_finalize_sums_kernel(const float* __restrict__ sums, double M, int C, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, float* __restrict__ running_mean,
+                                        float* __restrict__ running_var, float momentum, float eps, float* __restrict__ mean,
+                                        float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = (double)sums[c] / M;
+  double var = (double)sums[C + c] / M - mu * mu;
+  if (var < 0) var = 0;
+  const float rs = (float)(1.0 / sqrt(var + (double)eps));
+  mean[c] = (float)mu;
+  rstd[c] = rs;
+  const float a = gamma[c] * rs;
+  scale[c] = a;
+  shift[c] = beta[c] - (float)mu * a;
+  if (running_mean) {
+    const double unb = M > 1 ? var * M / (M - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  }
+}
+// backward constants of dx = a g + k0 - c2 x from (all-reduced) sums: c2 = a rstd dgamma / M, k0 = c2 mean - a dbeta / M
+__global__ void bn_bwd_consts_kernel(const float* __restrict__ scale, const float* __restrict__ rstd,
+                                     const float* __restrict__ mean, const float* __restrict__ dgamma,
+                                     const float* __restrict__ dbeta, float inv_m, int C, float* __restrict__ c2,
+                                     float* __restrict__ k0) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float a = scale[c];
+  const float v = a * rstd[c] * dgamma[c] * inv_m;
+  c2[c] = v;
+  k0[c] = v * mean[c] - a * dbeta[c] * inv_m;
+}
+
 // eval / frozen BN: fold running stats
 __global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C,
                                float* scale, float* shift, float* mean, float* rstd) {
@@ -1042,6 +1087,30 @@ extern "C" int evb_bn_finalize(const float* partial, int nblk, long long M, int 
   if (evb_launch_pdl_small(bn_finalize_kernel, dim3((C + 7) / 8), dim3(256), 0, ST, partial, nblk, M, C, gamma, beta,
                            running_mean, running_var, momentum, eps, mean, rstd, scale, shift) != cudaSuccess)
     return EVB_ERR_CUDA;
+  return LAUNCH_OK();
+}
+
+// nn.SyncBatchNorm (train.sync_bn, ever/trainer/th_ddp_trainer.py:21-22): statistics over the batch of ALL ranks.
+// evb_bn_partial_sums: this rank's sums[2][C] from the conv epilogue's partial columns; the caller all-reduces them;
+// evb_bn_finalize_sums: mean / rstd / folded scale / shift and the running statistics from global sums over M_total rows;
+// evb_bn_bwd_consts: the constants of evb_norm_bwd_apply from the all-reduced backward sums.
+extern "C" int evb_bn_partial_sums(const float* partial, int nblk, int C, float* sums, void* stream) {
+  if (nblk < 1 || nblk > kNbPad || C < 1) return EVB_ERR_ARG;
+  bn_partial_sums_kernel<<<(C + 7) / 8, 256, 0, ST>>>(partial, nblk, C, sums);
+  return LAUNCH_OK();
+}
+extern "C" int evb_bn_finalize_sums(const float* sums, double M_total, int C, const float* gamma, const float* beta,
+                                    float* running_mean, float* running_var, float momentum, float eps, float* mean,
+                                    float* rstd, float* scale, float* shift, void* stream) {
+  if (M_total < 1 || C < 1) return EVB_ERR_ARG;
+  bn_finalize_sums_kernel<<<(C + 127) / 128, 128, 0, ST>>>(sums, M_total, C, gamma, beta, running_mean, running_var, momentum,
+                                                           eps, mean, rstd, scale, shift);
+  return LAUNCH_OK();
+}
+extern "C" int evb_bn_bwd_consts(const float* scale, const float* rstd, const float* mean, const float* dgamma,
+                                 const float* dbeta, float inv_m, int C, float* c2, float* k0, void* stream) {
+  if (C < 1) return EVB_ERR_ARG;
+  bn_bwd_consts_kernel<<<(C + 127) / 128, 128, 0, ST>>>(scale, rstd, mean, dgamma, dbeta, inv_m, C, c2, k0);
   return LAUNCH_OK();
 }
 

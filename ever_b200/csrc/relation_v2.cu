@@ -113,6 +113,20 @@ channel_scale_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
   }
 }
 
+// y = keep ? bf16(x * scale) : 0   (nn.Dropout: keep = the element survived, scale = 1 / (1 - p); backward: same map on dy)
+__global__ void __launch_bounds__(256)
+dropout_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ keep, float scale,
+                     __nv_bfloat16* __restrict__ y, long long nvec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float v[8], k[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + i * 8), v);
+    unpack8(*reinterpret_cast<const bf16x8*>(keep + i * 8), k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = k[j] != 0.f ? v[j] * scale : 0.f;
+    *reinterpret_cast<bf16x8*>(y + i * 8) = pack8(v);
+  }
+}
+
 }  // namespace evb
 
 using namespace evb;
@@ -148,5 +162,14 @@ extern "C" int evb_channel_scale(const void* x, const float* m, void* y, int N, 
   long long b = ((long long)N * HW * (C / 8) + 255) / 256;
   if (b > 148 * 8) b = 148 * 8;
   channel_scale_kernel<<<(int)b, 256, 0, ST>>>((const __nv_bfloat16*)x, m, (__nv_bfloat16*)y, N, HW, C);
+  return LAUNCH_OK();
+}
+extern "C" int evb_dropout_apply(const void* x, const void* keep, float scale, void* y, long long numel, void* stream) {
+  if (numel % 8 || numel < 0) return EVB_ERR_ARG;
+  if (numel == 0) return EVB_OK;
+  long long b = (numel / 8 + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  dropout_apply_kernel<<<(int)b, 256, 0, ST>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)keep, scale,
+                                               (__nv_bfloat16*)y, numel / 8);
   return LAUNCH_OK();
 }

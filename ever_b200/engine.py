@@ -77,12 +77,10 @@ class BNP:
     """BatchNorm parameters; cpad > C gives zero-padded shadow buffers (padded channels: gamma 1, beta 0 -> stay 0)."""
 
     def __init__(self, bn, cpad=None):
-        if isinstance(bn, torch.nn.SyncBatchNorm):
-            # train.sync_bn (ever/trainer/th_ddp_trainer.py:21-22) converts every BatchNorm2d: statistics over the GLOBAL batch
-            # need two collectives per layer, which this engine does not issue -- refuse instead of silently normalising with
-            # per-GPU statistics
-            raise NotImplementedError('SyncBatchNorm (train.sync_bn=True) is not supported by the B200 engine: BatchNorm '
-                                      'statistics are per GPU (the reference default); set sync_bn=False')
+        # train.sync_bn (ever/trainer/th_ddp_trainer.py:21-22) converts every BatchNorm2d into nn.SyncBatchNorm: batch
+        # statistics over the batch of ALL ranks -- one small all-reduce per layer forward and one backward (engine._bn_fold /
+        # _bn_backward), captured as NCCL nodes in the step graph
+        self.sync = isinstance(bn, torch.nn.SyncBatchNorm)
         self.bn = bn
         self.c_real = bn.num_features
         self.c = cpad or bn.num_features
@@ -593,7 +591,26 @@ class FarSegEngine:
         c = bp.c
         stats = self._new(4, c, dtype=torch.float32)
         mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
-        if train and bn.training and x.stats is not None:
+        sync = bp.sync and self.world > 1 and train and bn.training
+        if sync and x.stats is None:
+            raise NotImplementedError('SyncBatchNorm behind a convolution with a fused add (no epilogue statistics)')
+        if sync:
+            import torch.distributed as dist
+            m_rows = x.data.numel() // c
+            mom = 0.1 if bn.momentum is None else bn.momentum
+            partial, nblk = x.stats
+            sums = self._new(2, c, dtype=torch.float32)
+            check(L.evb_bn_partial_sums(ptr(partial), c_int(nblk), c_int(c), ptr(sums), stream()), 'evb_bn_partial_sums')
+            dist.all_reduce(sums)     # every rank contributes the same number of rows (equal per-GPU batches under DDP)
+            check(L.evb_bn_finalize_sums(ptr(sums), ctypes.c_double(float(m_rows) * self.world), c_int(c), ptr(bp.gamma),
+                                         ptr(bp.beta), ptr(bp.rm), ptr(bp.rv), c_float(mom), c_float(bn.eps), ptr(mean),
+                                         ptr(rstd), ptr(scale), ptr(shift), stream()), 'evb_bn_finalize_sums')
+            if bp.padded:
+                for src, dst in ((bp.rm_p, bn.running_mean), (bp.rv_p, bn.running_var)):
+                    check(L.evb_copy2d_f32(ptr(src), c_int(bp.c), ptr(dst), c_int(bp.c_real), c_int(1), c_int(bp.c_real),
+                                           c_int(0), stream()), 'evb_copy2d_f32')
+            self._bn_tracked.append(bn)
+        elif train and bn.training and x.stats is not None:
             m_rows = x.data.numel() // c
             mom = 0.1 if bn.momentum is None else bn.momentum
             partial, nblk = x.stats
@@ -635,15 +652,43 @@ class FarSegEngine:
         acc = self.accumulate or bp._gw
         dgam = bp.dgamma_p if bp.padded else self._g(bp.bn.weight)
         dbet = bp.dbeta_p if bp.padded else self._g(bp.bn.bias)
-        check(L.evb_bn_bwd(ptr(dy), ptr(x.data), ptr(ymask), ptr(mean), ptr(rstd), ptr(scale), ptr(shift),
-                           c_int(mask_mode), c_int(0 if bp.bn.training else 1), ptr(gx), ptr(dres), c_int(1 if dres_acc else 0),
-                           ptr(dgam), ptr(dbet), c_int(1 if (acc and not bp.padded) else 0),
-                           c_ll(m_rows), c_int(c), ptr(ws), stream()), 'evb_bn_bwd')
+        if bp.sync and self.world > 1 and bp.bn.training:
+            # SyncBatchNorm backward (torch/nn/modules/_functions.py SyncBatchNorm.backward): the parameter gradients are this
+            # rank's sums (DDP / the arena all-reduce average them like every other gradient); d(input) uses the sums of ALL
+            # ranks and the global row count
+            import torch.distributed as dist
+            fresh = self._new(2, c, dtype=torch.float32)
+            check(L.evb_norm_bwd_reduce(ptr(dy), ptr(x.data), ptr(ymask), ptr(mean), ptr(rstd), ptr(scale), ptr(shift),
+                                        c_int(mask_mode), ptr(fresh[0]), ptr(fresh[1]), c_int(0), c_ll(m_rows), c_int(c),
+                                        ptr(ws), stream()), 'evb_norm_bwd_reduce')
+            for src, dst in ((fresh[0], dgam), (fresh[1], dbet)):
+                if dst is not None:
+                    check(L.evb_copy2d_f32(ptr(src), c_int(c), ptr(dst), c_int(c), c_int(1), c_int(c),
+                                           c_int(1 if (acc and not bp.padded) else 0), stream()), 'evb_copy2d_f32')
+            glob = fresh.clone()
+            dist.all_reduce(glob)
+            k = self._new(2, c, dtype=torch.float32)
+            check(L.evb_bn_bwd_consts(ptr(scale), ptr(rstd), ptr(mean), ptr(glob[0]), ptr(glob[1]),
+                                      c_float(1.0 / (float(m_rows) * self.world)), c_int(c), ptr(k[0]), ptr(k[1]), stream()),
+                  'evb_bn_bwd_consts')
+            check(L.evb_norm_bwd_apply(ptr(dy), ptr(x.data), ptr(ymask), ptr(scale), ptr(shift), ptr(k[0]), ptr(k[1]),
+                                       c_int(mask_mode), ptr(gx), ptr(dres), c_int(1 if dres_acc else 0), c_ll(m_rows), c_int(c),
+                                       stream()), 'evb_norm_bwd_apply')
+        else:
+            self._bn_bwd_local(dy, x, ymask, fold, mask_mode, bp, gx, dres, dres_acc, dgam, dbet, acc, m_rows, c, ws)
         if bp.padded and self._g(bp.bn.weight) is not None:
             for src, dst in ((bp.dgamma_p, self._g(bp.bn.weight)), (bp.dbeta_p, self._g(bp.bn.bias))):
                 check(L.evb_copy2d_f32(ptr(src), c_int(bp.c), ptr(dst), c_int(bp.c_real), c_int(1), c_int(bp.c_real),
                                        c_int(1 if acc else 0), stream()), 'evb_copy2d_f32')
         bp._gw = True
+
+    def _bn_bwd_local(self, dy, x, ymask, fold, mask_mode, bp, gx, dres, dres_acc, dgam, dbet, acc, m_rows, c, ws):
+        L = self.L
+        mean, rstd, scale, shift = fold
+        check(L.evb_bn_bwd(ptr(dy), ptr(x.data), ptr(ymask), ptr(mean), ptr(rstd), ptr(scale), ptr(shift),
+                           c_int(mask_mode), c_int(0 if bp.bn.training else 1), ptr(gx), ptr(dres), c_int(1 if dres_acc else 0),
+                           ptr(dgam), ptr(dbet), c_int(1 if (acc and not bp.padded) else 0),
+                           c_ll(m_rows), c_int(c), ptr(ws), stream()), 'evb_bn_bwd')
 
     def bn_act(self, x, bp, relu=True, res=None, train=True, name=None):
         L = self.L
@@ -1106,7 +1151,10 @@ class FarSegEngine:
         check(L.evb_merge4(ptr(outs[0].data), ptr(outs[1].data), ptr(outs[2].data), ptr(outs[3].data), ptr(merged.data),
                            c_ll(merged.data.numel()), stream()), 'evb_merge4')
         d00 = self.dec_blocks[0][0][0]
-        self._tf_fwd(merged, d00.name.split('.blocks.')[0] + '.dropout' if d00.name else None)
+        dname = d00.name.split('.blocks.')[0] + '.dropout' if d00.name else None
+        drop_p = float(getattr(self.m.head.fpn_decoder, 'dropout_rate', -1))
+        drop_on = train and drop_p > 0 and self.m.head.fpn_decoder.dropout.training
+        self._tf_fwd(merged, None if drop_on else dname)
         if train:
             def bwd():
                 if merged.grad is None:
@@ -1119,6 +1167,29 @@ class FarSegEngine:
                     o.grad, o.has_grad = dq, True
             self.tape.append(bwd)
         self._dbg('merged', merged)
+        if drop_on:
+            # classifier dropout (fpn.py:175-176,190): the survivors are drawn by torch's own dropout kernel on a tensor of ones
+            # of the reference's shape / dtype (NCHW bf16), i.e. from the same Philox stream as the reference's call; the scale
+            # 1 / (1 - p) is applied in fp32 inside the kernel, as torch's fused dropout does
+            nb, hh_, ww_, cc_ = merged.data.shape
+            keep = torch.nn.functional.dropout(torch.ones(nb, cc_, hh_, ww_, dtype=BF16, device=self.dev), drop_p, True)
+            keep = keep.permute(0, 2, 3, 1).contiguous()
+            dropped = Act(self._new(nb, hh_, ww_, cc_))
+            sc = c_float(1.0 / (1.0 - drop_p))
+            check(L.evb_dropout_apply(ptr(merged.data), ptr(keep), sc, ptr(dropped.data), c_ll(merged.data.numel()), stream()),
+                  'evb_dropout_apply')
+            self._tf_fwd(dropped, dname)
+
+            def bwd_drop():
+                if dropped.grad is None:
+                    return
+                self._tf_bwd(dropped)
+                g, acc = self._grad_into(merged)
+                assert not acc
+                check(L.evb_dropout_apply(ptr(dropped.grad), ptr(keep), sc, ptr(g), c_ll(g.numel()), stream()),
+                      'evb_dropout_apply')
+            self.tape.append(bwd_drop)
+            return dropped
         return merged
 
     def _classify(self, feat, cp, f, train, name='logits'):

@@ -154,9 +154,7 @@ class _Decoder(nn.Module):
         ks = int(cc.get('kernel_size', 1))
         if ks not in (1, 3):
             raise NotImplementedError('classifier kernel_size 1 or 3 (got %d)' % ks)
-        if float(cc.get('dropout_rate', -1)) > 0:
-            raise NotImplementedError('classifier dropout_rate > 0 (nn.Dropout on the merged decoder features, '
-                                      'ever/module/fpn.py:175-176) is not built')
+        self.dropout_rate = float(cc.get('dropout_rate', -1))   # nn.Dropout on the merged features (fpn.py:175-176,190)
         self.num_upsample = []
         self.blocks = nn.ModuleList()
         for os_ in in_feat_output_strides:
@@ -166,6 +164,7 @@ class _Decoder(nn.Module):
             self.blocks.append(nn.Sequential(*[
                 nn.Sequential(nn.Conv2d(in_channels if j == 0 else out_channels, out_channels, 3, 1, 1, bias=False),
                               nn.BatchNorm2d(out_channels), nn.ReLU(True), nn.Identity()) for j in range(nl)]))
+        self.dropout = nn.Dropout(self.dropout_rate) if self.dropout_rate > 0 else nn.Identity()
         self.classifier = nn.Sequential(nn.Conv2d(out_channels, self.num_classes, ks, padding=(ks - 1) // 2), nn.Identity())
 
 
@@ -183,6 +182,11 @@ class _Head(nn.Module):
         self.fs_relation = rel_cls(int(fs.scene_embedding_channels), tuple(fs.in_channels_list), int(fs.out_channels),
                                    bool(fs.scale_aware_proj))
         d = cfg.fpn_decoder
+        # AssymetricDecoder(norm_fn=nn.BatchNorm2d, num_groups_gn=None) (fpn.py:145-170): only the BatchNorm + ReLU branch
+        nf = d.get('norm_fn', None) if hasattr(d, 'get') else None
+        if nf is not None and nf is not nn.BatchNorm2d:
+            raise NotImplementedError('fpn_decoder.norm_fn other than nn.BatchNorm2d (GroupNorm / None + GELU branch of '
+                                      'AssymetricDecoder, ever/module/fpn.py:166-167) is not built')
         self.fpn_decoder = _Decoder(int(d.in_channels), int(d.out_channels), tuple(d.in_feat_output_strides),
                                     int(d.out_feat_output_stride), d.classifier_config)
 
@@ -344,7 +348,7 @@ class FarSegB200(NativeStepMixin, ERModule):
         enc, r = self.config.encoder, self.en.resnet
         if not bool(enc.batchnorm_trainable):
             for m in r.modules():
-                if isinstance(m, nn.BatchNorm2d):
+                if isinstance(m, nn.modules.batchnorm._BatchNorm):
                     for p in m.parameters():
                         p.requires_grad = False
                     m.eval()

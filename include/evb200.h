@@ -87,6 +87,16 @@ int evb_bn_stats(const void* x, long long M, int C, const float* gamma, const fl
 int evb_bn_finalize(const float* partial, int nblk, long long M, int C, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, float momentum, float eps, float* mean, float* rstd,
                     float* scale, float* shift, void* stream);
+/* nn.SyncBatchNorm (train.sync_bn, ever/trainer/th_ddp_trainer.py:21-22): batch statistics over ALL ranks.  partial_sums: this
+ * rank's sums[2][C] (sum | sum of squares) from the conv epilogue's partial columns -- the caller all-reduces them --;
+ * finalize_sums: mean / rstd / scale / shift + running statistics from global sums over M_total rows; bwd_consts: the constants
+ * (c2, k0) of evb_norm_bwd_apply from the all-reduced backward sums (dgamma, dbeta of evb_norm_bwd_reduce), inv_m = 1/M_total */
+int evb_bn_partial_sums(const float* partial, int nblk, int C, float* sums, void* stream);
+int evb_bn_finalize_sums(const float* sums, double M_total, int C, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, float momentum, float eps, float* mean, float* rstd, float* scale, float* shift,
+                         void* stream);
+int evb_bn_bwd_consts(const float* scale, const float* rstd, const float* mean, const float* dgamma, const float* dbeta,
+                      float inv_m, int C, float* c2, float* k0, void* stream);
 /* eval / frozen BN: fold running statistics (ever/module/resnet.py:155-160,227-234) */
 int evb_bn_fold(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, int C, float* scale,
                 float* shift, float* mean, float* rstd, void* stream);
@@ -171,6 +181,9 @@ int evb_copy2d_bf16(const void* src, int lds, void* dst, int ldd, long long rows
 /* y[n,hw,c] = bf16(x[n,hw,c] * m[n,c]): nn.Dropout2d (fs_relation.py:101,118) forward and backward; m = the {0, 1/(1-p)}
  * channel mask the caller draws with torch's own generator (same Philox stream as the reference's feature_dropout) */
 int evb_channel_scale(const void* x, const float* m, void* y, int N, long long HW, int C, void* stream);
+/* y = keep != 0 ? bf16(x * scale) : 0 on bf16 tensors of numel elements: nn.Dropout (AssymetricDecoder's classifier
+ * dropout_rate, ever/module/fpn.py:175-176,190) forward and backward; keep = the survivors drawn with torch's generator */
+int evb_dropout_apply(const void* x, const void* keep, float scale, void* y, long long numel, void* stream);
 int evb_linear_fwd(const float* x, const float* W, const float* b, float* y, int N, int I, int O, int relu, void* stream);
 int evb_linear_bwd(const float* dy, const float* y, const float* x, const float* W, float* dW, float* db, float* dx, int N,
                    int I, int O, int relu, int acc_w, int acc_x, void* stream);

@@ -305,7 +305,7 @@ class DecoderOracle(nn.Module):
     """AssymetricDecoder, reference ever/module/fpn.py:144-193."""
 
     def __init__(self, in_channels, out_channels, in_feat_output_strides=(4, 8, 16, 32), out_feat_output_stride=4,
-                 num_classes=1, scale_factor=4.0, kernel_size=1):
+                 num_classes=1, scale_factor=4.0, kernel_size=1, dropout_rate=-1):
         super().__init__()
         self.blocks = nn.ModuleList()
         for os_ in in_feat_output_strides:
@@ -318,7 +318,7 @@ class DecoderOracle(nn.Module):
                     nn.ReLU(True),
                     _Fp32Around(nn.UpsamplingBilinear2d(scale_factor=2)) if nup != 0 else nn.Identity())
                 for j in range(nl)]))
-        self.dropout = nn.Identity()
+        self.dropout = nn.Dropout(dropout_rate) if dropout_rate > 0 else nn.Identity()   # fpn.py:175-176
         self.classifier = nn.Sequential(
             nn.Conv2d(out_channels, num_classes, kernel_size, padding=(kernel_size - 1) // 2),
             _Fp32Around(nn.UpsamplingBilinear2d(scale_factor=scale_factor)) if scale_factor > 1 else nn.Identity())
@@ -333,13 +333,13 @@ class FarSegHeadOracle(nn.Module):
     """FarSegHead.forward, reference ever/module/fs_relation.py:166-206."""
 
     def __init__(self, in_channels_list=(256, 512, 1024, 2048), fpn_channels=256, decoder_channels=256, num_classes=1,
-                 scale_aware_proj=True, classifier_kernel_size=1, fs_version=1):
+                 scale_aware_proj=True, classifier_kernel_size=1, fs_version=1, classifier_dropout=-1):
         super().__init__()
         self.fpn = FPNOracle(in_channels_list, fpn_channels)
         rel_cls = FSRelationV2Oracle if fs_version == 2 else FSRelationOracle
         self.fs_relation = rel_cls(in_channels_list[-1], (fpn_channels,) * 4, fpn_channels, scale_aware_proj)
         self.fpn_decoder = DecoderOracle(fpn_channels, decoder_channels, num_classes=num_classes,
-                                         kernel_size=classifier_kernel_size)
+                                         kernel_size=classifier_kernel_size, dropout_rate=classifier_dropout)
 
     def forward(self, feats):
         ps = self.fpn(feats)
@@ -386,11 +386,12 @@ class FarSegOracle(nn.Module):
     in training, softmax probabilities in eval."""
 
     def __init__(self, resnet_type='resnet50', num_classes=15, decoder_channels=256, in_channels=3, freeze_at=0,
-                 batchnorm_trainable=True, scale_aware_proj=True, classifier_kernel_size=1, fs_version=1):
+                 batchnorm_trainable=True, scale_aware_proj=True, classifier_kernel_size=1, fs_version=1,
+                 classifier_dropout=-1):
         super().__init__()
         self.en = ResNetEncoderOracle(resnet_type, in_channels, freeze_at, batchnorm_trainable)
         self.head = FarSegHeadOracle(self.en.out_channels, 256, decoder_channels, num_classes, scale_aware_proj,
-                                     classifier_kernel_size, fs_version)
+                                     classifier_kernel_size, fs_version, classifier_dropout)
         self.dice_all_reduce = None
 
     def logits(self, x):

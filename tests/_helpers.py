@@ -34,9 +34,9 @@ class RefCapture:
         import torch.nn as nn
         self.fwd, self.bwd, self.handles, self._calls = {}, {}, [], {}
         for name, mod in model.named_modules():
-            leafish = isinstance(mod, (nn.Conv2d, nn.ReLU, nn.MaxPool2d, nn.Identity, nn.Dropout2d)) or \
+            leafish = isinstance(mod, (nn.Conv2d, nn.ReLU, nn.MaxPool2d, nn.Identity, nn.Dropout2d, nn.Dropout)) or \
                 type(mod).__name__ in ('_Fp32Around', 'Bf16compatible', 'SEBlock', 'SEBlockOracle') or \
-                (isinstance(mod, nn.BatchNorm2d) and '.downsample.' in name)
+                (isinstance(mod, nn.modules.batchnorm._BatchNorm) and '.downsample.' in name)
             if not leafish:
                 continue
             self.handles.append(mod.register_forward_hook(self._out_hook(name)))

@@ -37,7 +37,8 @@ def _build(resnet, k, dec, **opts):
                            head=dict(fs_relation=dict(scale_aware_proj=opts.get('scale_aware_proj', True),
                                                       version=opts.get('fs_version', 1)),
                                      fpn_decoder=dict(out_channels=dec, classifier_config=dict(
-                                         num_classes=k, kernel_size=opts.get('classifier_kernel_size', 1))))))
+                                         num_classes=k, kernel_size=opts.get('classifier_kernel_size', 1),
+                                         dropout_rate=opts.get('classifier_dropout', -1))))))
     mine.load_state_dict(ora.state_dict(), strict=True)
     return ora.cuda().train(), mine.cuda().train()
 
@@ -114,11 +115,13 @@ CASES = [
     # draw their channel masks from the same torch seed, so the same channels are dropped)
     ('resnet18', 5, 128, 2, 128, 128, dict(fs_version=2)),
     ('resnet50', 7, 256, 2, 256, 256, dict(fs_version=2)),
+    # nn.Dropout on the merged decoder features (classifier_config.dropout_rate, ever/module/fpn.py:175-176,190), same seed
+    ('resnet18', 5, 128, 2, 128, 128, dict(classifier_dropout=0.3)),
 ]
 DROP_SEED = 4242
 
 
-@pytest.mark.parametrize('case', CASES, ids=lambda c: '%s_k%d_%dx%d%s' % (c[0], c[1], c[3], c[4], '_v2' if c[6].get('fs_version') == 2 else '') if isinstance(c, tuple) else None)
+@pytest.mark.parametrize('case', CASES, ids=lambda c: '%s_k%d_%dx%d%s' % (c[0], c[1], c[3], c[4], '_v2' if c[6].get('fs_version') == 2 else '_drop' if c[6].get('classifier_dropout') else '') if isinstance(c, tuple) else None)
 def test_teacher_forced_step(case):
     from oracle.farseg_oracle import synthetic_batch
     resnet, k, dec, n, h, w, opts = case

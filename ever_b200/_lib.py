@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libevb200.so')
+LIB_PATH = os.environ.get('EVB_LIB') or os.path.join(_HERE, 'lib', 'libevb200.so')   # EVB_LIB: A/B builds (tools/)
 _lib = None
 
 

@@ -113,6 +113,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start (run its
 // prologue) while its predecessor drains; it must execute pdl_wait() before touching any global memory.
+// (an early griddepcontrol.launch_dependents right behind the wait was measured: the successor's parked CTAs take slots
+// from the running grid, 8.97 -> 9.20 ms/step; the implicit trigger at grid exit stays)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

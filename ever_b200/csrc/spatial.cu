@@ -94,6 +94,30 @@ static inline int sp_blocks(long long work) {
   return b < 1 ? 1 : (int)b;
 }
 
+// dst[p][y][x] (+)= bilinear(src[p]) with align_corners = true, fp32 planes (the TTA `Scale` transform and its inverse,
+// ever/magic/transform/segm.py:71-88 = F.interpolate(mode='bilinear', align_corners=True)).  Same fp32 operation order as
+// torch's upsample_bilinear2d: source coordinate = (in - 1) / (out - 1) * index, weights (1 - l, l), rows combined last.
+__global__ void __launch_bounds__(256)
+resize_bilinear_ac_kernel(const float* __restrict__ src, int h, int w, float* __restrict__ dst, int ho, int wo,
+                          long long total, float rh, float rw, int accumulate) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(t % wo);
+    long long q = t / wo;
+    const int y = (int)(q % ho);
+    const long long p = q / ho;
+    const float fy = rh * y, fx = rw * x;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int yp = y0 < h - 1 ? 1 : 0, xp = x0 < w - 1 ? 1 : 0;
+    const float ly1 = fy - y0, ly0 = 1.f - ly1, lx1 = fx - x0, lx0 = 1.f - lx1;
+    const float* s0 = src + (p * h + y0) * w + x0;
+    const float* s1 = s0 + (long long)yp * w;
+    const float top = __fadd_rn(__fmul_rn(lx0, s0[0]), __fmul_rn(lx1, s0[xp]));
+    const float bot = __fadd_rn(__fmul_rn(lx0, s1[0]), __fmul_rn(lx1, s1[xp]));
+    const float v = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+    dst[t] = accumulate ? dst[t] + v : v;
+  }
+}
+
 }  // namespace evb
 
 using namespace evb;
@@ -144,5 +168,16 @@ extern "C" int evb_canvas_finalize(const float* canvas, const float* count, floa
   if (P == 0) return EVB_OK;
   canvas_finalize_kernel<<<sp_blocks(B * P), 256, 0, (cudaStream_t)stream>>>(canvas, count, uniform_count, K, P, B * P, prob,
                                                                            (uint8_t*)mask);
+  return cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
+}
+
+// dst[P,ho,wo] (+)= bilinear resize (align_corners = true) of src[P,h,w], fp32 planes
+extern "C" int evb_resize_bilinear_ac(const float* src, long long P, int h, int w, float* dst, int ho, int wo, int accumulate,
+                                      void* stream) {
+  if (P < 0 || h < 1 || w < 1 || ho < 1 || wo < 1) return EVB_ERR_ARG;
+  const long long total = P * ho * wo;
+  if (total == 0) return EVB_OK;
+  const float rh = ho > 1 ? (float)(h - 1) / (float)(ho - 1) : 0.f, rw = wo > 1 ? (float)(w - 1) / (float)(wo - 1) : 0.f;
+  resize_bilinear_ac_kernel<<<sp_blocks(total), 256, 0, (cudaStream_t)stream>>>(src, h, w, dst, ho, wo, total, rh, rw, accumulate);
   return cudaGetLastError() == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
 }

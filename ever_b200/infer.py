@@ -5,7 +5,7 @@ Reference pieces mirrored:
   * ``sliding_window(input_size, kernel_size, stride)``  ever/magic/bigimage/sliding_window.py:8-33 -- same boxes, same
     order, including its duplicated border boxes (the meshgrid runs one step past the last row / column);
   * ``tta(model, image, tta_config)`` / ``TestTimeAugmentation``  ever/magic/transform/tta.py:11-42 with the transforms of
-    ever/magic/transform/segm.py:9-72 (Identity, Rotate90k, HorizontalFlip, VerticalFlip, Transpose): transformed copies
+    ever/magic/transform/segm.py:9-88 (Identity, Rotate90k, HorizontalFlip, VerticalFlip, Transpose, Scale): transformed copies
     -> model -> inverse transform -> ``sum(outs) / len(outs)`` (summed in transform order, then one true division --
     the same fp32 operation order as the reference, so equal per-transform outputs give bit-equal means).
 The reference does the crops / flips / accumulation with host-side torch ops, one image at a time.
@@ -72,6 +72,35 @@ class Transpose:
         return PixelMap(h, w).transpose()
 
 
+class Scale:
+    """bilinear resize with align_corners=True and back (segm.py:71-88); not an index map: runs ``evb_resize_bilinear_ac``"""
+
+    def __init__(self, size=None, scale_factor=None):
+        if (size is None) == (scale_factor is None):
+            raise ValueError('only one of size or scale_factor should be defined')   # F.interpolate's own rule
+        self.size, self.scale_factor = size, scale_factor
+
+
+def _scaled_size(t, h, w):
+    """output size of F.interpolate(size=..., scale_factor=...): floor(in * factor) computed in double"""
+    if t.size is not None:
+        return (t.size, t.size) if isinstance(t.size, int) else tuple(t.size)
+    f = t.scale_factor
+    fh, fw = (f, f) if isinstance(f, (int, float)) else f
+    return int(math.floor(float(h) * fh)), int(math.floor(float(w) * fw))
+
+
+def resize_bilinear(x, size, out=None, accumulate=False):
+    """F.interpolate(x, size, mode='bilinear', align_corners=True) for fp32 NCHW on the GPU; ``out`` (+)= the result"""
+    n, c, h, w = x.shape
+    x = x.float().contiguous()
+    if out is None:
+        out = torch.empty((n, c, size[0], size[1]), dtype=torch.float32, device=x.device)
+    check(lib().evb_resize_bilinear_ac(ptr(x), c_ll(n * c), c_int(h), c_int(w), ptr(out), c_int(size[0]), c_int(size[1]),
+                                       c_int(1 if accumulate else 0), stream()), 'evb_resize_bilinear_ac')
+    return out
+
+
 def _as_map(t, h, w):
     """accepts the classes above or the reference's own transform objects (matched by class name)"""
     if hasattr(t, 'map'):
@@ -131,12 +160,21 @@ def tta(model, image, tta_config, return_mask=False):
     h, w = (image.shape[1], image.shape[2]) if u8 else (image.shape[2], image.shape[3])
     canvas = None
     for t in tta_config:
-        m = _as_map(t, h, w)
-        prob = model(_transformed_batch(image, [m] * n))
+        scale = type(t).__name__ == 'Scale'
+        if scale:
+            if u8:
+                raise NotImplementedError('Scale interpolates: it needs the float NCHW image, not uint8 pixels')
+            prob = model(resize_bilinear(image, _scaled_size(t, h, w)))
+        else:
+            m = _as_map(t, h, w)
+            prob = model(_transformed_batch(image, [m] * n))
         if isinstance(prob, dict):
             raise NotImplementedError('tta() handles single-output models')
         if canvas is None:
             canvas = torch.zeros((n, prob.shape[1], h, w), dtype=torch.float32, device=image.device)
+        if scale:
+            resize_bilinear(prob, (h, w), out=canvas, accumulate=True)
+            continue
         inv = m.inverse().shifted(0, 0)   # canvas rows clip in canvas coordinates: the whole image
         _canvas_accumulate(prob.contiguous(), [inv.row(i, i) for i in range(n)], canvas, None, (0, h, 0, w))
     return _finalize_out(_canvas_finalize(canvas, None, float(len(tta_config)), return_mask), return_mask)

@@ -232,6 +232,11 @@ int evb_canvas_accumulate(const float* prob, int N, int K, int h, int w, const v
 int evb_canvas_finalize(const float* canvas, const float* count, float uniform_count, int B, int K, long long P,
                         float* prob, void* mask, void* stream);
 
+/* dst[P,ho,wo] (+)= bilinear resize with align_corners = true of the fp32 planes src[P,h,w]: the TTA `Scale` transform and
+ * its inverse (ever/magic/transform/segm.py:71-88, F.interpolate(mode='bilinear', align_corners=True)). */
+int evb_resize_bilinear_ac(const float* src, long long P, int h, int w, float* dst, int ho, int wo, int accumulate,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,9 +72,28 @@ TTA_OPS = {
 }
 
 
+def scale_ops(size=None, scale_factor=None):
+    """Scale, ever/magic/transform/segm.py:71-88: bilinear (align_corners=True) to size / by scale_factor, and back to the
+    recorded input shape"""
+    seen = {}
+
+    def fwd(x):
+        seen['hw'] = (x.shape[2], x.shape[3])
+        return F.interpolate(x, size=size, scale_factor=scale_factor, mode='bilinear', align_corners=True)
+
+    def inv(y):
+        return F.interpolate(y, size=seen['hw'], mode='bilinear', align_corners=True)
+    return fwd, inv
+
+
+def _tta_ops(name):
+    return scale_ops(**name[1]) if isinstance(name, tuple) else TTA_OPS[name]
+
+
 def tta_oracle(model, image, names):
     """tta.py:11-23: outs = [model(t(image))]; outs = inverse transforms; sum(outs) / len(outs).
     The final division is evaluated on the host: it is an IEEE fp32 division there, while torch's CUDA kernel for
     tensor / python-scalar multiplies by the rounded reciprocal (1 ulp off for some elements); the product kernel divides."""
-    outs = [TTA_OPS[n][1](model(TTA_OPS[n][0](image).contiguous())) for n in names]
+    ops = [_tta_ops(n) for n in names]   # names: keys of TTA_OPS, or ('Scale', dict(size=... | scale_factor=...))
+    outs = [inv(model(fwd(image).contiguous())) for fwd, inv in ops]
     return (sum(outs).cpu() / len(outs)).to(outs[0].device)

@@ -256,3 +256,54 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_device():
     # tuning switches validate their ranges
     assert L.evb_set_bn_reduce_blocks(c_int(9)) == ERR_ARG
     assert L.evb_version() >= 101
+
+
+def test_scale_transform_output_size_matches_interpolate():
+    """Scale (ever/magic/transform/segm.py:71-88): the size our TTA path resizes to == the shape F.interpolate produces, for
+    the factors the reference's own unit test sweeps (segm.py:100-105)"""
+    import numpy as np
+    import torch.nn.functional as F
+    from ever_b200.infer import Scale, _scaled_size
+    x = torch.zeros(1, 1, 90, 130)
+    factors = [float(f) for f in np.linspace(0.25, 2.0, num=8)] + [0.49, 1.3, (0.5, 1.5)]
+    for f in factors:
+        want = F.interpolate(x, scale_factor=f, mode='bilinear', align_corners=True).shape[2:]
+        assert _scaled_size(Scale(scale_factor=f), 90, 130) == tuple(want), f
+    assert _scaled_size(Scale(size=(894, 896)), 90, 130) == (894, 896)
+    assert _scaled_size(Scale(size=64), 90, 130) == (64, 64)
+    with pytest.raises(ValueError):
+        Scale()
+    with pytest.raises(ValueError):
+        Scale(size=4, scale_factor=2.0)
+
+
+@pytest.mark.parametrize('splits', [(3, 2, 1), (3,), ()])
+def test_gradient_buckets_tile_the_arena_in_backward_order(splits):
+    """the per-stage gradient buckets of the multi-GPU step: contiguous arena tails starting at the first
+    parameter of an encoder stage, listed in the order backward completes them, covering every gradient exactly once;
+    _allreduce_bucket maps a finished tape segment to its bucket (host logic only: the engine object is a shell here)"""
+    from ever_b200.engine import FarSegEngine, _ceil
+    from ever_b200.module import FarSegB200
+    m = FarSegB200(dict(encoder=dict(resnet_type='resnet18'),
+                        head=dict(fpn_decoder=dict(out_channels=128, classifier_config=dict(num_classes=5)))))
+    e = FarSegEngine.__new__(FarSegEngine)
+    e.m, e.ar_split_stages, e._buckets, e.side = m, splits, None, None
+    off, e._slots = 0, []
+    for p in m.parameters():
+        e._slots.append((off, p.numel()))
+        off += _ceil(p.numel(), 4)
+    e.flat_g = torch.zeros(off)
+    b = e._bucket_ranges()
+    assert len(b) == len(splits) + 1 and b[0][1] == off and b[-1][0] == 0
+    assert all(b[i][0] == b[i + 1][1] for i in range(len(b) - 1))          # adjacent, descending: backward order
+    names = [n for n, _ in m.named_parameters()]
+    starts = {e._slots[names.index('en.resnet.layer%d.0.conv1.weight' % (s + 1))][0] for s in splits}
+    assert {lo for lo, _ in b[:-1]} == starts
+    # a finished tape segment -> its bucket: tape split points are recorded in forward order (stage 1 first)
+    e.tape = list(range(100))
+    e._tape_splits = [10 * (i + 1) for i in range(len(splits))]
+    issued = []
+    e._issue_allreduce = lambda lo, hi: issued.append((lo, hi))
+    for lo, _ in e._segments():
+        e._allreduce_bucket(lo)
+    assert issued == b

@@ -110,6 +110,45 @@ def test_tta_equals_reference_formula(u8):
     assert torch.equal(mask.long(), want.argmax(dim=1))
 
 
+@pytest.mark.parametrize('shape,size', [((3, 5, 96, 128), (48, 64)), ((2, 3, 64, 64), (128, 160)), ((1, 4, 37, 53), (61, 20)),
+                                        ((2, 2, 32, 32), (32, 32)), ((1, 1, 9, 7), (1, 1))])
+def test_resize_bilinear_equals_interpolate(shape, size):
+    """evb_resize_bilinear_ac == F.interpolate(mode='bilinear', align_corners=True) (the Scale transform, segm.py:71-88):
+    same source coordinates and weights; torch's kernel may contract its products into FMAs, hence 1e-6 rather than equal"""
+    from ever_b200.infer import resize_bilinear
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(*shape, generator=g).cuda()
+    want = F.interpolate(x, size=size, mode='bilinear', align_corners=True)
+    got = resize_bilinear(x, size)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= 1e-6 * max(1.0, want.abs().max().item())
+    base = torch.rand_like(want)
+    acc = resize_bilinear(x, size, out=base.clone(), accumulate=True)
+    assert torch.equal(acc, base + got)
+
+
+def test_tta_with_scale():
+    """Scale in a TTA config: resize -> model -> resize back, summed with the index-map transforms in config order
+    (tta.py:11-23).  The bf16 engine amplifies a last-bit difference of its input, so the expected value feeds the model the
+    product's resized image (checked against F.interpolate to 1e-6 above) and uses torch for everything else: inverse
+    resize, flips, the sum and the division."""
+    from ever_b200.infer import HorizontalFlip, Identity, Scale, resize_bilinear, tta
+    model = _model()
+    g = torch.Generator().manual_seed(16)
+    x = torch.randn(2, 3, 128, 128, generator=g).cuda()
+    cfg = [Identity(), Scale(scale_factor=0.5), HorizontalFlip(), Scale(size=(160, 192)), Scale(scale_factor=1.25)]
+    got = tta(model, x, cfg)
+    back = lambda p: F.interpolate(p, size=(128, 128), mode='bilinear', align_corners=True)
+    outs = [model(x), back(model(resize_bilinear(x, (64, 64)))), torch.flip(model(torch.flip(x, [3]).contiguous()), [3]),
+            back(model(resize_bilinear(x, (160, 192)))), back(model(resize_bilinear(x, (160, 160))))]
+    want = (sum(outs).cpu() / len(outs)).cuda()
+    torch.cuda.synchronize()
+    assert (got - want).abs().max().item() <= 2e-6
+    with pytest.raises(NotImplementedError):
+        tta(model, torch.zeros(1, 64, 64, 3, dtype=torch.uint8, device='cuda'), [Scale(scale_factor=0.5)])
+
+
 @pytest.mark.parametrize('hw,tile,stride,batch,u8', [((300, 416), 256, 128, 4, True), ((200, 700), 256, 192, 3, False)])
 def test_sliding_window_predictor_equals_host_accumulation(hw, tile, stride, batch, u8):
     """the GPU canvas path == the host loop a user of the reference's sliding_window writes

@@ -36,6 +36,9 @@ CONFIGS = {
     'c2s': dict(model='FarSeg', resnet='resnet50', k=15, dec=256, hw=(512, 512), total=8, scaling='strong', cin=3,
                 workload='FarSeg-R50 15-class, 8x3x512x512 synthetic tiles in TOTAL split over the GPUs (strong scaling of '
                          'BASELINE configs[1]: 1 tile per GPU at 8 GPUs)', gflop_per_tile=343.1),
+    'c2x': dict(model='FarSeg', resnet='resnext50_32x4d', k=15, dec=256, hw=(512, 512), per_gpu=8, scaling='weak', cin=3,
+                workload='FarSeg-ResNeXt50-32x4d 15-class, 8x3x512x512 synthetic tiles per GPU (configs[1] with the grouped-conv '
+                         'backbone of ever/module/_resnets.py:291-300)', gflop_per_tile=None),
     'c3': dict(model='ChangeStar', resnet='resnet50', k=1, dec=256, hw=(512, 512), total=8, scaling='strong', cin=3,
                workload='ChangeStar (FarSeg-R50 + ChangeMixin), 8 bitemporal pairs of 3x512x512 sharded by batch over the '
                         'GPUs (BASELINE configs[2]); a pair counts as 2 tiles', gflop_per_tile=None),

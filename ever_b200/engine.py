@@ -47,18 +47,24 @@ class ConvP:
     the weight gradient goes through a dense scratch [cop][cip*k*k] and only the valid block is copied out, and the
     bias lives in a padded fp32 buffer."""
 
-    def __init__(self, weight, bias=None, stride=1, co=None, ci=None, k=None, cout_pad=None, cin_pad=None, w_off=0, w_ld=0):
+    def __init__(self, weight, bias=None, stride=1, co=None, ci=None, k=None, cout_pad=None, cin_pad=None, w_off=0, w_ld=0,
+                 groups=1):
         self.weight, self.bias = weight, bias
         wco, wci, kh, kw = weight.shape
         self.stride = stride
+        # grouped conv (ResNeXt conv2, _resnets.py:84): runs as a dense conv over a block-diagonal fp32 image of the weight
+        # (dense_w, refreshed before every pack); the dense weight gradient lands in gscr and its diagonal blocks are read
+        # back (csrc/grouped.cu)
+        self.groups = groups
+        self.dense_w = None
         self.co = wco if co is None else co
-        self.ci = wci if ci is None else ci
+        self.ci = wci * groups if ci is None else ci
         self.k = kh if k is None else k
         self.kk = self.k * self.k
         self.cop = cout_pad or _ceil(self.co, 64)   # rows of the forward pack / channels of dy
         self.cip = cin_pad or _ceil(self.ci, 64)
         self.w_off, self.w_ld = w_off, w_ld
-        self.direct_grad = (self.cop == self.co and self.cip == self.ci and w_off == 0 and w_ld == 0)
+        self.direct_grad = (self.cop == self.co and self.cip == self.ci and w_off == 0 and w_ld == 0 and groups == 1)
         self.wf = self.wb = None
         self.need_dgrad = True
         self.gscr = self.bias_pad = self.dbias_scr = None
@@ -70,7 +76,7 @@ class ConvP:
         if as_matrix:  # 7x7 stem lowered to a GEMM over im2col rows: [Co][Ci*49]
             co, ci, kh, kw = conv.weight.shape
             return ConvP(conv.weight, conv.bias, 1, co=co, ci=ci * kh * kw, k=1, cout_pad=cout_pad)
-        return ConvP(conv.weight, conv.bias, conv.stride[0], cout_pad=cout_pad)
+        return ConvP(conv.weight, conv.bias, conv.stride[0], cout_pad=cout_pad, groups=conv.groups)
 
 
 class BNP:
@@ -346,6 +352,10 @@ class FarSegEngine:
         for cp in self.convs:
             if not cp.direct_grad:
                 cp.gscr = torch.zeros(cp.cop * cp.cip * cp.kk, dtype=torch.float32, device=self.dev)
+            if cp.groups > 1:
+                if cp.cop != cp.co or cp.cip != cp.ci or cp.w_ld:
+                    raise NotImplementedError('grouped convolution with padded channels')
+                cp.dense_w = torch.zeros(cp.co * cp.ci * cp.kk, dtype=torch.float32, device=self.dev)
             if cp.bias is not None and cp.cop != cp.co:
                 cp.bias_pad = torch.zeros(cp.cop, dtype=torch.float32, device=self.dev)
                 cp.dbias_scr = torch.zeros(cp.cop, dtype=torch.float32, device=self.dev)
@@ -355,7 +365,8 @@ class FarSegEngine:
         for i, cp in enumerate(self.convs):
             kk = cp.k * cp.k
             nb = ((cp.co + 63) // 64) * ((cp.ci + 63) // 64)   # one block per 64x64 (co, ci) tile, all taps
-            rows.append([cp.weight.data_ptr() + 4 * cp.w_off, cp.wf.data_ptr(), cp.wb.data_ptr() if cp.need_dgrad else 0,
+            src = cp.dense_w.data_ptr() if cp.groups > 1 else cp.weight.data_ptr() + 4 * cp.w_off
+            rows.append([src, cp.wf.data_ptr(), cp.wb.data_ptr() if cp.need_dgrad else 0,
                          cp.co, cp.ci, kk, cp.cop, cp.cip, cp.cip, cp.cop, nblk, cp.w_ld])
             bmap += [i] * nb
             nblk += nb
@@ -378,6 +389,10 @@ class FarSegEngine:
         if getattr(self, '_pack_desc', None) is None or self._pack_ptrs != [cp.weight.data_ptr() for cp in self.convs]:
             self._build_pack_table()
         self._pack_ev = None
+        for cp in self.convs:
+            if cp.groups > 1:
+                check(self.L.evb_group_expand(ptr(cp.weight), ptr(cp.dense_w), c_int(cp.co), c_int(cp.ci), c_int(cp.kk),
+                                              c_int(cp.groups), st), 'evb_group_expand')
         if self._pack_split < self._pack_nblk:
             main = torch.cuda.current_stream()
             ev = torch.cuda.Event()
@@ -497,7 +512,10 @@ class FarSegEngine:
         check(L.evb_conv2d_wgrad(ptr(x_data), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(dy), c_int(cout), c_int(cp.k),
                                  c_int(stride), ptr(target), c_int(1 if (acc and cp.direct_grad) else 0), ptr(ws),
                                  c_ll(self._ws_cap()), c_int(0), c_int(0), st), 'evb_conv2d_wgrad')
-        if not cp.direct_grad:   # copy the valid [co][ci*kk] block of the dense scratch [cop][cip*kk] into the OIHW grad
+        if cp.groups > 1:        # the diagonal blocks of the dense gradient are the grouped conv's [co][ci/g][k][k]
+            check(L.evb_group_extract(ptr(cp.gscr), ptr(self._g(cp.weight)), c_int(cp.co), c_int(cp.ci), c_int(cp.kk),
+                                      c_int(cp.groups), c_int(1 if acc else 0), st), 'evb_group_extract')
+        elif not cp.direct_grad:   # copy the valid [co][ci*kk] block of the dense scratch [cop][cip*kk] into the OIHW grad
             dst = ctypes.c_void_p(self._g(cp.weight).data_ptr() + 4 * cp.w_off)
             check(L.evb_copy2d_f32(ptr(cp.gscr), c_int(cp.cip * cp.kk), dst, c_int(cp.w_ld or cp.ci * cp.kk), c_int(cp.co),
                                    c_int(cp.ci * cp.kk), c_int(1 if acc else 0), st), 'evb_copy2d_f32')

@@ -22,26 +22,32 @@ RESNETS = {  # block kind, blocks per stage  (ever/module/_resnets.py:241-278)
     # deep-stem variants: three 3x3 convs instead of the 7x7 (_resnets.py:137-147, 327-345)
     'resnet50_v1c': ('bottleneck', (3, 4, 6, 3)),
     'resnet101_v1c': ('bottleneck', (3, 4, 23, 3)),
+    # ResNeXt: grouped 3x3 in the bottleneck (_resnets.py:80-84, 291-324)
+    'resnext50_32x4d': ('bottleneck', (3, 4, 6, 3)),
+    'resnext101_32x4d': ('bottleneck', (3, 4, 23, 3)),
+    'resnext101_32x8d': ('bottleneck', (3, 4, 23, 3)),
 }
+RESNEXT = {'resnext50_32x4d': (32, 4), 'resnext101_32x4d': (32, 4), 'resnext101_32x8d': (32, 8)}   # groups, width_per_group
 
 
 class _Block(nn.Module):
     """Parameter container with the attribute names of BasicBlock / Bottleneck (_resnets.py:32-112)."""
 
-    def __init__(self, kind, cin, planes, stride, down):
+    def __init__(self, kind, cin, planes, stride, down, groups=1, base_width=64):
         super().__init__()
         self.kind, self.stride = kind, stride
+        width = int(planes * (base_width / 64.)) * groups   # _resnets.py:80
         if kind == 'basic':
             self.conv1 = nn.Conv2d(cin, planes, 3, stride, 1, bias=False)
             self.bn1 = nn.BatchNorm2d(planes)
             self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
             self.bn2 = nn.BatchNorm2d(planes)
         else:
-            self.conv1 = nn.Conv2d(cin, planes, 1, bias=False)
-            self.bn1 = nn.BatchNorm2d(planes)
-            self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
-            self.bn2 = nn.BatchNorm2d(planes)
-            self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+            self.conv1 = nn.Conv2d(cin, width, 1, bias=False)
+            self.bn1 = nn.BatchNorm2d(width)
+            self.conv2 = nn.Conv2d(width, width, 3, stride, 1, groups=groups, bias=False)
+            self.bn2 = nn.BatchNorm2d(width)
+            self.conv3 = nn.Conv2d(width, planes * 4, 1, bias=False)
             self.bn3 = nn.BatchNorm2d(planes * 4)
         self.downsample = down
 
@@ -50,6 +56,7 @@ class _ResNetParams(nn.Module):
     def __init__(self, resnet_type, in_channels=3):
         super().__init__()
         kind, counts = RESNETS[resnet_type]
+        groups, base_width = RESNEXT.get(resnet_type, (1, 64))
         exp = 1 if kind == 'basic' else 4
         self.kind = kind
         self.deep_stem = resnet_type.endswith('_v1c')
@@ -68,7 +75,7 @@ class _ResNetParams(nn.Module):
                 down = None
                 if b == 0 and (s != 1 or cin != planes * exp):
                     down = nn.Sequential(nn.Conv2d(cin, planes * exp, 1, s, bias=False), nn.BatchNorm2d(planes * exp))
-                blocks.append(_Block(kind, cin, planes, s, down))
+                blocks.append(_Block(kind, cin, planes, s, down, groups, base_width))
                 cin = planes * exp
             setattr(self, 'layer%d' % li, nn.Sequential(*blocks))
         self.out_channels = tuple(c * exp for c in (64, 128, 256, 512))
@@ -319,6 +326,9 @@ class FarSegB200(NativeStepMixin, ERModule):
         'resnet101': 'https://download.pytorch.org/models/resnet101-5d3b4d8f.pth',
         'resnet50_v1c': 'https://download.openmmlab.com/pretrain/third_party/resnet50_v1c-2cccc1ad.pth',
         'resnet101_v1c': 'https://download.openmmlab.com/pretrain/third_party/resnet101_v1c-e67eebb6.pth',
+        'resnext50_32x4d': 'https://download.pytorch.org/models/resnext50_32x4d-7cdf4587.pth',
+        'resnext101_32x8d': 'https://download.pytorch.org/models/resnext101_32x8d-8ba56ff5.pth',
+        'resnext101_32x4d': 'https://s3.ap-northeast-2.amazonaws.com/open-mmlab/pretrain/third_party/resnext101_32x4d-a5af3160.pth',
     }
 
     def _load_pretrained(self, resnet_type, in_channels, state_dict=None):

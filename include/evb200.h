@@ -237,6 +237,13 @@ int evb_canvas_finalize(const float* canvas, const float* count, float uniform_c
 int evb_resize_bilinear_ac(const float* src, long long P, int h, int w, float* dst, int ho, int wo, int accumulate,
                            void* stream);
 
+/* ---- grouped convolution (ResNeXt bottleneck conv2, ever/module/_resnets.py:21-24,80-84,291-324) on the dense kernels.
+ * evb_group_expand: dense[Co][Ci][kk] fp32 <- the block-diagonal image of w[Co][Ci/groups][kk] (only the diagonal blocks are
+ * written: the caller zero-fills `dense` once).  evb_group_extract: gw[Co][Ci/groups][kk] (+)= the diagonal blocks of the
+ * dense weight gradient evb_conv2d_wgrad produced. */
+int evb_group_expand(const float* w, float* dense, int Co, int Ci, int kk, int groups, void* stream);
+int evb_group_extract(const float* dense, float* gw, int Co, int Ci, int kk, int groups, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

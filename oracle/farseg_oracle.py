@@ -54,13 +54,14 @@ class _Bottle(nn.Module):
     """Bottleneck (stride on the 3x3), reference ever/module/_resnets.py:72-112."""
     expansion = 4
 
-    def __init__(self, cin, planes, stride, down):
+    def __init__(self, cin, planes, stride, down, groups=1, base_width=64):
         super().__init__()
-        self.conv1 = nn.Conv2d(cin, planes, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
-        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
-        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        width = int(planes * (base_width / 64.)) * groups   # ResNeXt: _resnets.py:80-84
+        self.conv1 = nn.Conv2d(cin, width, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(width)
+        self.conv2 = nn.Conv2d(width, width, 3, stride, 1, groups=groups, bias=False)
+        self.bn2 = nn.BatchNorm2d(width)
+        self.conv3 = nn.Conv2d(width, planes * 4, 1, bias=False)
         self.bn3 = nn.BatchNorm2d(planes * 4)
         self.relu = nn.ReLU(inplace=True)
         self.downsample = down
@@ -83,7 +84,11 @@ RESNET_SPECS = {
     'resnet101': (_Bottle, (3, 4, 23, 3)),
     'resnet50_v1c': (_Bottle, (3, 4, 6, 3)),    # deep stem, reference ever/module/_resnets.py:327-345
     'resnet101_v1c': (_Bottle, (3, 4, 23, 3)),
+    'resnext50_32x4d': (_Bottle, (3, 4, 6, 3)),   # reference ever/module/_resnets.py:291-324
+    'resnext101_32x4d': (_Bottle, (3, 4, 23, 3)),
+    'resnext101_32x8d': (_Bottle, (3, 4, 23, 3)),
 }
+RESNEXT_SPECS = {'resnext50_32x4d': (32, 4), 'resnext101_32x4d': (32, 4), 'resnext101_32x8d': (32, 8)}   # groups, width_per_group
 
 
 class _ResNetTrunk(nn.Module):
@@ -114,7 +119,8 @@ class _ResNetTrunk(nn.Module):
                 if b == 0 and (s != 1 or cin != planes * block.expansion):
                     down = nn.Sequential(nn.Conv2d(cin, planes * block.expansion, 1, s, bias=False),
                                          nn.BatchNorm2d(planes * block.expansion))
-                blocks.append(block(cin, planes, s, down))
+                blocks.append(block(cin, planes, s, down, *RESNEXT_SPECS[kind]) if kind in RESNEXT_SPECS
+                              else block(cin, planes, s, down))
                 cin = planes * block.expansion
             setattr(self, 'layer%d' % li, nn.Sequential(*blocks))
         self.avgpool = nn.AdaptiveAvgPool2d((1, 1))  # parameter-free, kept for module parity

@@ -33,6 +33,8 @@ CASES = {
     'r18_k5_c8_shared_2x64': ('resnet18', 5, 2, 64, 64, 128, dict(in_channels=8, scale_aware_proj=False)),
     # FSRelationV2 (fs_relation.py:76-163) swapped into the head; Dropout2d draws from torch.manual_seed(DROP_SEED)
     'r18_k5_v2_2x64': ('resnet18', 5, 2, 64, 64, 128, dict(fs_version=2)),
+    # ResNeXt: grouped 3x3 (32 groups x 4 channels) in every bottleneck (_resnets.py:80-84,291-300)
+    'rx50_k5_1x64': ('resnext50_32x4d', 5, 1, 64, 64, 128),
 }
 DROP_SEED = 20240
 

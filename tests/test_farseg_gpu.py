@@ -65,7 +65,9 @@ CASES = [('resnet18', 5, 128, 2, 128, 128), ('resnet50', 15, 256, 2, 128, 128), 
          # hyperspectral-style high-channel stem (BASELINE configs[4] shape class): 200 input channels, ragged tile
          ('resnet18', 5, 128, 1, 96, 160, dict(in_channels=200)),
          # deep-stem ResNet-50 v1c (three 3x3 convs, _resnets.py:137-147); real-reference fixture r50v1c_k5_1x64.pt
-         ('resnet50_v1c', 5, 128, 2, 128, 128)]
+         ('resnet50_v1c', 5, 128, 2, 128, 128),
+         # ResNeXt-50 32x4d (grouped 3x3, _resnets.py:291-300); real-reference fixture rx50_k5_1x64.pt
+         ('resnext50_32x4d', 5, 128, 2, 128, 128)]
 
 
 @pytest.mark.parametrize('case', CASES)
@@ -598,3 +600,55 @@ def test_step_loop_checkpoint_resume_is_bit_identical(tmp_path):
     opt = torch.optim.SGD(b.parameters(), lr=0.5, momentum=0.9, weight_decay=1e-4)
     opt.load_state_dict(ck['opt'])
     assert abs(opt.param_groups[0]['lr'] - lb.lr) < 1e-15 and len(opt.state) == len(list(b.parameters()))
+
+
+GOLDEN = ['r18_k5_2x64', 'r50_k15_1x64', 'r18_k1_2x64', 'r18_k5_c8_shared_2x64', 'r50v1c_k5_1x64', 'r18_k5_v2_2x64',
+          'rx50_k5_1x64']
+
+
+@pytest.mark.parametrize('name', GOLDEN)
+def test_engine_against_real_reference_fixture(name):
+    """the CUDA path against the committed outputs of the UNMODIFIED reference (tests/golden/*.pt, generated by
+    make_golden.py from /root/reference in fp32 on the CPU): same seeded weights and tile.  The fixtures are 64 x 64 tiles
+    (BatchNorm sees 4-8 samples per channel at c5), so a bf16 run is compared at bf16-of-a-deep-network gates: training
+    losses 5e-2 relative (measured: <= 1.8e-2), eval-mode probabilities after that one training forward 1.5e-2 mean absolute
+    and >= 97 % identical mask pixels (measured on the ResNet-18 fixtures: <= 7e-3, >= 98 %)."""
+    from ever_b200.module import FarSegB200
+    from oracle.farseg_oracle import FarSegOracle, deterministic_fill, synthetic_batch
+    g = torch.load(os.path.join(os.path.dirname(__file__), 'golden', name + '.pt'), weights_only=False)
+    resnet, k, n, h, w, dec = g['case'][:6]
+    opts = g['case'][6] if len(g['case']) > 6 else {}
+    ora = deterministic_fill(FarSegOracle(resnet, k, dec, **opts), 0)
+    mine = FarSegB200(dict(encoder=dict(resnet_type=resnet, in_channels=opts.get('in_channels', 3)),
+                           head=dict(fs_relation=dict(scale_aware_proj=opts.get('scale_aware_proj', True),
+                                                      version=opts.get('fs_version', 1)),
+                                     fpn_decoder=dict(out_channels=dec, classifier_config=dict(num_classes=k)))))
+    mine.load_state_dict(ora.state_dict(), strict=True)
+    mine = mine.cuda()
+    x, y = synthetic_batch(n, h, w, max(k, 2), in_channels=opts.get('in_channels', 3))
+    x, y = x.cuda(), y.cuda()
+    # same order as make_golden.run_case: one training forward (BatchNorm running statistics move once), then eval
+    mine.train()
+    torch.manual_seed(20240)   # make_golden.DROP_SEED (FSRelationV2's Dropout2d)
+    losses = mine(x, dict(cls=y))
+    losses = {kk: float(v.detach()) for kk, v in losses.items()}
+    mine.eval()
+    with torch.no_grad():
+        prob = mine(x).float().cpu()
+    mask = prob.argmax(dim=1).to(torch.uint8) if k > 1 else (prob > 0.5).to(torch.uint8)
+    rep = dict(case=name, prob_max_abs=float((prob[:, :, ::4, ::4] - g['eval_prob_slice']).abs().max()),
+               prob_mean_abs=float((prob[:, :, ::4, ::4] - g['eval_prob_slice']).abs().mean()),
+               mask_agree=float((mask == g['eval_mask']).float().mean()))
+    rep['losses'] = {kk: (v, g['losses'][kk]) for kk, v in losses.items() if kk in g['losses']}
+    os.makedirs('gpurun_out', exist_ok=True)
+    json.dump(rep, open('gpurun_out/golden_%s.json' % name, 'w'), indent=1)
+    print(json.dumps(rep))
+    assert set(g['losses']) <= set(losses)
+    # eval gates only where the fixture is conditioned well enough to carry one: the ResNet-18 cases (N = 2).  The 1 x 64 x 64
+    # ResNet-50-class fixtures normalise c5 with FOUR samples per channel after one momentum update -- the reference's own
+    # bf16-autocast run agrees with its fp32 mask on only 78-91 % of those pixels -- and the binary fixture's eval output is
+    # softmax over one channel (all ones); their numbers are recorded in gpurun_out/ without a gate.
+    if name.startswith('r18') and k > 1:
+        assert rep['prob_mean_abs'] <= 1.5e-2 and rep['mask_agree'] >= 0.97, rep
+    for kk, (got, want) in rep['losses'].items():   # V2: the CUDA generator drops other channels than the CPU one; the losses
+        assert abs(got - want) <= 5e-2 * max(abs(want), 1e-3), rep   # still agree at this gate

@@ -47,6 +47,7 @@ def test_sass_has_tcgen05_and_tma():
 @pytest.mark.parametrize('resnet,k,dec,opts', [('resnet18', 5, 128, {}), ('resnet50', 15, 256, {}), ('resnet101', 7, 256, {}),
                                                ('resnet18', 5, 128, dict(in_channels=8, scale_aware_proj=False)),
                                                ('resnet50_v1c', 5, 128, {}),
+                                               ('resnext50_32x4d', 5, 128, {}), ('resnext101_32x8d', 5, 128, {}),
                                                # FSRelationV2 (per-level and shared), keys as ever/module/fs_relation.py:76-139
                                                ('resnet18', 5, 128, dict(fs_version=2)),
                                                ('resnet18', 5, 128, dict(fs_version=2, scale_aware_proj=False))])

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 from oracle.farseg_oracle import (FarSegOracle, bce_loss_oracle, deterministic_fill, dice_loss_oracle,
                                   synthetic_batch)
 
-CASES = ['r18_k5_2x64', 'r50_k15_1x64', 'r18_k1_2x64', 'r18_k5_c8_shared_2x64', 'r50v1c_k5_1x64', 'r18_k5_v2_2x64']
+CASES = ['r18_k5_2x64', 'r50_k15_1x64', 'r18_k1_2x64', 'r18_k5_c8_shared_2x64', 'r50v1c_k5_1x64', 'r18_k5_v2_2x64', 'rx50_k5_1x64']
 DROP_SEED = 20240   # tests/golden/make_golden.py
 
 
@@ -57,7 +57,7 @@ def test_oracle_matches_golden(name, golden_dir):
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/ever'), reason='reference tree only exists in the build container')
-@pytest.mark.parametrize('name', ['r18_k5_2x64', 'r18_k5_c8_shared_2x64', 'r50v1c_k5_1x64', 'r18_k5_v2_2x64'])
+@pytest.mark.parametrize('name', ['r18_k5_2x64', 'r18_k5_c8_shared_2x64', 'r50v1c_k5_1x64', 'r18_k5_v2_2x64', 'rx50_k5_1x64'])
 def test_oracle_bit_exact_vs_reference(name, golden_dir):
     for p_ in ('/root/reference', os.path.join(golden_dir, '_stubs'), golden_dir):
         if p_ not in sys.path:

@@ -117,6 +117,8 @@ CASES = [
     ('resnet50', 7, 256, 2, 256, 256, dict(fs_version=2)),
     # nn.Dropout on the merged decoder features (classifier_config.dropout_rate, ever/module/fpn.py:175-176,190), same seed
     ('resnet18', 5, 128, 2, 128, 128, dict(classifier_dropout=0.3)),
+    # ResNeXt: grouped 3x3 (32 groups) in every bottleneck (ever/module/_resnets.py:80-84,291-300), dense block-diagonal on the GPU
+    ('resnext50_32x4d', 5, 128, 2, 256, 256, {}),
 ]
 DROP_SEED = 4242
 

@@ -27,7 +27,7 @@ def lib():
 
 
 # kernels launched per C-ABI call (lower bounds; evb_conv2d_dgrad stride 2 launches up to 4)
-_KERNELS = {'evb_conv2d_wgrad': 2, 'evb_conv2d_wgrad(stem)': 2, 'evb_bn_stats': 2, 'evb_bn_bwd': 3, 'evb_bias_grad': 2,
+_KERNELS = {'evb_zero_bytes': 0, 'evb_conv2d_wgrad': 2, 'evb_conv2d_wgrad(stem)': 2, 'evb_bn_stats': 2, 'evb_bn_bwd': 3, 'evb_bias_grad': 2,
             'evb_loss_stats': 2, 'evb_linear_bwd': 2, 'evb_grad_norm': 2, 'evb_relation_bwd': 2, 'evb_bilinear_up_bwd_sep': 2}
 launches = [0]
 

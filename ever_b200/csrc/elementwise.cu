@@ -1499,6 +1499,12 @@ extern "C" int evb_pack_weights_tiled(const void* desc, const void* block_map, i
 }
 // blocks [block0, block0 + nblocks) of the same table: lets the caller pack the first layers' weights on the main stream
 // and the rest on a second stream that overlaps the start of the forward pass
+// zero-fill as a memset node (no kernel): gradient buffers whose first writer accumulates
+extern "C" int evb_zero_bytes(void* dst, long long nbytes, void* stream) {
+  if (nbytes < 0) return EVB_ERR_ARG;
+  if (nbytes == 0) return EVB_OK;
+  return cudaMemsetAsync(dst, 0, (size_t)nbytes, ST) == cudaSuccess ? EVB_OK : EVB_ERR_CUDA;
+}
 extern "C" int evb_copy2d_f32(const float* src, int lds, float* dst, int ldd, int rows, int cols, int accumulate,
                               void* stream) {
   copy2d_kernel<<<ew_blocks((long long)rows * cols, kEwThreads), kEwThreads, 0, ST>>>(src, lds, dst, ldd, rows, cols,

@@ -488,6 +488,12 @@ class FarSegEngine:
     def _new(self, *shape, dtype=BF16):
         return torch.empty(shape, dtype=dtype, device=self.dev)
 
+    def _zero(self, t):
+        """t[:] = 0 on the current stream as a memset (a memset node of the captured step, not a fill kernel)"""
+        assert t.is_contiguous()
+        check(self.L.evb_zero_bytes(ptr(t), c_ll(t.numel() * t.element_size()), stream()), 'evb_zero_bytes')
+        return t
+
     # ------------------------------------------------------------------ ops (forward + tape)
     def _grad_into(self, act, shape=None):
         """Return (buffer, accumulate_flag) for writing a gradient contribution of `act`."""
@@ -581,7 +587,7 @@ class FarSegEngine:
                     self._wgrad(cp, x.data, dy, n, h, w, cin, cout, stride)
                     if bias and bias_grad_zero and self._g(cp.bias) is not None:
                         if not (self.accumulate or cp._gw):
-                            self._g(cp.bias).zero_()
+                            self._zero(self._g(cp.bias))
                     elif bias:
                         self._bias_grad(cp, dy, n * ho * wo, cout)
                     cp._gw = True
@@ -1104,7 +1110,7 @@ class FarSegEngine:
             def gap_bwd():
                 g, acc = self._grad_into(c5)
                 if not acc:
-                    g.zero_()
+                    self._zero(g)
                 ds = holder['dscenes']
                 for d in ds[1:]:     # d(scene) of the other scene MLPs, summed in level order (deterministic)
                     check(L.evb_copy2d_f32(ptr(d), c_int(cc5), ptr(ds[0]), c_int(cc5), c_int(n), c_int(cc5), c_int(1),
@@ -1357,7 +1363,7 @@ class FarSegEngine:
                                   c_int(self.ignore_index), ptr(g['coef']), ptr(dlogits), stream()), 'evb_loss_grad')
             if self.tf is not None and g.get('name'):
                 self.tf('bwd', g['name'], dlogits)
-            cls.grad = torch.zeros_like(cls.data)   # padding channels 16..63 stay zero
+            cls.grad = self._zero(torch.empty_like(cls.data))   # padding channels 16..63 stay zero
             cls.has_grad = True
             if f == 1:
                 check(L.evb_copy2d_bf16(ptr(dlogits), c_int(ld), ptr(cls.grad), c_int(64), c_ll(n * hh * ww), c_int(ld),
@@ -1658,7 +1664,7 @@ class ChangeStarEngine(FarSegEngine):
         """views of the t1 / t2 halves of the feature batch; their gradients land in the halves of one buffer"""
         f1, f2 = Act(merged.data[:n]), Act(merged.data[n:])
         if train:
-            g = torch.zeros_like(merged.data)
+            g = self._zero(torch.empty_like(merged.data))
             f1.grad, f2.grad = g[:n], g[n:]
 
             def bwd():

@@ -152,6 +152,8 @@ int evb_scale_add(const void* x, float alpha, const void* z, void* y, long long 
 int evb_gap_fwd(const void* x, float* out, int N, int HW, int C, void* stream);
 int evb_gap_bwd(const float* dscene, void* dx, int N, int HW, int C, void* stream);
 int evb_copy2d_f32(const float* src, int lds, float* dst, int ldd, int rows, int cols, int accumulate, void* stream);
+/* dst[0:nbytes] = 0 on the stream (cudaMemsetAsync: a memset node in a captured step, not a kernel) */
+int evb_zero_bytes(void* dst, long long nbytes, void* stream);
 
 /* ---- FS-Relation (FSRelation.forward, ever/module/fs_relation.py:57-73) and the scene-embedding MLP (:22-28) */
 int evb_relation_fwd(const void* u1, const void* u2, const float* scale1, const float* shift1, const float* scale2,

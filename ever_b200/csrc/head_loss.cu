@@ -450,7 +450,8 @@ __global__ void loss_finalize_kernel(const float* __restrict__ stats, const floa
                                      float* __restrict__ losses, float* __restrict__ coef) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float nvalid = stats[1];
-  losses[0] = nvalid > 0.f ? stats[0] / nvalid : 0.f;
+  // no valid pixel: 0 / 0 = NaN like F.cross_entropy's mean over an empty selection (its gradient is zero, not NaN)
+  losses[0] = stats[0] / nvalid;
   coef[0] = nvalid > 0.f ? ce_weight / nvalid : 0.f;
   float coeff_sum = 0.f;
   for (int c = 0; c < K; ++c) {

@@ -616,6 +616,12 @@ class FarSegEngine:
         stats = self._new(4, c, dtype=torch.float32)
         mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
         sync = bp.sync and self.world > 1 and train and bn.training
+        if train and bn.training and x.data.numel() // c <= 1 and not sync:
+            # F.batch_norm's own check (torch/nn/functional.py _verify_batch_size): the reference fails the same way on a
+            # 1 x 32 x 32 tile, whose c5 is a single pixel
+            n_, h_, w_, _ = x.data.shape
+            raise ValueError('Expected more than 1 value per channel when training, got input size %s'
+                             % str(torch.Size([n_, bp.c_real, h_, w_])))
         if sync and x.stats is None:
             raise NotImplementedError('SyncBatchNorm behind a convolution with a fused add (no epilogue statistics)')
         if sync:

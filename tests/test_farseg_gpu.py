@@ -602,6 +602,40 @@ def test_step_loop_checkpoint_resume_is_bit_identical(tmp_path):
     assert abs(opt.param_groups[0]['lr'] - lb.lr) < 1e-15 and len(opt.state) == len(list(b.parameters()))
 
 
+@pytest.mark.parametrize('n,h,w', [(1, 32, 32), (2, 32, 64), (1, 64, 32)])
+def test_smallest_tiles(n, h, w):
+    """the smallest tile the /32 pyramid admits (c5 is 1 x 1 or 1 x 2: BatchNorm over one or two samples per channel, bilinear
+    up-sampling from a single pixel, TMA boxes larger than the image): losses against the oracle's bf16 run, finite
+    gradients everywhere, graph replay == eager"""
+    from oracle.farseg_oracle import synthetic_batch
+    ora, mine = _build('resnet18', 5, 128)
+    x, y = synthetic_batch(n, h, w, 5)
+    x, y = x.cuda(), y.cuda()
+    ora, mine = ora.cuda(), mine.cuda()
+    mine.train()
+    if n * (h // 32) * (w // 32) == 1:   # one value per channel at c5: torch's batch_norm refuses, and so does the engine
+        with pytest.raises(ValueError, match='Expected more than 1 value per channel'):
+            _oracle_step(ora, x, y, autocast=True)
+        with pytest.raises(ValueError, match='Expected more than 1 value per channel'):
+            mine(x, dict(cls=y))
+        return
+    _, want, _ = _oracle_step(ora, x, y, autocast=True)
+    out = mine(x, dict(cls=y))
+    mine.backward(out, None, None)
+    got = {kk: float(v.detach()) for kk, v in out.items()}
+    for kk, v in want.items():
+        assert abs(got[kk] - v) <= 3e-2 * max(abs(v), 1e-3), (kk, got[kk], v)
+    flat = mine.engine.flat_g
+    assert torch.isfinite(flat).all() and float(flat.abs().max()) > 0
+    mine.config.cuda_graph = True
+    g1 = flat.clone()
+    out2 = mine(x, dict(cls=y))
+    mine.backward(out2, None, None)
+    torch.cuda.synchronize()
+    assert {kk: float(v.detach()) for kk, v in out2.items()} == got
+    assert torch.equal(mine.engine.flat_g, g1)
+
+
 GOLDEN = ['r18_k5_2x64', 'r50_k15_1x64', 'r18_k1_2x64', 'r18_k5_c8_shared_2x64', 'r50v1c_k5_1x64', 'r18_k5_v2_2x64',
           'rx50_k5_1x64']
 

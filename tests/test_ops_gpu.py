@@ -247,6 +247,51 @@ def test_loss(k):
     assert float(dl[..., k:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize('mode', ['none_ignored', 'all_ignored', 'class_absent', 'ragged'])
+def test_loss_edge_cases(mode):
+    """edge cases of CE(ignore_index=255) + Dice (ever/module/loss.py:26-75) with the reference's own behaviour as the
+    expected value: no ignored pixel; EVERY pixel ignored (F.cross_entropy is 0/0 = nan there while its gradient is zero, the
+    Dice term sees empty selections and is 0); a class that never occurs; a pixel count that is not a multiple of the
+    kernel's block"""
+    L, check, ptr, stream = _L()
+    g = _gen(17)
+    k = 5
+    n, h, w = (1, 37, 53) if mode == 'ragged' else (2, 32, 48)
+    npx = n * h * w
+    logits = torch.zeros(n, h, w, 16, device='cuda', dtype=torch.bfloat16)
+    logits[..., :k] = torch.randn(n, h, w, k, device='cuda', generator=g).bfloat16()
+    labels = torch.randint(0, k - 1 if mode == 'class_absent' else k, (n, h, w), device='cuda', generator=g)
+    if mode == 'all_ignored':
+        labels.fill_(255)
+    elif mode != 'none_ignored':
+        labels[torch.rand(n, h, w, device='cuda', generator=g) < 0.2] = 255
+    stats = torch.empty(2 + 3 * k, device='cuda')
+    ws = torch.empty(L.evb_loss_workspace(c_ll(npx), c_int(k)) // 4, device='cuda')
+    losses, coef = torch.empty(2, device='cuda'), torch.empty(1 + 2 * k, device='cuda')
+    dl = torch.empty_like(logits)
+    check(L.evb_loss_stats(ptr(logits), ptr(labels), c_ll(npx), c_int(k), c_int(16), c_int(255), ptr(stats), ptr(ws),
+                           stream()), 'ls')
+    check(L.evb_loss_finalize(ptr(stats), None, c_int(k), c_float(1.0), c_float(1.0), c_float(1.0), c_float(1.0),
+                              ptr(losses), ptr(coef), stream()), 'lf')
+    check(L.evb_loss_grad(ptr(logits), ptr(labels), c_ll(npx), c_int(k), c_int(16), c_int(255), ptr(coef), ptr(dl),
+                          stream()), 'lg')
+    torch.cuda.synchronize()
+    from oracle.farseg_oracle import dice_loss_oracle
+    lr = logits[..., :k].float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    ce = F.cross_entropy(lr, labels, ignore_index=255)
+    dice = dice_loss_oracle(lr, labels)
+    (ce + dice).backward()
+    if mode == 'all_ignored':
+        assert torch.isnan(ce) and torch.isnan(losses[0])           # the reference's 0 / 0
+        assert float(dice) == 0.0 and float(losses[1]) == 0.0
+        assert float(lr.grad.abs().max()) == 0.0 and float(dl.float().abs().max()) == 0.0   # and a ZERO gradient
+        return
+    assert abs(float(losses[0]) - float(ce)) < 1e-4 * abs(float(ce))
+    assert abs(float(losses[1]) - float(dice)) < 1e-4 * abs(float(dice))
+    assert _rel(dl[..., :k].float(), nhwc(lr.grad)) < 8e-3
+    assert float(dl[..., k:].abs().max()) == 0.0
+
+
 def test_pack_im2col_sgd():
     L, check, ptr, stream = _L()
     g = _gen(8)

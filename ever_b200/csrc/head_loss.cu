@@ -275,12 +275,22 @@ loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restric
   // KT > 0: K is a compile-time constant (arrays stay in registers); KT == 0: generic K <= KMAX (16 / 32 / 64)
   const int K = KT > 0 ? KT : Krt;
   constexpr int KA = KT > 0 ? KT : KMAX;
+  // BINS (statistics pass, K <= 16): the two per-class sums only the pixel's OWN class contributes to (I_c = sum p_t, and
+  // the class histogram) go to a private shared-memory column per thread, indexed by the label -- one read-modify-write
+  // each instead of K compare + select + add chains (the pass was instruction-bound: ~700 SASS instructions per pixel);
+  // bank = thread id, so no conflicts; fixed-order reduction below, so the sums stay deterministic.
+  constexpr bool BINS = PASS == 0 && KA <= 16;
   __shared__ float red[8][2 + 3 * KA];
+  __shared__ float bins[BINS ? 2 * KA : 1][BINS ? 256 : 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float acc[2 + 3 * KA];
   if (PASS == 0) {
 #pragma unroll
     for (int i = 0; i < 2 + 3 * KA; ++i) acc[i] = 0.f;
+    if (BINS) {
+#pragma unroll
+      for (int i = 0; i < 2 * KA; ++i) bins[i][threadIdx.x] = 0.f;
+    }
   }
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
     const long long t = labels[p];
@@ -306,7 +316,21 @@ loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restric
     for (int c = 0; c < K; ++c) { e[c] = __expf(z[c] - mx); se += e[c]; }
     const float lse = mx + logf(se);
     const float inv_se = 1.f / se;
-    if (PASS == 0) {
+    if (PASS == 0 && BINS) {
+      if (valid) {
+        const int ti = (int)t;
+        const bool in_range = ti >= 0 && ti < K;   // a label outside [0, K) matches no class (the reference asserts)
+        const float zt = in_range ? __bfloat162float(row[in_range ? ti : 0]) : 0.f;   // same bf16 value as z[t] (L1 hit)
+        acc[0] += lse - zt;
+        acc[1] += 1.f;
+#pragma unroll
+        for (int c = 0; c < K; ++c) acc[2 + K + c] += e[c] * inv_se;
+        if (in_range) {
+          bins[ti][threadIdx.x] += __expf(zt - mx) * inv_se;   // == e[t] * inv_se bit for bit
+          bins[KA + ti][threadIdx.x] += 1.f;
+        }
+      }
+    } else if (PASS == 0) {
       if (valid) {
         float zt = 0.f;
 #pragma unroll
@@ -361,6 +385,18 @@ loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restric
   }
   if (PASS == 0) {
     const int n = 2 + 3 * K;
+    if (BINS) {
+      __syncthreads();
+      // class c (I_c) and KA + c (histogram): 256 thread columns summed in a fixed order by one warp each
+      for (int b = wid; b < 2 * KA; b += 8) {
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v += bins[b][lane + 32 * j];
+        v = warp_sum(v);
+        const int c = b < KA ? b : b - KA;
+        if (lane == 0 && c < K) partial[(long long)blockIdx.x * n + (b < KA ? 2 + c : 2 + 2 * K + c)] = v;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 2 + 3 * KA; ++i) {   // no early break: keeps the indices static so acc[] stays in registers
       if (i < n) {
@@ -370,6 +406,7 @@ loss_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restric
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      if (BINS && i >= 2 && (i < 2 + K || i >= 2 + 2 * K)) continue;   // written from the bins above
       float s = 0.f;
       for (int w = 0; w < 8; ++w) s += red[w][i];
       partial[(long long)blockIdx.x * n + i] = s;

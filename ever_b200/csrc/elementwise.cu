@@ -742,6 +742,53 @@ bilinear_bwd_x_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ 
     dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
 }
+// Row-staged pass X: one block per output row (n, oy) and chunk of <= 8 channel groups.  The row of dy is read ONCE,
+// coalesced, into shared memory; every (ix, group) output then gathers its taps from there in the same order as
+// bilinear_bwd_x_kernel (bit-identical sums).  The gather version re-read every dy vector ~2x through L1 with ~11 dependent
+// candidate taps per output (67 us for the x4 logit gradient of the C2 step, against ~15 us of HBM time).
+__global__ void __launch_bounds__(kEwThreads)
+bilinear_bwd_x_row_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ tmp, int w, int C, int lddy, int f,
+                          int ncg) {
+  extern __shared__ __align__(16) unsigned char bwdx_sm[];
+  bf16x8* sh = reinterpret_cast<bf16x8*>(bwdx_sm);   // [Wo][ncg]
+  const int cg = C / 8, Wo = w * f;
+  const long long p = blockIdx.x;                    // n * Ho + oy
+  const int g0 = blockIdx.y * ncg;
+  const int ng = min(ncg, cg - g0);
+  const __nv_bfloat16* row = dy + p * Wo * lddy + g0 * 8;
+  for (int v = threadIdx.x; v < Wo * ng; v += blockDim.x) {
+    const int ox = v / ng, g = v - ox * ng;
+    sh[ox * ncg + g] = *reinterpret_cast<const bf16x8*>(row + (long long)ox * lddy + g * 8);
+  }
+  __syncthreads();
+  const float sx = Wo > 1 ? (float)(w - 1) / (float)(Wo - 1) : 0.f;
+  const float inv_sx = sx > 0.f ? 1.f / sx : 0.f;
+  for (int v = threadIdx.x; v < w * ng; v += blockDim.x) {
+    const int ix = v / ng, g = v - ix * ng;
+    int xlo = 0, xhi = Wo - 1;
+    if (sx > 0.f) { xlo = max(0, (int)floorf((ix - 1) * inv_sx) - 1); xhi = min(Wo - 1, (int)ceilf((ix + 1) * inv_sx) + 1); }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int ox = xlo; ox <= xhi; ++ox) {
+      const float fx = sx * ox;
+      const int x0 = (int)fx;
+      const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+      const float lx = fx - x0;
+      float wx = 0.f;
+      if (x0 == ix) wx += 1.f - lx;
+      if (x1 == ix) wx += lx;
+      if (wx == 0.f) continue;
+      float gv[8];
+      unpack8(sh[ox * ncg + g], gv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += wx * gv[j];
+    }
+    float4* dst = reinterpret_cast<float4*>(tmp + ((p * w + ix) * cg + g0 + g) * 8);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
 __global__ void __launch_bounds__(kEwThreads)
 bilinear_bwd_y_kernel(const float* __restrict__ tmp, __nv_bfloat16* __restrict__ dx, int N, int h, int w, int C, int lddx,
                       int f) {
@@ -1312,8 +1359,19 @@ extern "C" int evb_bilinear_up_bwd_sep(const void* dy, void* dx, int N, int h, i
   if (C % 8 || lddx % 8 || lddy % 8 || f < 1 || f > 4) return EVB_ERR_ARG;
   if (ws_bytes < evb_bilinear_up_bwd_workspace(N, h, w, C, f)) return EVB_ERR_ARG;
   const long long t1 = (long long)N * h * f * w * (C / 8), t2 = (long long)N * h * w * (C / 8);
-  bilinear_bwd_x_kernel<<<ew_blocks(t1, kEwThreads * 2), kEwThreads, 0, ST>>>((const __nv_bfloat16*)dy, (float*)ws, N, h, w, C,
-                                                                            lddy, f);
+  const int Wo = w * f, cg = C / 8;
+  // narrow rows (the logit gradient: <= 64 channels) go through the row-staged kernel (x4 at 8x512^2: 81 -> 47 us for both
+  // passes); for the 256-channel decoder maps the gather kernel is as fast (its taps hit L1) and stays
+  if (cg <= 8 && Wo <= 3072 && (long long)N * h * f < (1LL << 31)) {   // row of dy staged in <= 48 KB of shared memory
+    int ncg = 3072 / Wo;
+    if (ncg > 8) ncg = 8;
+    if (ncg > cg) ncg = cg;
+    bilinear_bwd_x_row_kernel<<<dim3((unsigned)(N * h * f), (unsigned)((cg + ncg - 1) / ncg)), kEwThreads,
+                                (size_t)Wo * ncg * 16, ST>>>((const __nv_bfloat16*)dy, (float*)ws, w, C, lddy, f, ncg);
+  } else {
+    bilinear_bwd_x_kernel<<<ew_blocks(t1, kEwThreads * 2), kEwThreads, 0, ST>>>((const __nv_bfloat16*)dy, (float*)ws, N, h, w,
+                                                                              C, lddy, f);
+  }
   bilinear_bwd_y_kernel<<<ew_blocks(t2, kEwThreads), kEwThreads, 0, ST>>>((const float*)ws, (__nv_bfloat16*)dx, N, h, w, C, lddx,
                                                                         f);
   return LAUNCH_OK();

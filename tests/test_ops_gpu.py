@@ -367,6 +367,36 @@ def test_loss_binary():
     assert float(dl[..., 1:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize('cin,ks,stride,pad,hw', [(3, 7, 2, 3, (96, 304)), (3, 3, 2, 1, (64, 260)), (8, 7, 2, 3, (32, 130)),
+                                                   (3, 7, 2, 3, (512, 512)), (16, 7, 2, 3, (32, 64))])
+def test_im2col_windows_bit_exact(cin, ks, stride, pad, hw):
+    """im2col of the stem windows (7x7 s2 p3, deep-stem 3x3 s2 p1) from float NCHW and from uint8 HWC pixels == F.unfold of
+    the (normalised) image, bit for bit: ragged widths, full-size tiles, Cin = 3 / 8 / 16"""
+    L, check, ptr, stream = _L()
+    g = _gen(31)
+    n, (h, w) = 2, hw
+    k = cin * ks * ks
+    kp = (k + 63) // 64 * 64
+    x = torch.randn(n, cin, h, w, device='cuda', generator=g)
+    a = torch.full((n, h // stride, w // stride, kp), 7.0, device='cuda', dtype=torch.bfloat16)
+    check(L.evb_im2col_nchw(ptr(x), ptr(a), c_int(n), c_int(cin), c_int(h), c_int(w), c_int(kp), c_int(ks), c_int(stride),
+                            c_int(pad), stream()), 'im2col')
+    torch.cuda.synchronize()
+    unf = F.unfold(x, ks, padding=pad, stride=stride).permute(0, 2, 1).bfloat16()
+    assert torch.equal(a[..., :k].reshape(n, -1, k), unf)
+    assert float(a[..., k:].abs().max()) == 0.0 if kp > k else True
+    img = torch.randint(0, 256, (n, h, w, cin), device='cuda', generator=g, dtype=torch.uint8)
+    mean = torch.linspace(90.0, 130.0, cin, device='cuda')
+    std = torch.linspace(50.0, 60.0, cin, device='cuda')
+    a.fill_(7.0)
+    check(L.evb_im2col_u8(ptr(img), ptr(mean), ptr(std), ptr(a), c_int(n), c_int(cin), c_int(h), c_int(w), c_int(kp),
+                          c_int(ks), c_int(stride), c_int(pad), stream()), 'im2col_u8')
+    torch.cuda.synchronize()
+    xf = img.permute(0, 3, 1, 2).float().sub(mean.view(1, cin, 1, 1)).div(std.view(1, cin, 1, 1))
+    unf = F.unfold(xf, ks, padding=pad, stride=stride).permute(0, 2, 1).bfloat16()
+    assert torch.equal(a[..., :k].reshape(n, -1, k), unf)
+
+
 def test_u8_input_pipeline_and_confusion_matrix():
     L, check, ptr, stream = _L()
     g = _gen(10)

@@ -308,3 +308,14 @@ def test_gradient_buckets_tile_the_arena_in_backward_order(splits):
     for lo, _ in e._segments():
         e._allreduce_bucket(lo)
     assert issued == b
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/ever'), reason='reference tree only exists in the build container')
+def test_backbone_names_equal_the_reference_registry():
+    """every `resnet_type` the reference's ResNetEncoder accepts (registry.MODEL.register calls of ever/module/resnet.py:26-34)
+    is a backbone of the plugin, and nothing else is"""
+    import re
+    from ever_b200.module import RESNETS
+    src = open('/root/reference/ever/module/resnet.py').read()
+    names = set(re.findall(r"registry\.MODEL\.register\('(res\w+)'", src))
+    assert names and names == set(RESNETS)

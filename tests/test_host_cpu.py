@@ -319,3 +319,13 @@ def test_backbone_names_equal_the_reference_registry():
     src = open('/root/reference/ever/module/resnet.py').read()
     names = set(re.findall(r"registry\.MODEL\.register\('(res\w+)'", src))
     assert names and names == set(RESNETS)
+
+
+def test_accounting_table_names_are_c_abi_entry_points():
+    """every rule of the step-accounting proxy (ever_b200/acct.py, bench.py's hbm_bytes_per_step / flops_per_step) is keyed by
+    a function include/evb200.h declares: a renamed entry point cannot silently drop out of the accounting"""
+    import re
+    from ever_b200.acct import TABLE
+    hdr = open(os.path.join(os.path.dirname(__file__), '..', 'include', 'evb200.h')).read()
+    declared = set(re.findall(r'\b(evb_\w+)\s*\(', hdr))
+    assert set(TABLE) <= declared, sorted(set(TABLE) - declared)

@@ -44,8 +44,9 @@ def _bn_apply(a):
 
 def _bn_bwd(a):
     m, c = _v(a[15]), _v(a[16])
-    passes = 4 + 1 + (2 if _v(a[2]) else 0) + ((2 if _v(a[11]) else 1) if _v(a[10]) else 0)
-    return 2 * m * c * passes, 0
+    ymask = (0.5 if _v(a[7]) == 3 else 2) if _v(a[2]) else 0     # mask_mode 3: uint32 per 8 channels = a quarter pass, twice
+    passes = 4 + 1 + ymask + ((2 if _v(a[11]) else 1) if _v(a[10]) else 0)
+    return int(2 * m * c * passes), 0
 
 
 def _rows_c(mi, ci, passes):
@@ -84,7 +85,8 @@ def _im2col(kp_i, elem):
 TABLE = {
     'evb_conv2d_fwd': _conv_fwd_add, 'evb_conv2d_fwd_stats': _conv_fwd, 'evb_conv2d_fwd_bias_stats': _conv_fwd,
     'evb_conv2d_dgrad': _conv_dgrad, 'evb_conv2d_wgrad': _conv_wgrad,
-    'evb_bn_apply': _bn_apply, 'evb_bn_bwd': _bn_bwd, 'evb_bn_stats': _rows_c(1, 2, 1),
+    'evb_bn_apply': _bn_apply,
+    'evb_bn_apply_mask': lambda a: (int(2 * _v(a[6]) * _v(a[7]) * 3.25), 0), 'evb_bn_bwd': _bn_bwd, 'evb_bn_stats': _rows_c(1, 2, 1),
     'evb_maxpool3x3s2_fwd': _maxpool_fwd, 'evb_maxpool3x3s2_bwd': _maxpool_bwd,
     'evb_bilinear_up': _bilinear, 'evb_bilinear_up_bwd_sep': _bilinear_bwd,
     'evb_relation_fwd': _rows_c(9, 11, 3), 'evb_relation_bwd': _rows_c(12, 14, 5),

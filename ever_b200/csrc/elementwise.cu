@@ -242,7 +242,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
 // ran at 46 % of the copy bandwidth, in-flight-limited).  MASK is a template parameter so unused constants are pruned.
 // ------------------------------------------------------------------------------------------------
 // BN backward reduction: per-channel sums of g = dy * mask and g * (x - mean) over M rows (rstd is applied by the finalize
-// kernel).  MASK 0: none; 1: ymask > 0; 2: recomputed bf16(x*scale+shift) > 0.  partial[which][C][kNbPadBwd], column = block.
+// kernel).  MASK 0: none; 1: ymask > 0; 2: recomputed bf16(x*scale+shift) > 0; 3: ymask is a uint32 per 8-channel vector, bit j = channel j survived the ReLU (written by bn_apply_ca<1>: a quarter of the bytes of re-reading the bf16 output).  partial[which][C][kNbPadBwd], column = block.
 constexpr int kNbPadBwd = 640;   // up to 4 reduce blocks per SM
 
 // finalize of bn_bwd_reduce_kernel: dbeta = sum g, dgamma = rstd * sum g (x - mean); fixed-order fp64 reduction
@@ -274,6 +274,9 @@ __global__ void bn_bwd_finalize2_kernel(const float* __restrict__ partial, int n
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -287,7 +290,7 @@ bn_bwd_reduce_ca_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
                         const __nv_bfloat16* __restrict__ ymask, const float* __restrict__ mean,
                         const float* __restrict__ scale, const float* __restrict__ shift, long long M, int C,
                         float* __restrict__ partial) {
-  constexpr int NT = MASK == 1 ? 3 : 2;   // tensors streamed
+  constexpr int NT = (MASK == 1 || MASK == 3) ? 3 : 2;   // tensors streamed
   constexpr int S = kCaStages;
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16x8* ring = reinterpret_cast<bf16x8*>(smraw);   // [S][NT][blockDim]
@@ -316,6 +319,7 @@ bn_bwd_reduce_ca_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
       cp_async16(slot, x + off);
       cp_async16(slot + nthr, dy + off);
       if (MASK == 1) cp_async16(slot + 2 * nthr, ymask + off);
+      if (MASK == 3) cp_async4(slot + 2 * nthr, reinterpret_cast<const unsigned*>(ymask) + off / 8);
     }
     cp_async_commit();
   };
@@ -336,6 +340,10 @@ bn_bwd_reduce_ca_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
     } else if (MASK == 2) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) gv[j] = bf16_round(xv[j] * sc[j] + sh[j]) > 0.f ? gv[j] : 0.f;
+    } else if (MASK == 3) {
+      const unsigned mb = *reinterpret_cast<const unsigned*>(slot + 2 * nthr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] = (mb >> j & 1u) ? gv[j] : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s0[j] += gv[j]; s1[j] += gv[j] * (xv[j] - mu[j]); }
@@ -365,7 +373,7 @@ bn_bwd_apply_ca_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
                        const float* __restrict__ dgamma, const float* __restrict__ dbeta, int frozen,
                        __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres, int dres_acc, unsigned nvec, int C,
                        float inv_m) {
-  constexpr int NT = MASK == 1 ? 3 : 2;
+  constexpr int NT = (MASK == 1 || MASK == 3) ? 3 : 2;
   constexpr int S = kCaStages;
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16x8* ring = reinterpret_cast<bf16x8*>(smraw);   // [S][NT][blockDim]
@@ -400,6 +408,7 @@ bn_bwd_apply_ca_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
       cp_async16(slot, gx + i);
       cp_async16(slot + nthr, gg + i);
       if (MASK == 1) cp_async16(slot + 2 * nthr, gy + i);
+      if (MASK == 3) cp_async4(slot + 2 * nthr, reinterpret_cast<const unsigned*>(ymask) + i);
     }
     cp_async_commit();
   };
@@ -421,6 +430,10 @@ bn_bwd_apply_ca_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
     } else if (MASK == 2) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] = bf16_round(xf[j] * a[j] + sh[j]) > 0.f ? g[j] : 0.f;
+    } else if (MASK == 3) {
+      const unsigned mb = *reinterpret_cast<const unsigned*>(slot + 2 * nthr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = (mb >> j & 1u) ? g[j] : 0.f;
     }
     if (dres) {
       float d[8];
@@ -446,7 +459,8 @@ bn_bwd_apply_ca_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
 template <int RES>
 __global__ void __launch_bounds__(kEwThreads)
 bn_apply_ca_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-                   const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, unsigned nvec, int C, int relu) {
+                   const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, unsigned nvec, int C, int relu,
+                   unsigned* __restrict__ mbits) {
   constexpr int NT = RES ? 2 : 1;
   constexpr int S = kCaStages;
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -493,7 +507,16 @@ bn_apply_ca_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
     }
-    reinterpret_cast<bf16x8*>(y)[i] = pack8(v);
+    const bf16x8 out = pack8(v);
+    reinterpret_cast<bf16x8*>(y)[i] = out;
+    if (RES && mbits) {   // survivors of the ReLU as the backward pass sees them: the ROUNDED output > 0
+      float r8[8];
+      unpack8(out, r8);
+      unsigned mb = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mb |= (r8[j] > 0.f ? 1u : 0u) << j;
+      mbits[i] = mb;
+    }
   }
   cp_async_wait<0>();
 }
@@ -1174,8 +1197,21 @@ extern "C" int evb_set_bn_reduce_blocks(int per_sm) {
   g_bn_blocks_per_sm = per_sm;
   return EVB_OK;
 }
+static int bn_apply_impl(const void* x, const float* scale, const float* shift, const void* res, void* y, void* mask32,
+                         long long M, int C, int relu, void* stream);
 extern "C" int evb_bn_apply(const void* x, const float* scale, const float* shift, const void* res, void* y, long long M,
                             int C, int relu, void* stream) {
+  return bn_apply_impl(x, scale, shift, res, y, nullptr, M, C, relu, stream);
+}
+// same with a residual operand, also writing the ReLU survivors as one uint32 per 8-channel vector (bit j = channel j of
+// the rounded output is > 0) for evb_bn_bwd(mask_mode = 3)
+extern "C" int evb_bn_apply_mask(const void* x, const float* scale, const float* shift, const void* res, void* y,
+                                 void* mask32, long long M, int C, void* stream) {
+  if (!res || !mask32) return EVB_ERR_ARG;
+  return bn_apply_impl(x, scale, shift, res, y, mask32, M, C, 1, stream);
+}
+static int bn_apply_impl(const void* x, const float* scale, const float* shift, const void* res, void* y, void* mask32,
+                         long long M, int C, int relu, void* stream) {
   if (C % 8) return EVB_ERR_ARG;
   if (C / 8 > kEwThreads) return EVB_ERR_ARG;
   if (M * C / 8 >= (1LL << 31) - (1LL << 24)) return EVB_ERR_ARG;   // vectors are indexed with 32 bits
@@ -1194,11 +1230,11 @@ extern "C" int evb_bn_apply(const void* x, const float* scale, const float* shif
     if (res)
       e = evb_launch_pdl_small(bn_apply_ca_kernel<1>, dim3(ew_blocks(nvec, bt * 8, 148 * 3)), dim3(bt),
                                (size_t)kCaStages * 2 * bt * 16, ST, (const __nv_bfloat16*)x, scale, shift,
-                               (const __nv_bfloat16*)res, (__nv_bfloat16*)y, (unsigned)nvec, C, relu);
+                               (const __nv_bfloat16*)res, (__nv_bfloat16*)y, (unsigned)nvec, C, relu, (unsigned*)mask32);
     else
       e = evb_launch_pdl_small(bn_apply_ca_kernel<0>, dim3(ew_blocks(nvec, bt * 8, 148 * 4)), dim3(bt),
                                (size_t)kCaStages * bt * 16, ST, (const __nv_bfloat16*)x, scale, shift,
-                               (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)y, (unsigned)nvec, C, relu);
+                               (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)y, (unsigned)nvec, C, relu, (unsigned*)nullptr);
     if (e != cudaSuccess) return EVB_ERR_CUDA;
     return LAUNCH_OK();
   }
@@ -1212,7 +1248,7 @@ static int launch_bn_bwd_ca(const void* dy, const void* x, const void* ymask, co
                             int phase = 0) {
   // phase 0: reduce + finalize + apply (BatchNorm).  1: reduce + finalize only (per-channel sums -> dgamma / dbeta).
   // 2: apply only, with explicit per-channel constants c2 = dgamma[], k0 = dbeta[] (frozen must be 2).
-  constexpr int NT = MASK == 1 ? 3 : 2;
+  constexpr int NT = (MASK == 1 || MASK == 3) ? 3 : 2;
   const int cg = C / 8;
   const int bt = (kEwThreads / cg) * cg;
   const int rows_par = bt / cg;
@@ -1256,10 +1292,11 @@ extern "C" int evb_bn_bwd(const void* dy, const void* x, const void* ymask, cons
                           const float* scale, const float* shift, int mask_mode, int frozen, void* dx, void* dres,
                           int dres_acc, float* dgamma, float* dbeta, int param_acc, long long M, int C, void* ws,
                           void* stream) {
-  if (C % 8 || C > 2048 || mask_mode < 0 || mask_mode > 2) return EVB_ERR_ARG;
+  if (C % 8 || C > 2048 || mask_mode < 0 || mask_mode > 3) return EVB_ERR_ARG;
   if (M * C / 8 >= (1LL << 31) - (1LL << 24)) return EVB_ERR_ARG;
   int rc;
-  if (mask_mode == 0) rc = launch_bn_bwd_ca<0>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
+  if (mask_mode == 3) rc = launch_bn_bwd_ca<3>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
+  else if (mask_mode == 0) rc = launch_bn_bwd_ca<0>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
   else if (mask_mode == 1) rc = launch_bn_bwd_ca<1>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
   else rc = launch_bn_bwd_ca<2>(dy, x, ymask, mean, rstd, scale, shift, frozen, dx, dres, dres_acc, dgamma, dbeta, param_acc, M, C, ws, ST);
   if (rc) return rc;

@@ -725,9 +725,18 @@ class FarSegEngine:
         fold = self._bn_fold(x, bp, train)
         y = Act(self._new(*x.data.shape))
         c = bp.c
-        check(L.evb_bn_apply(ptr(x.data), ptr(fold[2]), ptr(fold[3]), ptr(res.data if res is not None else None),
-                             ptr(y.data), c_ll(x.data.numel() // c), c_int(c), c_int(1 if relu else 0), stream()),
-              'evb_bn_apply')
+        # block tail relu(bn(x) + identity): the backward needs the ReLU survivors; one uint32 of bits per 8-channel vector
+        # (a quarter of y's bytes) is written here instead of re-reading y twice there.  Not under teacher forcing (the
+        # output is overwritten by the reference's tensor, whose mask must be used) nor for SyncBatchNorm's split backward.
+        bits = None
+        if train and relu and res is not None and self.tf is None and not (bp.sync and self.world > 1):
+            bits = self._new(x.data.numel() // 8, dtype=torch.int32)
+            check(L.evb_bn_apply_mask(ptr(x.data), ptr(fold[2]), ptr(fold[3]), ptr(res.data), ptr(y.data), ptr(bits),
+                                      c_ll(x.data.numel() // c), c_int(c), stream()), 'evb_bn_apply_mask')
+        else:
+            check(L.evb_bn_apply(ptr(x.data), ptr(fold[2]), ptr(fold[3]), ptr(res.data if res is not None else None),
+                                 ptr(y.data), c_ll(x.data.numel() // c), c_int(c), c_int(1 if relu else 0), stream()),
+                  'evb_bn_apply')
         self._tf_fwd(y, name)
         if train:
             def bwd():
@@ -736,6 +745,8 @@ class FarSegEngine:
                 self._tf_bwd(y)
                 if relu and res is None:   # mask recomputed from x: one tensor read less per pass
                     self._bn_backward(y.grad, x, bp, fold, 2, None, None)
+                elif bits is not None:
+                    self._bn_backward(y.grad, x, bp, fold, 3, bits, res)
                 else:
                     self._bn_backward(y.grad, x, bp, fold, 1 if relu else 0, y.data if relu else None, res)
             self.tape.append(bwd)

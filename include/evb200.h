@@ -103,7 +103,13 @@ int evb_bn_fold(const float* gamma, const float* beta, const float* rm, const fl
 /* y = act(bf16(x*scale+shift) [+ res]) */
 int evb_bn_apply(const void* x, const float* scale, const float* shift, const void* res, void* y, long long M, int C,
                  int relu, void* stream);
-/* backward of the above.  mask_mode 0 none | 1 (ymask>0) | 2 recomputed from x.  dres (+)= masked dy. */
+/* y = relu(bf16(x*scale+shift) + res), and mask32[v] (one uint32 per 8-channel vector v of y) = bit j set when channel j of
+ * the rounded output is > 0: the ReLU survivors for evb_bn_bwd(mask_mode = 3), a quarter of the bytes of re-reading y
+ * (Bottleneck / BasicBlock tail: out = relu(bn(conv(x)) + identity), ever/module/_resnets.py:64-69,105-112) */
+int evb_bn_apply_mask(const void* x, const float* scale, const float* shift, const void* res, void* y, void* mask32,
+                      long long M, int C, void* stream);
+/* backward of the above.  mask_mode 0 none | 1 (ymask>0) | 2 recomputed from x | 3 ymask = the uint32 bit masks of
+ * evb_bn_apply_mask.  dres (+)= masked dy. */
 /* grid cap of the BN backward reduction, blocks per SM (1..4, default 4) */
 int evb_set_bn_reduce_blocks(int per_sm);
 int evb_bn_bwd(const void* dy, const void* x, const void* ymask, const float* mean, const float* rstd, const float* scale,

@@ -242,7 +242,8 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_device():
                                   c_int(64), null, null, null) == ERR_ARG
     # BatchNorm: C % 8, mask mode, partial-column count
     assert L.evb_bn_apply(null, null, null, null, null, c_ll(16), c_int(12), c_int(1), null) == ERR_ARG
-    assert L.evb_bn_bwd(null, null, null, null, null, null, null, c_int(3), c_int(0), null, null, c_int(0), null, null,
+    assert L.evb_bn_apply_mask(null, null, null, null, null, null, c_ll(16), c_int(64), null) == ERR_ARG   # needs res + mask
+    assert L.evb_bn_bwd(null, null, null, null, null, null, null, c_int(4), c_int(0), null, null, c_int(0), null, null,
                         c_int(0), c_ll(16), c_int(64), null, null) == ERR_ARG
     assert L.evb_bn_finalize(null, c_int(0), c_ll(16), c_int(64), null, null, null, null, c_f(0.1), c_f(1e-5), null, null, null,
                              null, null) == ERR_ARG

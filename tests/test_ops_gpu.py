@@ -75,6 +75,22 @@ def test_bn_train_fwd_bwd(shape, mode):
     assert _rel(dgamma, gr.grad) < 1.5e-2 and _rel(dbeta, br.grad) < 1.5e-2
     if res is not None:
         assert _rel(dres.float(), nhwc(rr.grad)) < 1.5e-2
+        # bit-mask variant (block tail): same output, mask bits == (y > 0), and a backward that reads the bits instead of y
+        # gives the same dx / dres / dgamma / dbeta bit for bit
+        y2, bits = torch.empty_like(x), torch.empty(m_rows * c // 8, dtype=torch.int32, device='cuda')
+        check(L.evb_bn_apply_mask(ptr(x), ptr(st[2]), ptr(st[3]), ptr(res), ptr(y2), ptr(bits), c_ll(m_rows), c_int(c),
+                                  stream()), 'apply_mask')
+        dx2, dres2 = torch.empty_like(x), torch.empty_like(x)
+        dgamma2, dbeta2 = torch.empty(c, device='cuda'), torch.empty(c, device='cuda')
+        check(L.evb_bn_bwd(ptr(dy), ptr(x), ptr(bits), ptr(st[0]), ptr(st[1]), ptr(st[2]), ptr(st[3]), c_int(3), c_int(0),
+                           ptr(dx2), ptr(dres2), c_int(0), ptr(dgamma2), ptr(dbeta2), c_int(0), c_ll(m_rows), c_int(c),
+                           ptr(ws), stream()), 'bwd_bits')
+        torch.cuda.synchronize()
+        assert torch.equal(y2, y)
+        want = ((y.view(-1, 8) > 0).int() << torch.arange(8, device='cuda', dtype=torch.int32)).sum(dim=1, dtype=torch.int32)
+        assert torch.equal(bits, want)
+        assert torch.equal(dx2, dx) and torch.equal(dres2, dres)
+        assert torch.equal(dgamma2, dgamma) and torch.equal(dbeta2, dbeta)
 
 
 def test_maxpool():
